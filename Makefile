@@ -1,0 +1,14 @@
+# Builds libbsr.so (sm_100a only) and nothing else; `python -c "import __graft_entry__ as g; g.build()"` calls this.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+CSRC := blindshadowremoval_b200/csrc
+OUT  := blindshadowremoval_b200/libbsr.so
+HDRS := $(wildcard $(CSRC)/*.cuh) include/bsr.h
+
+$(OUT): $(CSRC)/bsr_api.cu $(HDRS)
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared -Xptxas -v \
+	    --expt-relaxed-constexpr -o $@ $(CSRC)/bsr_api.cu 2> build.log || (cat build.log; exit 1)
+	@grep -E "error|warning" build.log | grep -v "ptxas info" | head -20 || true
+
+clean:
+	rm -f $(OUT) build.log

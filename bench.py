@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the shadow-removal generator forward on B200 (see the repo brief).
+
+  python bench.py --gpus N --steps K --warmup W             our arm (libbsr.so, bf16 tcgen05 path)
+  python bench.py --impl reference ...                      the reference's algorithm on host cores
+                                                            (PyTorch-CPU restatement = oracle; TensorFlow
+                                                            is not installable in this image)
+One step = one forward of the GSC generator over `--batch` synthetic 256x256 face crops per GPU
+(weak scaling: every rank owns its own batch; no data-path collective).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GSC_GFLOP_PER_IMAGE = 18.10
+METRIC = "images/sec @ 256x256 crop (GSC generator forward)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--variant", default="gsc", choices=["gsc", "tsm"])
+    ap.add_argument("--frame", type=int, default=2)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32check"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="also print the per-layer roofline table to stderr")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per layer (per image): FLOPs = 2*MACs; bytes = unique in + out + weights (bf16
+# activations).  Same arithmetic as SURVEY 8d / App. B; used for the roofline object.
+def layer_work(variant):
+    c1, c2 = (99, 261) if variant == "gsc" else (291, 877)
+    w1, w2 = max(c1, 257), max(c2, 257)
+    L = {}
+
+    def conv(name, hw_out, k, cin, cout, in_hw=None, extra_bytes=0, out_bytes_per=2):
+        macs = hw_out * k * k * cin * cout
+        in_hw = in_hw or hw_out
+        L[name] = (2.0 * macs, in_hw * cin * 2 + hw_out * cout * out_bytes_per + k * k * cin * cout * 2 + extra_bytes)
+
+    def convt(name, hw_in, cin, cout):
+        macs = hw_in * 9 * cin * cout
+        L[name] = (2.0 * macs, hw_in * cin * 2 + 4 * hw_in * cout * 2 + 9 * cin * cout * 2)
+
+    conv("conv1", 65536, 7, 3, 32, extra_bytes=65536 * 3 * 2)        # fp32 input: 12 B/px instead of 6
+    conv("down1", 16384, 3, 32, 64, in_hw=65536)
+    conv("down2", 4096, 3, 64, 64, in_hw=16384)
+    conv("down3", 1024, 3, 64, 96, in_hw=4096)
+    for i in range(6):
+        cin = (c1 if i == 0 else w1) if i < 3 else (c2 if i == 3 else w2)
+        wide = w1 if i < 3 else w2
+        conv("res%d.conv1" % i, 1024, 1, cin, 128)
+        conv("res%d.conv2" % i, 1024, 3, 128, 128)
+        conv("res%d.conv3" % i, 1024, 1, 128, 257)
+        conv("res%d.qkv" % i, 1024, 1, 257, 384)
+        L["res%d.attention" % i] = (2.0 * 2 * 1024 * 1024 * 128, 1024 * 384 * 2 + 1024 * 128 * 2)
+        conv("res%d.w" % i, 1024, 1, 128, 257, extra_bytes=1024 * (257 + cin) * 2 + 1024 * (wide - 257) * 2)
+    convt("up1", 1024, w1, 96)
+    convt("up2", 4096, 160, 64)
+    convt("up3", 16384, 128, 64)
+    conv("heads", 65536, 7, 64, 2, out_bytes_per=4)
+    L["compose"] = (0.0, 65536 * (8 + 12 + 4 + 2))
+    convt("clr_up1", 1024, w2, 128)
+    convt("clr_up2", 4096, 128, 96)
+    convt("clr_up3", 16384, 96, 64)
+    conv("clr_conv1", 65536, 3, 65, 16)
+    L["clr_tail"] = (2.0 * 65536 * (256 + 48), 65536 * (32 + 12 + 12 + 4))
+    return L
+
+
+def sample_clocks(stop, out):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    idx = os.environ.get("LOCAL_RANK", "0")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", idx, "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.1)
+
+
+def clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    mhz = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+            "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": reasons,
+            "samples": len(samples)}
+
+
+def cpu_reference_rate(variant, frame, n_images, repeats=1):
+    """images/s of the oracle (reference restated in PyTorch CPU) with all host threads."""
+    import torch
+    from blindshadowremoval_b200.synthetic import make_inputs
+    from blindshadowremoval_b200.weights import random_weights
+    from oracle.generator_ref import generator_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = random_weights(variant, 1234)
+    d = make_inputs(n_images, 0, with_reg=(variant == "tsm"))
+    generator_forward(w, d["img"][:frame], d["uv"][:frame], d.get("reg", [None])[:frame] if variant == "tsm" else None,
+                      variant=variant, frame=frame)                      # warm-up
+    t0 = time.time()
+    for _ in range(repeats):
+        generator_forward(w, d["img"], d["uv"], d.get("reg"), variant=variant, frame=frame)
+    dt = time.time() - t0
+    return n_images * repeats / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 8 if args.variant == "gsc" else 4 * args.frame
+    times = []
+    import torch
+    from blindshadowremoval_b200.synthetic import make_inputs
+    from blindshadowremoval_b200.weights import random_weights
+    from oracle.generator_ref import generator_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = random_weights(args.variant, 1234)
+    d = make_inputs(n, 0, with_reg=(args.variant == "tsm"))
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    for i in range(warm + steps):
+        t0 = time.time()
+        generator_forward(w, d["img"], d["uv"], d.get("reg"), variant=args.variant, frame=args.frame)
+        if i >= warm:
+            times.append(time.time() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = n / (ms / 1e3)
+    sample = "%d synthetic %s images per step (bounded sample of the %d-image workload), %d timed steps" % (
+        n, args.variant.upper(), args.batch, steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample,
+                         "note": "reference restated in PyTorch CPU (TensorFlow unavailable in this image)"},
+        "e2e": {"value": round(value, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": "%s generator forward, %d synthetic 256x256 face crops per GPU per step, micro-batch %d, "
+                        "random-init weights seed 1234" % (args.variant.upper(), args.batch, args.micro_batch),
+            "variant": args.variant, "images_per_gpu_per_step": args.batch, "micro_batch": args.micro_batch,
+            "frame": args.frame if args.variant == "tsm" else None,
+            "cache": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" %
+                     (args.batch * 256 * 256 * 6 * 4 / 1e6)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from blindshadowremoval_b200.generator import Generator
+    from blindshadowremoval_b200.synthetic import make_inputs
+    from blindshadowremoval_b200.weights import random_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    tsm = args.variant == "tsm"
+    B = args.batch
+    if tsm:
+        B = B // args.frame * args.frame
+    w = random_weights(args.variant, 1234)
+    gen = Generator(args.variant, args.precision, device=local, micro_batch=args.micro_batch, weights=w)
+
+    # synthetic inputs: 32 distinct images tiled to the batch (generation cost only), resident in HBM
+    base = make_inputs(32, seed=rank, with_reg=tsm)
+    reps = (B + 31) // 32
+
+    def dev_t(a):
+        return torch.from_numpy(a).to(dev).repeat(reps, 1, 1, 1)[:B].contiguous()
+
+    img, uv = dev_t(base["img"]), dev_t(base["uv"])
+    reg = dev_t(base["reg"]) if tsm else None
+    want = ("con_rgb", "dif")          # what every inference caller keeps (train_test_GSC.py:871-873)
+
+    def step():
+        return gen(img, uv, reg, frame=args.frame if tsm else None, share=True, training=False, want=want)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop, samples), daemon=True)
+    th.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    stop.set()
+    th.join(timeout=2)
+    launches = gen.launch_count() * args.steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = B * world / (ms_step / 1e3)
+    checksum = float(out[1].float().mean().item())
+
+    # ---- e2e: same metric through the public host API (pinned host buffers, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        n_e = B
+        h_img = torch.from_numpy(base["img"]).repeat(reps, 1, 1, 1)[:n_e].contiguous().pin_memory()
+        h_uv = torch.from_numpy(base["uv"]).repeat(reps, 1, 1, 1)[:n_e].contiguous().pin_memory()
+        h_reg = torch.from_numpy(base["reg"]).repeat(reps, 1, 1, 1)[:n_e].contiguous().pin_memory() if tsm else None
+        h_rgb = torch.empty((n_e, 256, 256, 3)).pin_memory()
+        h_dif = torch.empty((n_e, 256, 256, 1)).pin_memory()
+
+        def host_step():
+            gen.forward_host_ptrs(h_img.data_ptr(), h_uv.data_ptr(), h_reg.data_ptr() if tsm else 0, n_e, args.frame,
+                                  True, 0, h_rgb.data_ptr(), 0, h_dif.data_ptr())
+
+        for _ in range(2):
+            host_step()
+        barrier()
+        k_e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e):
+            host_step()            # synchronises its stream before returning: results are on the host
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = n_e * 256 * 256 * (6 + (6 if tsm else 0)) * 4
+        d2h = n_e * 256 * 256 * 4 * 4
+        e2e = {"value": round(n_e * world * k_e / tt.item(), 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e,
+               "api": "Generator.__call__ host path -> bsr_forward_%s_host" % args.variant}
+
+    # ---- roofline of the dominant kernel: per-layer CUDA events on the launching stream (BSR_PROFILE handle)
+    roof, table = None, None
+    if rank == 0:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops_sustained": pk["bf16_tflops_sustained"], "src": "measured"}
+        except Exception:
+            pass
+        os.environ["BSR_PROFILE"] = "1"
+        pgen = Generator(args.variant, args.precision, device=local, micro_batch=args.micro_batch, weights=w)
+        os.environ.pop("BSR_PROFILE")
+        mb = min(args.micro_batch, B)
+        if tsm:
+            mb = mb // args.frame * args.frame
+        acc = {}
+        for i in range(3 + 5):
+            pgen(img[:mb], uv[:mb], reg[:mb] if tsm else None, frame=args.frame if tsm else None, want=want)
+            torch.cuda.synchronize()
+            if i >= 3:
+                for name, ms in pgen.layer_times():
+                    acc.setdefault(name, []).append(ms)
+        work = layer_work(args.variant)
+        rows = []
+        # res blocks: the profiler names attention/res_tail/share generically -> aggregate by name
+        for name, v in acc.items():
+            per_call = sum(v) / len(v)
+            calls = len(v) // 5
+            key = name if name in work else ("res0.attention" if name == "attention" else None)
+            fl, by = work.get(key, (0.0, 0.0))
+            t_s = per_call * 1e-3
+            tf = fl * mb / t_s / 1e12 if t_s > 0 else 0.0
+            gb = by * mb / t_s / 1e9 if t_s > 0 else 0.0
+            tc_bound = fl > 0 and (fl / max(by, 1)) > peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+            rows.append(dict(layer=name, calls_per_forward=calls, ms_per_launch=round(per_call, 4),
+                             ms_per_forward=round(per_call * calls, 4), tflops=round(tf, 1), gbs=round(gb, 1),
+                             bound="tensor" if tc_bound else "hbm",
+                             frac=round(tf / peaks["bf16_tflops_sustained"] if tc_bound else gb / peaks["hbm_gbs"], 4)))
+        rows.sort(key=lambda r: -r["ms_per_forward"])
+        total_ms = sum(r["ms_per_forward"] for r in rows)
+        top = rows[0]
+        unit_work = work.get(top["layer"], work.get("res0.attention"))
+        roof = {"kernel": top["layer"], "bound": top["bound"],
+                "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
+                "peak": peaks["bf16_tflops_sustained"] if top["bound"] == "tensor" else peaks["hbm_gbs"],
+                "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
+                "peak_source": peaks["src"] + (" sustained" if top["bound"] == "tensor" else ""),
+                "share_of_forward": round(top["ms_per_forward"] / total_ms, 4), "images_per_launch": mb,
+                "algorithmic_bytes_per_image": unit_work[1], "algorithmic_flops_per_image": unit_work[0],
+                "ms_per_launch": top["ms_per_launch"],
+                "network": {"ms_per_forward_profiled": round(total_ms, 4),
+                            "tflops_effective": round(GSC_GFLOP_PER_IMAGE * 1e9 * B * world / (ms_step / 1e3) / 1e12, 1)
+                            if args.variant == "gsc" else None}}
+        table = rows
+        if args.layers:
+            for r in rows:
+                print("%-14s x%d  %8.4f ms/launch  %8.4f ms/fwd  %7.1f TF/s  %7.1f GB/s  %-6s %.3f" % (
+                    r["layer"], r["calls_per_forward"], r["ms_per_launch"], r["ms_per_forward"], r["tflops"], r["gbs"],
+                    r["bound"], r["frac"]), file=sys.stderr)
+        pgen.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_s = 8 if not tsm else 4 * args.frame
+        v, cores = cpu_reference_rate(args.variant, args.frame, n_s, repeats=2)
+        cpu = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "%d synthetic images x 2 passes of the oracle (reference restated in PyTorch CPU; "
+                         "TensorFlow unavailable)" % n_s}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks_summary(samples),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "checksum_mean_rgb": round(checksum, 6),
+        }
+        if args.layers and table:
+            line["layers"] = table
+        print(json.dumps(line))
+    gen.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,747 @@
+// libbsr.so — host side of the C ABI declared in include/bsr.h: handle, weight packing, workspace
+// and the launch plan of Generator.call (/root/reference/model.py:228-290,
+// /root/reference/model_with_TSM.py:261-325).  No torch types; CUDA runtime only.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bsr.h"
+#include "attention_simple.cuh"
+#include "attention_tc.cuh"
+#include "common.cuh"
+#include "conv_direct.cuh"
+#include "conv_tc.cuh"
+#include "glue.cuh"
+
+using namespace bsr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Layer {
+  std::string name;
+  int kh = 0, kw = 0, cin = 0, cout = 0, transposed = 0;
+  std::vector<float> w_host, b_host;   // canonical fp32 [tap][cin][cout], [cout]
+  float* w_dev = nullptr;              // same, on device (CUDA-core kernels)
+  float* b_dev = nullptr;              // bias padded with zeros to a multiple of 16 (+256 slack)
+  TcWeights tc;                        // bf16 K-major packing + tensor map (conv_tc.cuh)
+};
+
+struct DebugBuf { float* dev = nullptr; size_t n = 0; };
+
+}  // namespace
+
+struct bsr_handle {
+  int variant = 0, precision = 0, device = 0, mb = 0;
+  bool loaded = false;
+  bool debug_keep = false, profile = false;
+  int force_direct = 0;      // BSR_FORCE_DIRECT=1: bf16 storage but CUDA-core convs/attention (bring-up aid)
+  std::string err;
+  std::map<std::string, Layer> layers;
+  // channel geometry
+  int c_first = 0, c_second = 0, ld1 = 0, ld2 = 0;
+  size_t es = 2;             // activation element size
+  // workspace
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  char *X1 = nullptr, *CAT3 = nullptr, *CAT2 = nullptr, *XA = nullptr, *XB = nullptr, *T1 = nullptr, *T2 = nullptr,
+       *Y = nullptr, *QK = nullptr, *VT = nullptr, *O = nullptr, *UP3 = nullptr, *F1 = nullptr, *F2 = nullptr,
+       *CAT1 = nullptr, *C16 = nullptr;
+  float *RAW = nullptr, *DIFGS = nullptr, *UVS = nullptr, *OFF = nullptr, *BMASK = nullptr, *DIFSMALL = nullptr,
+        *SH = nullptr;
+  int* errflag = nullptr;    // device flag set by kernels whose mbarrier wait timed out
+  int launches = 0;
+  std::map<std::string, DebugBuf> dbg;
+  // profiling
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> ev_names;
+  size_t ev_used = 0;
+  std::vector<std::pair<const char*, float>> times;
+  // host-path staging
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  TmaEncoder tma;
+};
+
+namespace {
+
+int configure_tc_kernels() {
+  if (int r = configure_tc_kernels_conv()) return r;
+  return configure_tc_kernels_attn();
+}
+
+int fail(bsr_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail(h, BSR_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+inline int pad8(int c) { return (c + 7) / 8 * 8; }
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+// ---------------------------------------------------------------------------------------------
+// weight blob (written by blindshadowremoval_b200/convert.py)
+//   char magic[8] = "BSRW0001"; int32 variant; int32 n_layers;
+//   n_layers x { char name[32]; int32 kh, kw, cin, cout, transposed, pad; uint64 w_off, b_off; }
+//   then fp32 payload; offsets are from the start of the blob.
+struct BlobEntry {
+  char name[32];
+  int32_t kh, kw, cin, cout, transposed, pad;
+  uint64_t w_off, b_off;
+};
+
+struct Step {
+  bsr_handle* h;
+  cudaStream_t st;
+  const char* name;
+  Step(bsr_handle* h_, cudaStream_t st_, const char* n) : h(h_), st(st_), name(n) {
+    if (h->profile && h->ev_used + 2 <= h->ev.size()) {
+      cudaEventRecord(h->ev[h->ev_used], st);
+    }
+  }
+  ~Step() {
+    if (h->profile && h->ev_used + 2 <= h->ev.size()) {
+      cudaEventRecord(h->ev[h->ev_used + 1], st);
+      h->ev_names.push_back(name);
+      h->ev_used += 2;
+    }
+  }
+};
+
+template <typename T>
+void debug_capture_t(bsr_handle* h, cudaStream_t st, const char* name, const void* buf, int ld, int coff, int C,
+                     long long npix) {
+  DebugBuf& d = h->dbg[name];
+  size_t n = (size_t)npix * C;
+  if (d.n != n) {
+    if (d.dev) cudaFree(d.dev);
+    cudaMalloc(&d.dev, n * sizeof(float));
+    d.n = n;
+  }
+  long long tot = npix * C;
+  slice_to_f32_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const T*)buf, ld, coff, C, d.dev, npix);
+}
+
+void debug_capture(bsr_handle* h, cudaStream_t st, const char* name, const void* buf, int ld, int coff, int C,
+                   long long npix, bool is_f32 = false) {
+  if (!h->debug_keep) return;
+  if (is_f32 || h->precision == BSR_PRECISION_FP32CHECK)
+    debug_capture_t<float>(h, st, name, buf, ld, coff, C, npix);
+  else
+    debug_capture_t<bf16>(h, st, name, buf, ld, coff, C, npix);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one convolution (any of: conv / transposed conv / 1x1) with fused epilogue
+struct ConvCall {
+  const char* layer;
+  const void* in; int in_ld, in_coff; bool in_f32;
+  int H, W;           // input spatial size
+  int stride;         // 1 or 2 (ignored for transposed)
+  EpiParams e;
+};
+
+template <typename TIn, typename T>
+void launch_direct(bsr_handle* h, cudaStream_t st, const Layer& L, const ConvCall& c, int n) {
+  ConvDirectParams p;
+  p.in = c.in; p.in_ld = c.in_ld; p.in_coff = c.in_coff; p.cin = L.cin;
+  p.H = c.H; p.W = c.W; p.N = n;
+  p.kh = L.kh; p.kw = L.kw; p.transposed = L.transposed;
+  if (L.transposed) {
+    p.OH = 2 * c.H; p.OW = 2 * c.W; p.stride = 2; p.pad_t = p.pad_l = 0;
+  } else {
+    p.stride = c.stride;
+    p.OH = (c.H + c.stride - 1) / c.stride;
+    p.OW = (c.W + c.stride - 1) / c.stride;
+    int tot_h = (p.OH - 1) * c.stride + L.kh - c.H; if (tot_h < 0) tot_h = 0;
+    int tot_w = (p.OW - 1) * c.stride + L.kw - c.W; if (tot_w < 0) tot_w = 0;
+    p.pad_t = tot_h / 2; p.pad_l = tot_w / 2;       // TF SAME: before = total // 2
+  }
+  p.w = L.w_dev; p.cout = L.cout;
+  long long M = (long long)n * p.OH * p.OW;
+  int nc = c.e.out_c > L.cout ? c.e.out_c : L.cout;
+  dim3 grid((unsigned)((M + CD_TM - 1) / CD_TM), (unsigned)((nc + CD_TN - 1) / CD_TN));
+  conv_direct_kernel<TIn, T><<<grid, 256, 0, st>>>(p, c.e);
+  h->launches++;
+}
+
+int run_conv(bsr_handle* h, cudaStream_t st, ConvCall c, int n) {
+  auto it = h->layers.find(c.layer);
+  if (it == h->layers.end()) return fail(h, BSR_ESTATE, "layer %s missing from weight blob", c.layer);
+  Layer& L = it->second;
+  c.e.bias = L.b_dev;
+  c.e.cout = L.cout;
+  Step step(h, st, L.name.c_str());
+  if (h->precision == BSR_PRECISION_FP32CHECK) {
+    launch_direct<float, float>(h, st, L, c, n);
+    return BSR_OK;
+  }
+  if (!h->force_direct && L.tc.ready && !c.in_f32) {
+    int rc = launch_conv_tc(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, h->errflag, st,
+                            &h->launches);
+    if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core conv %s: launch failed (%d): %s", c.layer, rc,
+                             h->tma.last_error.c_str());
+    return BSR_OK;
+  }
+  if (c.in_f32) launch_direct<float, bf16>(h, st, L, c, n);
+  else launch_direct<bf16, bf16>(h, st, L, c, n);
+  return BSR_OK;
+}
+
+EpiParams epi(void* out, int out_ld, int out_coff, int out_c, int act, int mode = OUT_T) {
+  EpiParams e;
+  memset(&e, 0, sizeof e);
+  e.out = out; e.out_ld = out_ld; e.out_coff = out_coff; e.out_c = out_c; e.act = act; e.out_mode = mode;
+  return e;
+}
+
+int run_attention(bsr_handle* h, cudaStream_t st, int n) {
+  Step step(h, st, "attention");
+  if (h->precision == BSR_PRECISION_FP32CHECK) {
+    attention_simple_kernel<float><<<dim3(AS_S / AS_Q, n), 256, kAttnSimpleSmem, st>>>(
+        (const float*)h->QK, (const float*)h->VT, (float*)h->O, 128);
+    h->launches++;
+    return BSR_OK;
+  }
+  if (!h->force_direct) {
+    int rc = launch_attention_tc(h->tma, (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, n, h->errflag, st);
+    if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
+    h->launches++;
+    return BSR_OK;
+  }
+  attention_simple_kernel<bf16><<<dim3(AS_S / AS_Q, n), 256, kAttnSimpleSmem, st>>>(
+      (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, 128);
+  h->launches++;
+  return BSR_OK;
+}
+
+// ResBottleneck + NonLocalBlock (model.py:98-113, 23-61).  cur: [n,1024,ld] with c_cur live channels.
+template <typename T>
+int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt, int ld, int c_cur, int n) {
+  char nm[5][32];
+  snprintf(nm[0], 32, "res%d.conv1", idx);
+  snprintf(nm[1], 32, "res%d.conv2", idx);
+  snprintf(nm[2], 32, "res%d.conv3", idx);
+  snprintf(nm[3], 32, "res%d.qkv", idx);
+  snprintf(nm[4], 32, "res%d.w", idx);
+  int rc;
+  const int ldy = 264;
+  ConvCall c1{nm[0], cur, ld, 0, false, FEAT, FEAT, 1, epi(h->T1, 128, 0, 128, 1)};
+  if ((rc = run_conv(h, st, c1, n))) return rc;
+  ConvCall c2{nm[1], h->T1, 128, 0, false, FEAT, FEAT, 1, epi(h->T2, 128, 0, 128, 1)};
+  if ((rc = run_conv(h, st, c2, n))) return rc;
+  ConvCall c3{nm[2], h->T2, 128, 0, false, FEAT, FEAT, 1, epi(h->Y, ldy, 0, ldy, 0)};
+  if ((rc = run_conv(h, st, c3, n))) return rc;
+  EpiParams eq = epi(h->QK, 256, 0, 384, 0, OUT_QKV);
+  eq.out2 = h->VT;
+  eq.spatial = FEAT * FEAT;
+  ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq};
+  if ((rc = run_conv(h, st, c4, n))) return rc;
+  if ((rc = run_attention(h, st, n))) return rc;
+  int oc = ld < ldy ? ld : ldy;
+  EpiParams ew = epi(nxt, ld, 0, oc, 1);
+  ew.res1 = h->Y; ew.res1_ld = ldy; ew.res1_c = 257;
+  ew.res2 = cur; ew.res2_ld = ld; ew.res2_c = c_cur;
+  ConvCall c5{nm[4], h->O, 128, 0, false, FEAT, FEAT, 1, ew};
+  if ((rc = run_conv(h, st, c5, n))) return rc;
+  if (ld > oc) {
+    Step step(h, st, "res_tail");
+    long long npix = (long long)n * FEAT * FEAT, tot = npix * (ld - oc);
+    res_tail_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const T*)cur, ld, (T*)nxt, ld, oc, ld, npix);
+    h->launches++;
+  }
+  return BSR_OK;
+}
+
+template <typename T>
+int run_share(bsr_handle* h, cudaStream_t st, char* x, int ld, int C, int coff, int n, int frame, int share) {
+  Step step(h, st, "share_layer");
+  long long npix = (long long)n * FEAT * FEAT;
+  if (!share) {
+    long long tot = npix * C;
+    share_dup_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((T*)x, ld, C, coff, npix);
+    h->launches++;
+    return BSR_OK;
+  }
+  int chunks = n / frame;
+  share_reduce_kernel<T><<<chunks * FEAT * FEAT, 128, 0, st>>>((const T*)x, ld, C, h->OFF, frame, h->SH);
+  share_out_kernel<T><<<n * FEAT * FEAT, 128, 0, st>>>(h->SH, 2 * C, h->OFF, frame, (T*)x, ld, coff);
+  h->launches += 2;
+  return BSR_OK;
+}
+
+// one micro-batch
+template <typename T>
+int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv, const float* reg, int n, int frame,
+               int share, float* gs, float* rgb, float* mask22, float* dif) {
+  const bool tsm = h->variant == BSR_VARIANT_TSM;
+  int rc;
+  const long long px256 = (long long)n * IMG * IMG, px32 = (long long)n * FEAT * FEAT;
+  // ---- encoder (model.py:230-233)
+  ConvCall cv1{"conv1", img, 3, 0, true, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1)};
+  if ((rc = run_conv(h, st, cv1, n))) return rc;
+  debug_capture(h, st, "x1", h->X1, 32, 0, 32, px256);
+  ConvCall d1{"down1", h->X1, 32, 0, false, IMG, IMG, 2, epi(h->CAT3, 128, 64, 64, 1)};
+  if ((rc = run_conv(h, st, d1, n))) return rc;
+  debug_capture(h, st, "x2", h->CAT3, 128, 64, 64, (long long)n * 128 * 128);
+  ConvCall d2{"down2", h->CAT3, 128, 64, false, 128, 128, 2, epi(h->CAT2, 160, 96, 64, 1)};
+  if ((rc = run_conv(h, st, d2, n))) return rc;
+  debug_capture(h, st, "x3", h->CAT2, 160, 96, 64, (long long)n * 64 * 64);
+  const int ld1 = h->ld1, ld2 = h->ld2;
+  ConvCall d3{"down3", h->CAT2, 160, 96, false, 64, 64, 2, epi(h->XA, ld1, 0, 96, 1)};
+  if ((rc = run_conv(h, st, d3, n))) return rc;
+  // ---- uv / registration fields at 32x32 (model.py:237; warp.py:137)
+  {
+    Step step(h, st, "uv_small");
+    int tot = n * FEAT * FEAT * 3;
+    uv_small_kernel<<<(tot + 255) / 256, 256, 0, st>>>(uv, h->UVS, n);
+    h->launches++;
+    if (tsm) {
+      int tot4 = n * FEAT * FEAT * 4;
+      reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
+      h->launches++;
+    }
+  }
+  int c_cur = h->c_first;
+  if (tsm) {
+    if ((rc = run_share<T>(h, st, h->XA, ld1, 96, 96, n, frame, share))) return rc;   // model_with_TSM.py:271
+  }
+  {
+    Step step(h, st, "assemble_uv");
+    int uv_off = c_cur - 3;
+    long long tot = px32 * (3 + (ld1 - c_cur));
+    assemble_uv_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((T*)h->XA, ld1, h->UVS, uv_off, c_cur, ld1,
+                                                                         (int)px32);
+    h->launches++;
+  }
+  debug_capture(h, st, "x_in0", h->XA, ld1, 0, c_cur, px32);
+  // ---- res blocks 0-2 (model.py:239-240)
+  char *cur = h->XA, *nxt = h->XB;
+  static const char* res_names[6] = {"res0", "res1", "res2", "res3", "res4", "res5"};
+  for (int i = 0; i < 3; ++i) {
+    if ((rc = run_res_block<T>(h, st, i, cur, nxt, ld1, c_cur, n))) return rc;
+    if (c_cur < 257) c_cur = 257;
+    std::swap(cur, nxt);
+    debug_capture(h, st, res_names[i], cur, ld1, 0, c_cur, px32);
+  }
+  // ---- grey decoder (model.py:243-252)
+  ConvCall u1{"up1", cur, ld1, 0, false, FEAT, FEAT, 2, epi(h->CAT2, 160, 0, 96, 1)};
+  if ((rc = run_conv(h, st, u1, n))) return rc;
+  debug_capture(h, st, "up1", h->CAT2, 160, 0, 96, (long long)n * 64 * 64);
+  ConvCall u2{"up2", h->CAT2, 160, 0, false, 64, 64, 2, epi(h->CAT3, 128, 0, 64, 1)};
+  if ((rc = run_conv(h, st, u2, n))) return rc;
+  debug_capture(h, st, "up2", h->CAT3, 128, 0, 64, (long long)n * 128 * 128);
+  ConvCall u3{"up3", h->CAT3, 128, 0, false, 128, 128, 2, epi(h->UP3, 64, 0, 64, 1)};
+  if ((rc = run_conv(h, st, u3, n))) return rc;
+  debug_capture(h, st, "up3", h->UP3, 64, 0, 64, px256);
+  ConvCall hd{"heads", h->UP3, 64, 0, false, IMG, IMG, 1, epi(h->RAW, 2, 0, 2, 0, OUT_F32)};
+  if ((rc = run_conv(h, st, hd, n))) return rc;
+  {
+    Step step(h, st, "compose");
+    compose_kernel<T><<<(unsigned)((px256 + 255) / 256), 256, 0, st>>>(h->RAW, img, gs, mask22, h->DIFGS, (T*)h->CAT1,
+                                                                       72, 64, px256);
+    h->launches++;
+  }
+  // ---- hole mask + second-half input (model.py:256-259; model_with_TSM.py:290-294)
+  {
+    Step step(h, st, "hole");
+    int cx = c_cur;
+    int uv_off = tsm ? cx + 1 + 2 * cx : cx + 1;
+    int cells = (int)px32;
+    hole_kernel<T><<<(cells + 3) / 4, 128, 0, st>>>(h->DIFGS, (const T*)cur, ld1, (T*)nxt, ld2, cx, h->UVS, uv_off,
+                                                    uv_off + 3, ld2, h->BMASK, h->DIFSMALL, cells);
+    h->launches++;
+  }
+  // the hole kernel wrote into `nxt` viewed with ld2; from here on (cur, nxt) = (that buffer, the other)
+  std::swap(cur, nxt);
+  if (tsm) {
+    if ((rc = run_share<T>(h, st, cur, ld2, c_cur, c_cur + 1, n, frame, share))) return rc;   // model_with_TSM.py:293
+  }
+  c_cur = h->c_second;
+  debug_capture(h, st, "x_in3", cur, ld2, 0, c_cur, px32);
+  debug_capture(h, st, "bmask", h->BMASK, 1, 0, 1, px32, true);
+  debug_capture(h, st, "dif_small", h->DIFSMALL, 1, 0, 1, px32, true);
+  for (int i = 3; i < 6; ++i) {
+    if ((rc = run_res_block<T>(h, st, i, cur, nxt, ld2, c_cur, n))) return rc;
+    std::swap(cur, nxt);
+    debug_capture(h, st, res_names[i], cur, ld2, 0, c_cur, px32);
+  }
+  // ---- colour decoder (model.py:264-269, 288)
+  ConvCall k1{"clr_up1", cur, ld2, 0, false, FEAT, FEAT, 2, epi(h->F1, 128, 0, 128, 1)};
+  if ((rc = run_conv(h, st, k1, n))) return rc;
+  debug_capture(h, st, "clr_up1", h->F1, 128, 0, 128, (long long)n * 64 * 64);
+  ConvCall k2{"clr_up2", h->F1, 128, 0, false, 64, 64, 2, epi(h->F2, 96, 0, 96, 1)};
+  if ((rc = run_conv(h, st, k2, n))) return rc;
+  debug_capture(h, st, "clr_up2", h->F2, 96, 0, 96, (long long)n * 128 * 128);
+  ConvCall k3{"clr_up3", h->F2, 96, 0, false, 128, 128, 2, epi(h->CAT1, 72, 0, 64, 1)};
+  if ((rc = run_conv(h, st, k3, n))) return rc;
+  debug_capture(h, st, "clr_up3", h->CAT1, 72, 0, 64, px256);
+  ConvCall kc{"clr_conv1", h->CAT1, 72, 0, false, IMG, IMG, 1, epi(h->C16, 16, 0, 16, 1)};
+  if ((rc = run_conv(h, st, kc, n))) return rc;
+  {
+    Step step(h, st, "clr_tail");
+    Layer& l2 = h->layers["clr_conv2"];
+    Layer& l3 = h->layers["clr_conv3"];
+    clr_tail_kernel<T><<<(unsigned)((px256 + 127) / 128), 128, 0, st>>>((const T*)h->C16, 16, l2.w_dev, l2.b_dev,
+                                                                        l3.w_dev, l3.b_dev, img, rgb, dif, px256);
+    h->launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, BSR_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return BSR_OK;
+}
+
+int forward_common(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
+                   float* gs, float* rgb, float* mask22, float* dif, cudaStream_t st) {
+  if (!h) return BSR_EINVAL;
+  if (!h->loaded) return fail(h, BSR_ESTATE, "bsr_load_weights has not been called");
+  if (n <= 0 || !img || !uv) return fail(h, BSR_EINVAL, "n must be > 0 and img/uv non-NULL");
+  const bool tsm = h->variant == BSR_VARIANT_TSM;
+  if (tsm && (!reg || frame <= 0 || n % frame)) return fail(h, BSR_EINVAL, "TSM needs reg and n %% frame == 0");
+  if (tsm && frame > h->mb) return fail(h, BSR_EINVAL, "frame %d exceeds micro_batch %d", frame, h->mb);
+  int dev;
+  CK(h, cudaGetDevice(&dev));
+  if (dev != h->device) CK(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  h->ev_used = 0;
+  h->ev_names.clear();
+  int step = h->mb;
+  if (tsm) step = h->mb / frame * frame;
+  for (int i0 = 0; i0 < n; i0 += step) {
+    int m = n - i0 < step ? n - i0 : step;
+    const size_t o3 = (size_t)i0 * IMG * IMG * 3, o1 = (size_t)i0 * IMG * IMG;
+    int rc;
+    const float* regp = reg ? reg + (size_t)i0 * IMG * IMG * 6 : nullptr;
+    if (h->precision == BSR_PRECISION_FP32CHECK)
+      rc = forward_mb<float>(h, st, img + o3, uv + o3, regp, m, frame, share, gs ? gs + o1 : nullptr,
+                             rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
+    else
+      rc = forward_mb<bf16>(h, st, img + o3, uv + o3, regp, m, frame, share, gs ? gs + o1 : nullptr,
+                            rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
+    if (rc) return rc;
+  }
+  if (dev != h->device) cudaSetDevice(dev);
+  return BSR_OK;
+}
+
+int forward_host(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
+                 float* gs, float* rgb, float* mask22, float* dif) {
+  if (!h) return BSR_EINVAL;
+  if (n <= 0) return fail(h, BSR_EINVAL, "n must be > 0");
+  CK(h, cudaSetDevice(h->device));
+  const size_t p = (size_t)n * IMG * IMG * sizeof(float);
+  size_t need = p * (3 + 3 + (reg ? 6 : 0) + 1 + 3 + 3 + 1);
+  if (need > h->stage_bytes) {
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    if (cudaMalloc(&h->stage, need) != cudaSuccess) return fail(h, BSR_ENOMEM, "staging allocation of %zu bytes failed", need);
+    h->stage_bytes = need;
+  }
+  char* s = (char*)h->stage;
+  float* d_img = (float*)s; s += 3 * p;
+  float* d_uv = (float*)s; s += 3 * p;
+  float* d_reg = nullptr;
+  if (reg) { d_reg = (float*)s; s += 6 * p; }
+  float* d_gs = (float*)s; s += p;
+  float* d_rgb = (float*)s; s += 3 * p;
+  float* d_m22 = (float*)s; s += 3 * p;
+  float* d_dif = (float*)s;
+  cudaStream_t st = h->own_stream;
+  CK(h, cudaMemcpyAsync(d_img, img, 3 * p, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(d_uv, uv, 3 * p, cudaMemcpyHostToDevice, st));
+  if (reg) CK(h, cudaMemcpyAsync(d_reg, reg, 6 * p, cudaMemcpyHostToDevice, st));
+  int rc = forward_common(h, d_img, d_uv, d_reg, n, frame, share, gs ? d_gs : nullptr, rgb ? d_rgb : nullptr,
+                          mask22 ? d_m22 : nullptr, dif ? d_dif : nullptr, st);
+  if (rc) return rc;
+  if (gs) CK(h, cudaMemcpyAsync(gs, d_gs, p, cudaMemcpyDeviceToHost, st));
+  if (rgb) CK(h, cudaMemcpyAsync(rgb, d_rgb, 3 * p, cudaMemcpyDeviceToHost, st));
+  if (mask22) CK(h, cudaMemcpyAsync(mask22, d_m22, 3 * p, cudaMemcpyDeviceToHost, st));
+  if (dif) CK(h, cudaMemcpyAsync(dif, d_dif, p, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  int flag = 0;
+  CK(h, cudaMemcpy(&flag, h->errflag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return fail(h, BSR_ECUDA, "device watchdog: an mbarrier wait timed out (code %d)", flag);
+  return BSR_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* bsr_version(void) { return "bsr-b200 0.1 (sm_100a)"; }
+
+const char* bsr_last_error(const bsr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int bsr_create(int variant, int precision, int device, int micro_batch, bsr_handle** out) {
+  if (!out) return BSR_EINVAL;
+  *out = nullptr;
+  if (variant != BSR_VARIANT_GSC && variant != BSR_VARIANT_TSM) return fail(nullptr, BSR_EINVAL, "bad variant %d", variant);
+  if (precision != BSR_PRECISION_BF16 && precision != BSR_PRECISION_FP32CHECK)
+    return fail(nullptr, BSR_EINVAL, "bad precision %d", precision);
+  if (micro_batch <= 0 || micro_batch > 4096) return fail(nullptr, BSR_EINVAL, "micro_batch out of range");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, BSR_ECUDA, "no CUDA device available (%s); this library has no CPU path",
+                cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(nullptr, BSR_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CK(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, BSR_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  CK(nullptr, cudaSetDevice(device));
+  bsr_handle* h = new bsr_handle();
+  h->variant = variant; h->precision = precision; h->device = device; h->mb = micro_batch;
+  h->es = precision == BSR_PRECISION_FP32CHECK ? 4 : 2;
+  const char* ev = getenv("BSR_DEBUG_KEEP");
+  h->debug_keep = ev && atoi(ev) != 0;
+  ev = getenv("BSR_PROFILE");
+  h->profile = ev && atoi(ev) != 0;
+  ev = getenv("BSR_FORCE_DIRECT");
+  h->force_direct = ev ? atoi(ev) : 0;
+  h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
+  h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
+  h->ld1 = pad8(h->c_first > 257 ? h->c_first : 257);
+  if (h->ld1 < 264) h->ld1 = 264;
+  h->ld2 = pad8(h->c_second);
+  // ---- workspace: one arena, carved with 256-byte alignment
+  const size_t es = h->es, mb = micro_batch;
+  const size_t ldmax = h->ld1 > h->ld2 ? h->ld1 : h->ld2;
+  struct Req { char** p; size_t bytes; };
+  std::vector<Req> reqs = {
+      {&h->X1, mb * IMG * IMG * 32 * es}, {&h->CAT3, mb * 128 * 128 * 128 * es}, {&h->CAT2, mb * 64 * 64 * 160 * es},
+      {&h->XA, mb * 1024 * ldmax * es}, {&h->XB, mb * 1024 * ldmax * es}, {&h->T1, mb * 1024 * 128 * es},
+      {&h->T2, mb * 1024 * 128 * es}, {&h->Y, mb * 1024 * 264 * es}, {&h->QK, mb * 1024 * 256 * es},
+      {&h->VT, mb * 1024 * 128 * es}, {&h->O, mb * 1024 * 128 * es}, {&h->UP3, mb * IMG * IMG * 64 * es},
+      {&h->F1, mb * 64 * 64 * 128 * es}, {&h->F2, mb * 128 * 128 * 96 * es}, {&h->CAT1, mb * IMG * IMG * 72 * es},
+      {&h->C16, mb * IMG * IMG * 16 * es},
+      {(char**)&h->RAW, mb * IMG * IMG * 2 * 4}, {(char**)&h->DIFGS, mb * IMG * IMG * 4},
+      {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
+      {(char**)&h->DIFSMALL, mb * 1024 * 4},
+      {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 2 * 291 * 4 : 256},
+      {(char**)&h->errflag, 256}};
+  size_t total = 0;
+  for (auto& r : reqs) total += align256(r.bytes);
+  if (cudaMalloc(&h->arena, total) != cudaSuccess) {
+    cudaGetLastError();
+    delete h;
+    return fail(nullptr, BSR_ENOMEM, "workspace allocation of %zu bytes failed", total);
+  }
+  h->arena_bytes = total;
+  cudaMemset(h->arena, 0, total);
+  size_t off = 0;
+  for (auto& r : reqs) { *r.p = (char*)h->arena + off; off += align256(r.bytes); }
+  cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (h->profile) {
+    h->ev.resize(512);
+    for (auto& e : h->ev) cudaEventCreate(&e);
+  }
+  if (!h->tma.init()) {
+    std::string msg = h->tma.last_error;
+    bsr_destroy(h);
+    return fail(nullptr, BSR_ECUDA, "cuTensorMapEncodeTiled unavailable: %s", msg.c_str());
+  }
+  if (int rc = configure_tc_kernels()) {
+    bsr_destroy(h);
+    return fail(nullptr, BSR_ECUDA, "cudaFuncSetAttribute failed for tensor-core kernels (%d)", rc);
+  }
+  cudaFuncSetAttribute(attention_simple_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSimpleSmem);
+  cudaFuncSetAttribute(attention_simple_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSimpleSmem);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    bsr_destroy(h);
+    return fail(nullptr, BSR_ECUDA, "device init failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return BSR_OK;
+}
+
+int bsr_destroy(bsr_handle* h) {
+  if (!h) return BSR_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->layers) {
+    if (kv.second.w_dev) cudaFree(kv.second.w_dev);
+    if (kv.second.b_dev) cudaFree(kv.second.b_dev);
+    kv.second.tc.release();
+  }
+  for (auto& kv : h->dbg) if (kv.second.dev) cudaFree(kv.second.dev);
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  if (h->arena) cudaFree(h->arena);
+  if (h->stage) cudaFree(h->stage);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return BSR_OK;
+}
+
+int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
+  if (!h || !blob) return BSR_EINVAL;
+  CK(h, cudaSetDevice(h->device));
+  const char* b = (const char*)blob;
+  if (nbytes < 16 || memcmp(b, "BSRW0001", 8) != 0) return fail(h, BSR_EINVAL, "bad weight blob magic");
+  int32_t variant, n_layers;
+  memcpy(&variant, b + 8, 4);
+  memcpy(&n_layers, b + 12, 4);
+  if (variant != h->variant) return fail(h, BSR_EINVAL, "blob is for variant %d, handle is %d", variant, h->variant);
+  if (n_layers <= 0 || 16 + (size_t)n_layers * sizeof(BlobEntry) > nbytes) return fail(h, BSR_EINVAL, "truncated blob");
+  for (int i = 0; i < n_layers; ++i) {
+    BlobEntry en;
+    memcpy(&en, b + 16 + (size_t)i * sizeof(BlobEntry), sizeof en);
+    en.name[31] = 0;
+    size_t wn = (size_t)en.kh * en.kw * en.cin * en.cout;
+    if (en.w_off + wn * 4 > nbytes || en.b_off + (size_t)en.cout * 4 > nbytes)
+      return fail(h, BSR_EINVAL, "layer %s: payload outside blob", en.name);
+    Layer& L = h->layers[en.name];
+    if (L.w_dev) { cudaFree(L.w_dev); L.w_dev = nullptr; }
+    if (L.b_dev) { cudaFree(L.b_dev); L.b_dev = nullptr; }
+    L.tc.release();
+    L.name = en.name;
+    L.kh = en.kh; L.kw = en.kw; L.cin = en.cin; L.cout = en.cout; L.transposed = en.transposed;
+    L.w_host.assign((const float*)(b + en.w_off), (const float*)(b + en.w_off) + wn);
+    L.b_host.assign((const float*)(b + en.b_off), (const float*)(b + en.b_off) + en.cout);
+    CK(h, cudaMalloc(&L.w_dev, wn * 4));
+    CK(h, cudaMemcpy(L.w_dev, L.w_host.data(), wn * 4, cudaMemcpyHostToDevice));
+    size_t bn = ((size_t)en.cout + 15) / 16 * 16 + 1024;
+    std::vector<float> bp(bn, 0.f);
+    memcpy(bp.data(), L.b_host.data(), (size_t)en.cout * 4);
+    CK(h, cudaMalloc(&L.b_dev, bn * 4));
+    CK(h, cudaMemcpy(L.b_dev, bp.data(), bn * 4, cudaMemcpyHostToDevice));
+    if (h->precision == BSR_PRECISION_BF16) {
+      std::string why;
+      if (!pack_tc_weights(h->tma, L.name, L.kh, L.kw, L.cin, L.cout, L.transposed, L.w_host, &L.tc, &why) &&
+          !why.empty())
+        return fail(h, BSR_ECUDA, "packing %s for tensor cores failed: %s", en.name, why.c_str());
+    }
+  }
+  static const char* required[] = {"conv1", "down1", "down2", "down3", "up1", "up2", "up3", "heads", "clr_up1",
+                                   "clr_up2", "clr_up3", "clr_conv1", "clr_conv2", "clr_conv3"};
+  for (const char* r : required)
+    if (!h->layers.count(r)) return fail(h, BSR_EINVAL, "blob lacks layer %s", r);
+  for (int i = 0; i < 6; ++i)
+    for (const char* s : {"conv1", "conv2", "conv3", "qkv", "w"}) {
+      char nm[32];
+      snprintf(nm, 32, "res%d.%s", i, s);
+      if (!h->layers.count(nm)) return fail(h, BSR_EINVAL, "blob lacks layer %s", nm);
+    }
+  const int cin_first = h->c_first, cin_second = h->c_second;
+  if (h->layers["res0.conv1"].cin != cin_first || h->layers["res3.conv1"].cin != cin_second)
+    return fail(h, BSR_EINVAL, "res-stack input widths do not match variant");
+  h->loaded = true;
+  return BSR_OK;
+}
+
+int bsr_forward_gsc(bsr_handle* h, const float* img, const float* uv, int n, float* gs, float* rgb, float* mask22,
+                    float* dif, void* cuda_stream) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_GSC) return fail(h, BSR_EINVAL, "handle is not a GSC generator");
+  return forward_common(h, img, uv, nullptr, n, 1, 0, gs, rgb, mask22, dif, (cudaStream_t)cuda_stream);
+}
+
+int bsr_forward_tsm(bsr_handle* h, const float* img, const float* uv, const float* reg, int n_chunks, int frame,
+                    int share, float* gs, float* rgb, float* mask22, float* dif, void* cuda_stream) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_TSM) return fail(h, BSR_EINVAL, "handle is not a TSM generator");
+  if (n_chunks <= 0 || frame <= 0) return fail(h, BSR_EINVAL, "n_chunks and frame must be > 0");
+  return forward_common(h, img, uv, reg, n_chunks * frame, frame, share, gs, rgb, mask22, dif,
+                        (cudaStream_t)cuda_stream);
+}
+
+int bsr_forward_gsc_host(bsr_handle* h, const float* img, const float* uv, int n, float* gs, float* rgb,
+                         float* mask22, float* dif) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_GSC) return fail(h, BSR_EINVAL, "handle is not a GSC generator");
+  return forward_host(h, img, uv, nullptr, n, 1, 0, gs, rgb, mask22, dif);
+}
+
+int bsr_forward_tsm_host(bsr_handle* h, const float* img, const float* uv, const float* reg, int n_chunks, int frame,
+                         int share, float* gs, float* rgb, float* mask22, float* dif) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_TSM) return fail(h, BSR_EINVAL, "handle is not a TSM generator");
+  if (n_chunks <= 0 || frame <= 0 || !reg) return fail(h, BSR_EINVAL, "n_chunks, frame > 0 and reg required");
+  return forward_host(h, img, uv, reg, n_chunks * frame, frame, share, gs, rgb, mask22, dif);
+}
+
+int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n, float* rgb_clipped,
+                    float* mask_pred, void* cuda_stream) {
+  if (!h || n <= 0) return BSR_EINVAL;
+  if (mask_pred && (!dif || !face)) return fail(h, BSR_EINVAL, "mask_pred needs dif and face");
+  if (rgb_clipped && !rgb) return fail(h, BSR_EINVAL, "rgb_clipped needs rgb");
+  long long px = (long long)n * IMG * IMG;
+  caller_glue_kernel<<<(unsigned)((px + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(rgb, dif, face, rgb_clipped,
+                                                                                         mask_pred, px);
+  CK(h, cudaGetLastError());
+  return BSR_OK;
+}
+
+int bsr_composite(bsr_handle* h, const float* pred, const float* inp, const float* m, size_t n_elems, float* out,
+                  void* cuda_stream) {
+  if (!h || !pred || !inp || !m || !out) return BSR_EINVAL;
+  if (n_elems == 0) return BSR_OK;
+  size_t blocks = (n_elems + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  composite_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(pred, inp, m, out, n_elems);
+  CK(h, cudaGetLastError());
+  return BSR_OK;
+}
+
+int bsr_launch_count(const bsr_handle* h) { return h ? h->launches : 0; }
+size_t bsr_workspace_bytes(const bsr_handle* h) { return h ? h->arena_bytes : 0; }
+
+int bsr_debug_read(bsr_handle* h, const char* name, float* host_out, size_t capacity, size_t* n_elems) {
+  if (!h || !name) return BSR_EINVAL;
+  if (!h->debug_keep) return fail(h, BSR_ESTATE, "create the handle with BSR_DEBUG_KEEP=1 to keep intermediates");
+  if (!strcmp(name, "errflag")) {
+    int flag = 0;
+    CK(h, cudaMemcpy(&flag, h->errflag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n_elems) *n_elems = 1;
+    if (host_out && capacity >= 1) host_out[0] = (float)flag;
+    return BSR_OK;
+  }
+  auto it = h->dbg.find(name);
+  if (it == h->dbg.end()) return fail(h, BSR_EINVAL, "no intermediate named %s", name);
+  if (n_elems) *n_elems = it->second.n;
+  if (!host_out) return BSR_OK;
+  if (capacity < it->second.n) return fail(h, BSR_EINVAL, "capacity %zu < %zu", capacity, it->second.n);
+  CK(h, cudaDeviceSynchronize());
+  CK(h, cudaMemcpy(host_out, it->second.dev, it->second.n * sizeof(float), cudaMemcpyDeviceToHost));
+  return BSR_OK;
+}
+
+int bsr_layer_times(const bsr_handle* hc, const char** names, float* ms, int capacity) {
+  bsr_handle* h = const_cast<bsr_handle*>(hc);
+  if (!h || !h->profile) return 0;
+  cudaDeviceSynchronize();
+  int n = 0;
+  for (size_t i = 0; i + 1 < h->ev_used && n < capacity; i += 2, ++n) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]);
+    names[n] = h->ev_names[i / 2];
+    ms[n] = t;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// Bandwidth-bound glue between the convolutions: 256->32 resizes, grey composition, hole mask,
+// temporal sharing (ShareLayer), colour tail, caller-side blends.  T = activation storage type
+// (bf16 in the product path, float in FP32CHECK).  Reference lines are cited per kernel.
+#pragma once
+#include "common.cuh"
+
+namespace bsr {
+
+constexpr int IMG = 256, FEAT = 32, CELL = 8;
+
+// tf.image.resize(x, [32,32]) of a 256x256 map (bilinear, half-pixel centres, no antialias): source
+// coordinate 8i+3.5 -> rows/cols (8i+3, 8i+4) with weights 1/2 (model.py:237, 256; warp.py:137).
+__device__ __forceinline__ float resize8(const float* __restrict__ p, int n, int i, int j, int ld, int c) {
+  const float* b = p + (((size_t)n * IMG + (CELL * i + 3)) * IMG + (CELL * j + 3)) * ld + c;
+  float top = b[0] * 0.5f + b[ld] * 0.5f;
+  float bot = b[(size_t)IMG * ld] * 0.5f + b[(size_t)IMG * ld + ld] * 0.5f;
+  return top * 0.5f + bot * 0.5f;
+}
+
+// uv[N,256,256,3] -> uvs[N,32,32,3]   (model.py:237)
+__global__ void uv_small_kernel(const float* __restrict__ uv, float* __restrict__ uvs, int n_img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * FEAT * FEAT * 3) return;
+  int c = idx % 3, cell = idx / 3;
+  int j = cell % FEAT, i = (cell / FEAT) % FEAT, n = cell / (FEAT * FEAT);
+  uvs[idx] = resize8(uv, n, i, j, 3, c);
+}
+
+// reg[N,256,256,6] -> off[N,32,32,4] = 32 * resize(reg)[(0,1) of reg_in, (0,1) of reg_out]
+// (model_with_TSM.py:207; warp.py:137-139).  NaN offsets (generate_offset_map does no nan_to_num,
+// warp.py:194-213) are defined as 0 here.
+__global__ void reg_small_kernel(const float* __restrict__ reg, float* __restrict__ off, int n_img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * FEAT * FEAT * 4) return;
+  int k = idx & 3, cell = idx >> 2;
+  int j = cell % FEAT, i = (cell / FEAT) % FEAT, n = cell / (FEAT * FEAT);
+  int c = (k < 2) ? k : k + 1;          // channels 0,1,3,4
+  float v = resize8(reg, n, i, j, 6, c) * (float)FEAT;
+  off[idx] = (v == v) ? v : 0.f;
+}
+
+// First-half res-stack input: write uv at channel uv_off and zero [z0, z1)   (model.py:238;
+// model_with_TSM.py:272).  One thread per (pixel, channel of the written range).
+template <typename T>
+__global__ void assemble_uv_kernel(T* __restrict__ x, int ld, const float* __restrict__ uvs, int uv_off,
+                                   int z0, int z1, int n_pix) {
+  int span = 3 + (z1 - z0);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_pix * span) return;
+  int k = (int)(idx % span);
+  size_t pix = (size_t)(idx / span);
+  if (k < 3) stf<T>(x, pix * ld + uv_off + k, uvs[pix * 3 + k]);
+  else stf<T>(x, pix * ld + z0 + (k - 3), 0.f);
+}
+
+// model.py:246-252: mask = tanh(conv2(y)); con = conv3(y); gs = grey*(1+mask)+con; dif = gs-grey;
+// mask22 = [relu(mask), 0, relu(-mask)].  raw[...,0] = conv2(y), raw[...,1] = conv3(y) (bias included).
+// Also writes gs as channel `gs_c` of the clr_conv1 input buffer and zeroes its pad channels.
+template <typename T>
+__global__ void compose_kernel(const float* __restrict__ raw, const float* __restrict__ img,
+                               float* __restrict__ gs_out, float* __restrict__ mask22_out,
+                               float* __restrict__ difgs, T* __restrict__ cat1, int cat_ld, int gs_c,
+                               long long n_pix) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  float2 r = *reinterpret_cast<const float2*>(raw + 2 * p);
+  float mask = tanhf(r.x), con = r.y;
+  float g = img[3 * p] * kGrayR + img[3 * p + 1] * kGrayG + img[3 * p + 2] * kGrayB;
+  float gs = g * (1.f + mask) + con;
+  difgs[p] = gs - g;
+  if (gs_out) gs_out[p] = gs;
+  if (mask22_out) {
+    mask22_out[3 * p] = fmaxf(mask, 0.f);
+    mask22_out[3 * p + 1] = mask * 0.f;
+    mask22_out[3 * p + 2] = fmaxf(-mask, 0.f);
+  }
+  stf<T>(cat1, (size_t)p * cat_ld + gs_c, gs);
+  for (int c = gs_c + 1; c < cat_ld; ++c) stf<T>(cat1, (size_t)p * cat_ld + c, 0.f);
+}
+
+// model.py:256-259 / model_with_TSM.py:290-294: bmask = resize(dif,[32,32]) > 0.1 (strict);
+// x_hole = x*(1-bmask); out = [x_hole (cx ch) | bmask | ... | uv at uv_off]; zero [z0,z1).
+// One warp per 32x32 cell.
+template <typename T>
+__global__ void hole_kernel(const float* __restrict__ difgs, const T* __restrict__ xa, int lda,
+                            T* __restrict__ xb, int ldb, int cx, const float* __restrict__ uvs, int uv_off,
+                            int z0, int z1, float* __restrict__ bmask_out, float* __restrict__ difsmall_out,
+                            int n_cells) {
+  int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (cell >= n_cells) return;
+  int j = cell % FEAT, i = (cell / FEAT) % FEAT, n = cell / (FEAT * FEAT);
+  float d = resize8(difgs, n, i, j, 1, 0);
+  float bm = d > kHoleThr ? 1.f : 0.f;
+  float keep = 1.f - bm;
+  const T* src = xa + (size_t)cell * lda;
+  T* dst = xb + (size_t)cell * ldb;
+  for (int c = lane; c < cx; c += 32) stf<T>(dst, c, ldf<T>(src, c) * keep);
+  if (lane == 0) {
+    stf<T>(dst, cx, bm);
+    bmask_out[cell] = bm;
+    difsmall_out[cell] = d;
+  }
+  if (lane < 3) stf<T>(dst, uv_off + lane, uvs[(size_t)cell * 3 + lane]);
+  for (int c = z0 + lane; c < z1; c += 32) stf<T>(dst, c, 0.f);
+}
+
+// ---- ShareLayer (model_with_TSM.py:204-229) ---------------------------------------------------
+// tf_batch_map_coordinates (warp.py:71-115): clip coords to [0, s-1], corners floor/ceil,
+// v_t = lt + (rt-lt)*o0 ; v_b = lb + (rb-lb)*o0 ; out = v_t + (v_b-v_t)*o1, with coordinate 0 = row.
+struct WarpTap { int lt, rt, lb, rb; float o0, o1; };
+__device__ __forceinline__ WarpTap warp_tap(float off0, float off1, int i, int j) {
+  float c0 = fminf(fmaxf(off0 + (float)i, 0.f), (float)(FEAT - 1));
+  float c1 = fminf(fmaxf(off1 + (float)j, 0.f), (float)(FEAT - 1));
+  float f0 = floorf(c0), f1 = floorf(c1);
+  int r0 = (int)f0, r1 = (int)ceilf(c0), q0 = (int)f1, q1 = (int)ceilf(c1);
+  WarpTap w;
+  w.lt = r0 * FEAT + q0;      // (floor0, floor1)
+  w.rb = r1 * FEAT + q1;      // (ceil0, ceil1)
+  w.lb = r0 * FEAT + q1;      // warp.py:88 (lt[0], rb[1])
+  w.rt = r1 * FEAT + q0;      // warp.py:89 (rb[0], lt[1])
+  w.o0 = c0 - f0;
+  w.o1 = c1 - f1;
+  return w;
+}
+__device__ __forceinline__ float warp_mix(float lt, float rt, float lb, float rb, float o0, float o1) {
+  float vt = lt + (rt - lt) * o0;
+  float vb = lb + (rb - lb) * o0;
+  return vt + (vb - vt) * o1;
+}
+
+// sh[chunk][pix][0:C] = max_f warp_in(x_f), sh[chunk][pix][C:2C] = mean_f warp_in(x_f)
+template <typename T>
+__global__ void share_reduce_kernel(const T* __restrict__ x, int ld, int C, const float* __restrict__ off,
+                                    int frame, float* __restrict__ sh) {
+  int pix = blockIdx.x % (FEAT * FEAT), chunk = blockIdx.x / (FEAT * FEAT);
+  int i = pix / FEAT, j = pix % FEAT;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mx = -INFINITY, sum = 0.f;
+    for (int f = 0; f < frame; ++f) {
+      size_t n = (size_t)chunk * frame + f;
+      const float* o = off + (n * FEAT * FEAT + pix) * 4;
+      WarpTap w = warp_tap(o[0], o[1], i, j);
+      const T* b = x + n * FEAT * FEAT * ld + c;
+      float v = warp_mix(ldf<T>(b, (size_t)w.lt * ld), ldf<T>(b, (size_t)w.rt * ld),
+                         ldf<T>(b, (size_t)w.lb * ld), ldf<T>(b, (size_t)w.rb * ld), w.o0, w.o1);
+      mx = fmaxf(mx, v);
+      sum += v;
+    }
+    float* d = sh + ((size_t)chunk * FEAT * FEAT + pix) * 2 * C;
+    d[c] = mx;
+    d[C + c] = sum / (float)frame;
+  }
+}
+
+// x[n][pix][coff + c] = warp_out(sh[chunk])[pix][c], c < 2C
+template <typename T>
+__global__ void share_out_kernel(const float* __restrict__ sh, int C2, const float* __restrict__ off, int frame,
+                                 T* __restrict__ x, int ld, int coff) {
+  int pix = blockIdx.x % (FEAT * FEAT);
+  size_t n = blockIdx.x / (FEAT * FEAT);
+  size_t chunk = n / frame;
+  int i = pix / FEAT, j = pix % FEAT;
+  const float* o = off + (n * FEAT * FEAT + pix) * 4;
+  WarpTap w = warp_tap(o[2], o[3], i, j);
+  const float* b = sh + chunk * FEAT * FEAT * C2;
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    float v = warp_mix(b[(size_t)w.lt * C2 + c], b[(size_t)w.rt * C2 + c], b[(size_t)w.lb * C2 + c],
+                       b[(size_t)w.rb * C2 + c], w.o0, w.o1);
+    stf<T>(x, (n * FEAT * FEAT + pix) * ld + coff + c, v);
+  }
+}
+
+// share == False: x_share = concat([x, x])  (model_with_TSM.py:227)
+template <typename T>
+__global__ void share_dup_kernel(T* __restrict__ x, int ld, int C, int coff, long long n_pix) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * C) return;
+  size_t pix = (size_t)(idx / C);
+  int c = (int)(idx % C);
+  T v = x[pix * ld + c];
+  x[pix * ld + coff + c] = v;
+  x[pix * ld + coff + C + c] = v;
+}
+
+// Pass-through channels of the ResBottleneck output: out[c] = leaky(x[c]) for c in [c0, c1)
+// (model.py:109-113: y zero-extended, relu3(x + 0)).
+template <typename T>
+__global__ void res_tail_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int c0, int c1,
+                                long long n_pix) {
+  int span = c1 - c0;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * span) return;
+  size_t pix = (size_t)(idx / span);
+  int c = c0 + (int)(idx % span);
+  stf<T>(out, pix * ldo + c, leaky(ldf<T>(x, pix * ldx + c)));
+}
+
+// clr_conv2 (1x1 16->16 + BN + LeakyReLU), clr_conv3 (1x1 16->3) and the final
+// dif = grey(con_rgb) - grey(inputs)   (model.py:268-269, 288).  w2[16][16] (in,out), w3[16][3].
+template <typename T>
+__global__ void clr_tail_kernel(const T* __restrict__ c16, int ld, const float* __restrict__ w2,
+                                const float* __restrict__ b2, const float* __restrict__ w3,
+                                const float* __restrict__ b3, const float* __restrict__ img,
+                                float* __restrict__ rgb_out, float* __restrict__ dif_out, long long n_pix) {
+  __shared__ float sw2[256], sb2[16], sw3[48], sb3[3];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sw2[i] = w2[i];
+  if (threadIdx.x < 16) sb2[threadIdx.x] = b2[threadIdx.x];
+  if (threadIdx.x < 48) sw3[threadIdx.x] = w3[threadIdx.x];
+  if (threadIdx.x < 3) sb3[threadIdx.x] = b3[threadIdx.x];
+  __syncthreads();
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  float a[16], h[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = ldf<T>(c16, (size_t)p * ld + c);
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    float s = sb2[o];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s = fmaf(a[c], sw2[c * 16 + o], s);
+    h[o] = leaky(s);
+  }
+  float rgb[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    float s = sb3[o];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s = fmaf(h[c], sw3[c * 3 + o], s);
+    rgb[o] = s;
+  }
+  if (rgb_out) {
+    rgb_out[3 * p] = rgb[0];
+    rgb_out[3 * p + 1] = rgb[1];
+    rgb_out[3 * p + 2] = rgb[2];
+  }
+  if (dif_out) {
+    float g1 = rgb[0] * kGrayR + rgb[1] * kGrayG + rgb[2] * kGrayB;
+    float g0 = img[3 * p] * kGrayR + img[3 * p + 1] * kGrayG + img[3 * p + 2] * kGrayB;
+    dif_out[p] = g1 - g0;
+  }
+}
+
+// train_test_GSC.py:808-809: mask_pred = dif*face ; rgb = clip(rgb, 0, 1)
+__global__ void caller_glue_kernel(const float* __restrict__ rgb, const float* __restrict__ dif,
+                                   const float* __restrict__ face, float* __restrict__ rgb_c,
+                                   float* __restrict__ mask_pred, long long n_pix) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  if (mask_pred) mask_pred[p] = dif[p] * face[p];
+  if (rgb_c) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb_c[3 * p + c] = fminf(fmaxf(rgb[3 * p + c], 0.f), 1.f);
+  }
+}
+
+// train_test_GSC.py:711,718: out = clip(pred*m + inp*(1-m), 0, 1)
+__global__ void composite_kernel(const float* __restrict__ pred, const float* __restrict__ inp,
+                                 const float* __restrict__ m, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float mm = m[i];
+    out[i] = fminf(fmaxf(pred[i] * mm + inp[i] * (1.f - mm), 0.f), 1.f);
+  }
+}
+
+// debug: dense fp32 copy of channels [coff, coff+C) of an activation buffer
+template <typename T>
+__global__ void slice_to_f32_kernel(const T* __restrict__ x, int ld, int coff, int C, float* __restrict__ out,
+                                    long long n_pix) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * C) return;
+  size_t pix = (size_t)(idx / C);
+  int c = (int)(idx % C);
+  out[idx] = ldf<T>(x, pix * ld + coff + c);
+}
+
+}  // namespace bsr

@@ -1,0 +1,244 @@
+"""Drop-in ``Generator`` for the reference's Keras model, backed by libbsr.so through ctypes.
+
+Mirrors the call signatures of /root/reference/model.py:228 (``gen(inputs, uv, reg, chuck, training)``)
+and /root/reference/model_with_TSM.py:261 (``gen(inputs, uv, reg, frame, share, chuck, training)``) and
+returns the same 4-tuple ``(gs, con_rgb, mask22, dif)``.  PyTorch is only a device-memory container:
+CUDA tensors go straight to the C ABI as pointers; NumPy arrays take the host path
+(``bsr_forward_*_host``: H2D copy, forward, D2H copy).  There is no CPU fallback: if libbsr.so is
+missing or no B200 is present this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import convert
+from .weights import VARIANTS, random_weights
+
+_LIB = None
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsr.so")
+PRECISIONS = ("bf16", "fp32check")
+IMG = 256
+
+_F = ctypes.POINTER(ctypes.c_float)
+_SYMBOLS = {
+    "bsr_version": (ctypes.c_char_p, []),
+    "bsr_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bsr_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "bsr_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "bsr_load_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "bsr_forward_gsc": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 5),
+    "bsr_forward_tsm": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5),
+    "bsr_forward_gsc_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "bsr_forward_tsm_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4),
+    "bsr_caller_glue": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3),
+    "bsr_composite": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t] + [ctypes.c_void_p] * 2),
+    "bsr_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "bsr_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "bsr_debug_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "bsr_layer_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
+}
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen libbsr.so and bind every symbol of include/bsr.h; raises if anything is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class BsrError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Generator:
+    """B200 replacement of ``Generator()`` (train_test_GSC.py:120 / train_with_TSM.py).
+
+    variant   'gsc' (model.py) or 'tsm' (model_with_TSM.py)
+    precision 'bf16' (tcgen05 product path) or 'fp32check' (CUDA-core check mode)
+    """
+
+    def __init__(self, variant: str = "gsc", precision: str = "bf16", device: int = 0, micro_batch: int = 16,
+                 weights: Optional[Dict[str, np.ndarray]] = None, seed: Optional[int] = None):
+        if variant not in VARIANTS:
+            raise ValueError("variant must be one of %r" % (VARIANTS,))
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %r" % (PRECISIONS,))
+        self.variant, self.precision, self.device = variant, precision, int(device)
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.bsr_create(VARIANTS.index(variant), PRECISIONS.index(precision), self.device, int(micro_batch),
+                                  ctypes.byref(h))
+        if rc != 0:
+            raise BsrError("bsr_create failed (%d): %s" % (rc, self._lib.bsr_last_error(None).decode()))
+        self._h = h
+        if weights is not None:
+            self.load_weights(weights)
+        elif seed is not None:
+            self.load_weights(random_weights(variant, seed))
+
+    # -- weights ---------------------------------------------------------------------------
+    def load_weights(self, weights: Dict[str, np.ndarray]) -> None:
+        blob = convert.build_blob(self.variant, weights)
+        self.load_blob(blob)
+
+    def load_blob(self, blob: bytes) -> None:
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        self._check(self._lib.bsr_load_weights(self._h, buf, len(blob)))
+
+    def load_checkpoint(self, index_path: str) -> None:
+        """``checkpoint.restore(latest).expect_partial()`` (train_test_GSC.py:362-365) without TF."""
+        self.load_blob(convert.convert_checkpoint(index_path, self.variant))
+
+    # -- forward ---------------------------------------------------------------------------
+    def __call__(self, inputs, uv, reg=None, frame: Optional[int] = None, share=True, chuck: int = 1,
+                 training: bool = False, want=("gs", "con_rgb", "mask22", "dif")):
+        if training:
+            raise BsrError("training=True is not supported: this is the inference forward only")
+        share = bool(share.item() if hasattr(share, "item") else share)
+        if isinstance(inputs, np.ndarray):
+            return self._call_host(inputs, uv, reg, frame, share, want)
+        import torch
+        if not (inputs.is_cuda and uv.is_cuda):
+            raise BsrError("pass CUDA tensors (device path) or NumPy arrays (host path)")
+        n = self._check_shapes(tuple(inputs.shape), tuple(uv.shape), None if reg is None else tuple(reg.shape), frame)
+        inputs = inputs.contiguous().float()
+        uv = uv.contiguous().float()
+        dev = inputs.device
+        out = {
+            "gs": torch.empty((n, IMG, IMG, 1), device=dev) if "gs" in want else None,
+            "con_rgb": torch.empty((n, IMG, IMG, 3), device=dev) if "con_rgb" in want else None,
+            "mask22": torch.empty((n, IMG, IMG, 3), device=dev) if "mask22" in want else None,
+            "dif": torch.empty((n, IMG, IMG, 1), device=dev) if "dif" in want else None,
+        }
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if self.variant == "gsc":
+            rc = self._lib.bsr_forward_gsc(self._h, _ptr(inputs), _ptr(uv), n, _ptr(out["gs"]), _ptr(out["con_rgb"]),
+                                           _ptr(out["mask22"]), _ptr(out["dif"]), stream)
+        else:
+            reg = reg.contiguous().float()
+            rc = self._lib.bsr_forward_tsm(self._h, _ptr(inputs), _ptr(uv), _ptr(reg), n // frame, frame, int(share),
+                                           _ptr(out["gs"]), _ptr(out["con_rgb"]), _ptr(out["mask22"]), _ptr(out["dif"]),
+                                           stream)
+        self._check(rc)
+        return out["gs"], out["con_rgb"], out["mask22"], out["dif"]
+
+    def _check_shapes(self, s_img, s_uv, s_reg, frame):
+        if len(s_img) != 4 or s_img[1:] != (IMG, IMG, 3):
+            raise ValueError("inputs must be [N,256,256,3] NHWC, got %r" % (s_img,))
+        if s_uv != s_img:
+            raise ValueError("uv must be [N,256,256,3], got %r" % (s_uv,))
+        n = s_img[0]
+        if n <= 0:
+            raise ValueError("empty batch")
+        if self.variant == "tsm":
+            if frame is None or frame <= 0:
+                raise ValueError("TSM variant needs frame > 0")
+            if s_reg != (n, IMG, IMG, 6):
+                raise ValueError("reg must be [N,256,256,6], got %r" % (s_reg,))
+            if n % frame:
+                raise ValueError("batch %d is not a multiple of frame %d (model_with_TSM.py:218)" % (n, frame))
+        return n
+
+    def _call_host(self, inputs, uv, reg, frame, share, want):
+        n = self._check_shapes(inputs.shape, uv.shape, None if reg is None else reg.shape, frame)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        inputs, uv = f32(inputs), f32(uv)
+        out = {
+            "gs": np.empty((n, IMG, IMG, 1), np.float32) if "gs" in want else None,
+            "con_rgb": np.empty((n, IMG, IMG, 3), np.float32) if "con_rgb" in want else None,
+            "mask22": np.empty((n, IMG, IMG, 3), np.float32) if "mask22" in want else None,
+            "dif": np.empty((n, IMG, IMG, 1), np.float32) if "dif" in want else None,
+        }
+        p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        if self.variant == "gsc":
+            rc = self._lib.bsr_forward_gsc_host(self._h, p(inputs), p(uv), n, p(out["gs"]), p(out["con_rgb"]),
+                                                p(out["mask22"]), p(out["dif"]))
+        else:
+            reg = f32(reg)
+            rc = self._lib.bsr_forward_tsm_host(self._h, p(inputs), p(uv), p(reg), n // frame, frame, int(share),
+                                                p(out["gs"]), p(out["con_rgb"]), p(out["mask22"]), p(out["dif"]))
+        self._check(rc)
+        return out["gs"], out["con_rgb"], out["mask22"], out["dif"]
+
+    def forward_host_ptrs(self, img_ptr, uv_ptr, reg_ptr, n, frame, share, gs_ptr, rgb_ptr, m22_ptr, dif_ptr):
+        """Host path on raw (e.g. pinned) pointers; used by bench.py's e2e leg."""
+        v = lambda x: None if not x else ctypes.c_void_p(x)
+        if self.variant == "gsc":
+            rc = self._lib.bsr_forward_gsc_host(self._h, v(img_ptr), v(uv_ptr), n, v(gs_ptr), v(rgb_ptr), v(m22_ptr), v(dif_ptr))
+        else:
+            rc = self._lib.bsr_forward_tsm_host(self._h, v(img_ptr), v(uv_ptr), v(reg_ptr), n // frame, frame, int(share),
+                                                v(gs_ptr), v(rgb_ptr), v(m22_ptr), v(dif_ptr))
+        self._check(rc)
+
+    # -- caller glue (train_test_GSC.py:808-809, 711-718) ------------------------------------
+    def caller_glue(self, con_rgb, dif, face):
+        import torch
+        n = con_rgb.shape[0]
+        rgb_c, mask_pred = torch.empty_like(con_rgb), torch.empty_like(dif)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(con_rgb.device).cuda_stream)
+        self._check(self._lib.bsr_caller_glue(self._h, _ptr(con_rgb.contiguous()), _ptr(dif.contiguous()),
+                                              _ptr(face.contiguous().float()), n, _ptr(rgb_c), _ptr(mask_pred), stream))
+        return rgb_c, mask_pred
+
+    def composite(self, pred, inp, m):
+        import torch
+        out = torch.empty_like(pred)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(pred.device).cuda_stream)
+        self._check(self._lib.bsr_composite(self._h, _ptr(pred.contiguous()), _ptr(inp.contiguous()),
+                                            _ptr(m.expand_as(pred).contiguous()), pred.numel(), _ptr(out), stream))
+        return out
+
+    # -- introspection -----------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.bsr_launch_count(self._h))
+
+    def workspace_bytes(self) -> int:
+        return int(self._lib.bsr_workspace_bytes(self._h))
+
+    def debug_read(self, name: str) -> np.ndarray:
+        n = ctypes.c_size_t()
+        self._check(self._lib.bsr_debug_read(self._h, name.encode(), None, 0, ctypes.byref(n)))
+        out = np.empty(n.value, np.float32)
+        self._check(self._lib.bsr_debug_read(self._h, name.encode(), out.ctypes.data_as(ctypes.c_void_p), n.value,
+                                             ctypes.byref(n)))
+        return out
+
+    def layer_times(self):
+        names = (ctypes.c_char_p * 512)()
+        ms = (ctypes.c_float * 512)()
+        k = self._lib.bsr_layer_times(self._h, names, ms, 512)
+        return [(names[i].decode(), float(ms[i])) for i in range(k)]
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BsrError("libbsr error %d: %s" % (rc, self._lib.bsr_last_error(self._h).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bsr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,97 @@
+/*
+ * bsr.h — C ABI of libbsr.so: B200 (sm_100a) forward pass of the BlindShadowRemoval generator.
+ *
+ * The reference has no plugin/FFI layer; the seam this library replaces is the Keras model call
+ *     gs, rgb, mask22, dif = self.gen(img, uv, reg, chuck=k, training=False)
+ * (/root/reference/train_test_GSC.py:422, 807, 871, 901 -> /root/reference/model.py:228-290) and
+ *     self.gen(img, uv, reg, frame=F, share=tf.constant(True), chuck=1, training=False)
+ * (/root/reference/train_with_TSM.py:433, 676, 718 -> /root/reference/model_with_TSM.py:261-325),
+ * plus the element-wise caller glue next to those calls.  Plain pointers and sizes only; all tensors
+ * are NHWC float32 at the boundary exactly like the reference's tensors.  Every function returns 0 on
+ * success or a negative BSR_E* code; bsr_last_error() gives the message.  A handle is bound to one
+ * device and is not thread-safe (one handle per GPU per process, as the reference drives one model
+ * from one Python thread).  forward_* calls are asynchronous on the given CUDA stream and perform no
+ * allocation; training=True has no equivalent here (inference only).
+ */
+#ifndef BSR_H_
+#define BSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsr_handle bsr_handle;
+
+enum { BSR_VARIANT_GSC = 0, BSR_VARIANT_TSM = 1 };
+/* BF16: bf16 activations/weights, tcgen05 tensor-core convs, fp32 accumulation (the product path).
+ * FP32CHECK: fp32 activations/weights on CUDA cores — the check mode north_star asks for (<=1e-4). */
+enum { BSR_PRECISION_BF16 = 0, BSR_PRECISION_FP32CHECK = 1 };
+enum {
+  BSR_OK = 0, BSR_EINVAL = -1, BSR_ECUDA = -2, BSR_ENOMEM = -3, BSR_ESTATE = -4, BSR_EUNSUPPORTED = -5
+};
+
+#define BSR_IMG 256   /* Config.IMG_SIZE, train_test_GSC.py:31 */
+#define BSR_FEAT 32   /* bottleneck resolution after three stride-2 convs, model.py:231-234 */
+
+const char* bsr_version(void);
+
+/* Replaces `self.gen = Generator()` (train_test_GSC.py:120).  micro_batch = images resident in the
+ * workspace at once (forward loops over larger batches); for TSM it must be >= frame. */
+int bsr_create(int variant, int precision, int device, int micro_batch, bsr_handle** out);
+int bsr_destroy(bsr_handle* h);
+const char* bsr_last_error(const bsr_handle* h);   /* h may be NULL: last error of a failed create */
+
+/* Replaces `checkpoint.restore(...).expect_partial()` (train_test_GSC.py:362-365): `blob` is the
+ * output of blindshadowremoval_b200.convert (BN-folded canonical fp32 layers); the library packs it
+ * into its device layouts (bf16, K-major, channel-padded).  Host pointer. */
+int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes);
+
+/* Generator.call of model.py:228-290.  Device pointers, NHWC fp32: img[n,256,256,3], uv[n,256,256,3];
+ * outputs gs[n,256,256,1], rgb[n,256,256,3], mask22[n,256,256,3], dif[n,256,256,1]; any output may be
+ * NULL (every inference caller discards gs and mask22).  `reg`/`chuck` of the reference signature are
+ * ignored by model.py and therefore absent. */
+int bsr_forward_gsc(bsr_handle* h, const float* img, const float* uv, int n,
+                    float* gs, float* rgb, float* mask22, float* dif, void* cuda_stream);
+
+/* Generator.call of model_with_TSM.py:261-325: n = n_chunks*frame images, reg[n,256,256,6]
+ * (= [reg_in(3) | reg_out(3)], only channels 0:2 of each half are used, warp.py:139); temporal sharing
+ * acts inside each group of `frame` consecutive images; share=0 selects concat([x,x]) (:227-228). */
+int bsr_forward_tsm(bsr_handle* h, const float* img, const float* uv, const float* reg,
+                    int n_chunks, int frame, int share,
+                    float* gs, float* rgb, float* mask22, float* dif, void* cuda_stream);
+
+/* Same as the two calls above but with HOST buffers: copies inputs H2D, runs, copies the non-NULL
+ * outputs D2H and synchronises the stream.  This is what a drop-in replacement of the eager Keras
+ * call costs end to end (the reference feeds host NumPy batches, dataset.py:296-302). */
+int bsr_forward_gsc_host(bsr_handle* h, const float* img, const float* uv, int n,
+                         float* gs, float* rgb, float* mask22, float* dif);
+int bsr_forward_tsm_host(bsr_handle* h, const float* img, const float* uv, const float* reg,
+                         int n_chunks, int frame, int share,
+                         float* gs, float* rgb, float* mask22, float* dif);
+
+/* Caller glue, train_test_GSC.py:808-809 / 872-873 / 902-903 (TSM: train_with_TSM.py:677-678):
+ * mask_pred = dif*face ; rgb_clipped = clip(rgb, 0, 1).  Device pointers; in-place allowed. */
+int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n,
+                    float* rgb_clipped, float* mask_pred, void* cuda_stream);
+/* Composite, train_test_GSC.py:711,718: out = clip(pred*m + inp*(1-m), 0, 1) over n_elems floats. */
+int bsr_composite(bsr_handle* h, const float* pred, const float* inp, const float* m, size_t n_elems,
+                  float* out, void* cuda_stream);
+
+/* Introspection for tests/bench. */
+int bsr_launch_count(const bsr_handle* h);          /* kernels launched by the last forward call */
+size_t bsr_workspace_bytes(const bsr_handle* h);
+/* Copy a named intermediate of the LAST micro-batch to host as fp32 (dense NHWC, logical channels).
+ * Names: x1 x2 x3 x_in0 res0..res5 up1 up2 up3 x_in3 clr_up1 clr_up2 clr_up3 bmask dif_small.
+ * Returns the element count in *n_elems (call with host_out=NULL to query). */
+int bsr_debug_read(bsr_handle* h, const char* name, float* host_out, size_t capacity, size_t* n_elems);
+/* Per-layer device time of the last forward when BSR_PROFILE=1 was set at create time: fills up to
+ * `capacity` entries; names are static strings. Returns the number of entries. */
+int bsr_layer_times(const bsr_handle* h, const char** names, float* ms, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* BSR_H_ */
