@@ -55,7 +55,7 @@ struct bsr_handle {
   size_t arena_bytes = 0;
   char *X1 = nullptr, *CAT3 = nullptr, *CAT2 = nullptr, *XA = nullptr, *XB = nullptr, *T1 = nullptr, *T2 = nullptr,
        *Y = nullptr, *QK = nullptr, *VT = nullptr, *O = nullptr, *UP3 = nullptr, *F1 = nullptr, *F2 = nullptr,
-       *CAT1 = nullptr, *C16 = nullptr;
+       *CAT1 = nullptr, *C16 = nullptr, *PIMG = nullptr;
   float *RAW = nullptr, *DIFGS = nullptr, *UVS = nullptr, *OFF = nullptr, *BMASK = nullptr, *DIFSMALL = nullptr,
         *SH = nullptr;
   int* errflag = nullptr;    // device flag set by kernels whose mbarrier wait timed out
@@ -298,8 +298,19 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
   int rc;
   const long long px256 = (long long)n * IMG * IMG, px32 = (long long)n * FEAT * FEAT;
   // ---- encoder (model.py:230-233)
-  ConvCall cv1{"conv1", img, 3, 0, true, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1)};
-  if ((rc = run_conv(h, st, cv1, n))) return rc;
+  if (h->precision == BSR_PRECISION_BF16 && !h->force_direct && h->layers["conv1"].tc.ready) {
+    {
+      Step step(h, st, "pack_img");
+      long long rows = (long long)n * IMG, tot = rows * (IMG + 8);
+      pack_img_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(img, (bf16*)h->PIMG, rows);
+      h->launches++;
+    }
+    ConvCall cv1{"conv1", h->PIMG, 8, 0, false, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1)};
+    if ((rc = run_conv(h, st, cv1, n))) return rc;
+  } else {
+    ConvCall cv1{"conv1", img, 3, 0, true, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1)};
+    if ((rc = run_conv(h, st, cv1, n))) return rc;
+  }
   debug_capture(h, st, "x1", h->X1, 32, 0, 32, px256);
   ConvCall d1{"down1", h->X1, 32, 0, false, IMG, IMG, 2, epi(h->CAT3, 128, 64, 64, 1)};
   if ((rc = run_conv(h, st, d1, n))) return rc;
@@ -537,7 +548,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {&h->T2, mb * 1024 * 128 * es}, {&h->Y, mb * 1024 * 264 * es}, {&h->QK, mb * 1024 * 256 * es},
       {&h->VT, mb * 1024 * 128 * es}, {&h->O, mb * 1024 * 128 * es}, {&h->UP3, mb * IMG * IMG * 64 * es},
       {&h->F1, mb * 64 * 64 * 128 * es}, {&h->F2, mb * 128 * 128 * 96 * es}, {&h->CAT1, mb * IMG * IMG * 72 * es},
-      {&h->C16, mb * IMG * IMG * 16 * es},
+      {&h->C16, mb * IMG * IMG * 16 * es}, {&h->PIMG, mb * IMG * (IMG + 8) * 8 * 2},
       {(char**)&h->RAW, mb * IMG * IMG * 2 * 4}, {(char**)&h->DIFGS, mb * IMG * IMG * 4},
       {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
       {(char**)&h->DIFSMALL, mb * 1024 * 4},

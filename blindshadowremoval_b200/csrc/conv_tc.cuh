@@ -33,6 +33,7 @@ constexpr int TC_MAX_TAPS = 49;
 struct TcWeights {
   bool ready = false;
   int kh = 0, kw = 0, cin = 0, cout = 0, transposed = 0;
+  int row_packed = 0;     // conv1: input pre-packed as [N][H][W+8][8] bf16, one k-block = the 7(+1) pixels x 8 ch window
   int cin_pad = 0;        // multiple of 64
   int bn = 0;             // UMMA N per tile
   int n_tiles = 0;
@@ -168,29 +169,42 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const bool ok = mbar_wait(bar_tmem, 0, p.errflag, 3);
     tc_fence_after();
     if (ok) {
-      const bool fast = e.out_mode == OUT_T && (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
+      const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
+      const int s_img = gy * p.OW * p.out_scale + gx;      // OUT_QKV only (out_scale 1): pixel index inside the image
       for (int j = 0; j < p.bn; j += 16) {
         const int c = ntile * p.bn + j;
         if (c >= e.out_c) break;               // warp-uniform
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);
-        if (fast && c + 16 <= e.out_c) {
+        if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);      // bias is zero-padded past cout
           if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
           if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
           if (e.act) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
           }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-          uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + pix * e.out_ld + e.out_coff + c);
-          dst[0] = o0;
-          dst[1] = o1;
+          if (e.out_mode == OUT_F32) {
+            float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = v[i];
+          } else if (e.out_mode == OUT_QKV && c >= 256) {
+            // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes of a warp write consecutive tokens
+            bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + s_img;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
+          } else {
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+            o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+            o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+            o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+            const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
+            uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
+            dst[0] = o0;
+            dst[1] = o1;
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
@@ -227,7 +241,7 @@ inline uint16_t f32_to_bf16_bits(float f) {
 inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, int kw, int cin, int cout, int transposed,
                             const std::vector<float>& w, TcWeights* out, std::string* why) {
   why->clear();
-  if (name == "conv1" || name == "clr_conv2" || name == "clr_conv3") return false;   // fp32 3-channel input / fused tail
+  if (name == "clr_conv2" || name == "clr_conv3") return false;   // fused into the colour tail kernel
   if (const char* dis = getenv("BSR_TC_DISABLE")) {
     std::string d = std::string(",") + dis + ",";
     if (d.find("," + name + ",") != std::string::npos) return false;
@@ -238,6 +252,29 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   }
   TcWeights& t = *out;
   t.kh = kh; t.kw = kw; t.cin = cin; t.cout = cout; t.transposed = transposed;
+  if (name == "conv1") {
+    // 7x7 conv over 3 channels (model.py:203): K per filter ROW = 7 taps x 8 (3 real + 5 zero) channels + one
+    // zero-weight pixel = 64 = one 128-byte swizzle row, fetched as an overlapping window of the packed image.
+    if (kh != 7 || kw != 7 || cin > 8 || transposed) { *why = "conv1 must be 7x7 with <= 8 input channels"; return false; }
+    t.row_packed = 1; t.cin_pad = 64; t.taps = 7; t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1;
+    for (int a = 0; a < 7; ++a) { t.tap_kh[a] = (int8_t)a; t.tap_kw[a] = 3; }
+    t.phase_begin[0] = 0;
+    for (int i = 1; i < 5; ++i) t.phase_begin[i] = 7;
+    const size_t K = 7 * 64, rows = t.bn;
+    std::vector<uint16_t> host(rows * K, 0);
+    for (int a = 0; a < 7; ++a)
+      for (int b = 0; b < 7; ++b)
+        for (int c = 0; c < cin; ++c)
+          for (int o = 0; o < cout; ++o)
+            host[(size_t)o * K + a * 64 + b * 8 + c] = f32_to_bf16_bits(w[((size_t)(a * 7 + b) * cin + c) * cout + o]);
+    if (cudaMalloc(&t.dev, host.size() * 2) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
+    if (cudaMemcpy(t.dev, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
+    uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
+    uint32_t box[2] = {TC_BK, (uint32_t)t.bn};
+    if (!tma.encode_bf16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
+    t.ready = true;
+    return true;
+  }
   t.cin_pad = (cin + 63) / 64 * 64;
   t.taps = kh * kw;
   if (t.taps > TC_MAX_TAPS) return false;
@@ -311,12 +348,19 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   for (int i = 0; i < 5; ++i) p.phase_begin[i] = t.phase_begin[i];
   p.errflag = errflag;
   if ((in_ld % 8) || (in_coff % 8)) { tma.last_error = "input channel stride/offset must be multiples of 8"; return -2; }
+  if (t.row_packed) { for (int i = 0; i < t.taps; ++i) p.dx[i] = 0; }
   TmapKey key{in, in_ld, in_coff, t.cin, H, W, n, p.in_stride, p.bw, p.bh};
   auto it = cache.find(key);
   if (it == cache.end()) {
     CUtensorMap m;
     uint64_t dims[4] = {(uint64_t)t.cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
     uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)W * in_ld * 2, (uint64_t)H * W * in_ld * 2};
+    if (t.row_packed) {
+      // packed image [N][H][W + 8][8]: window of output column x = 64 contiguous elements starting at packed
+      // pixel x (= image pixel x-3); consecutive windows overlap (dim-1 stride 16 B < dim-0 extent 128 B)
+      dims[0] = 64;
+      strides[0] = 16; strides[1] = (uint64_t)(W + 8) * 16; strides[2] = (uint64_t)H * (W + 8) * 16;
+    }
     uint32_t box[4] = {TC_BK, (uint32_t)(p.bw * p.in_stride), (uint32_t)(p.bh * p.in_stride), 1};
     uint32_t es[4] = {1, (uint32_t)p.in_stride, (uint32_t)p.in_stride, 1};
     if (!tma.encode_bf16(&m, (void*)((const bf16*)in + in_coff), 4, dims, strides, box, es)) return -3;

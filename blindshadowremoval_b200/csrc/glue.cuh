@@ -26,6 +26,25 @@ __global__ void uv_small_kernel(const float* __restrict__ uv, float* __restrict_
   uvs[idx] = resize8(uv, n, i, j, 3, c);
 }
 
+// conv1 input packing: img fp32 [N,256,256,3] -> bf16 [N][256][264][8]; packed pixel xp holds image pixel
+// xp-3 (zero outside the image, channels 3..7 zero), so the 7-tap row window of output x starts at xp = x.
+__global__ void pack_img_kernel(const float* __restrict__ img, bf16* __restrict__ out, long long n_rows) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * (IMG + 8)) return;
+  int xp = (int)(idx % (IMG + 8));
+  long long row = idx / (IMG + 8);
+  int x = xp - 3;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (x >= 0 && x < IMG) {
+    const float* s = img + (row * IMG + x) * 3;
+    __nv_bfloat162 a = __floats2bfloat162_rn(s[0], s[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(s[2], 0.f);
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+  }
+  reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
 // reg[N,256,256,6] -> off[N,32,32,4] = 32 * resize(reg)[(0,1) of reg_in, (0,1) of reg_out]
 // (model_with_TSM.py:207; warp.py:137-139).  NaN offsets (generate_offset_map does no nan_to_num,
 // warp.py:194-213) are defined as 0 here.

@@ -130,13 +130,15 @@ def test_sfw_auc_matches_to_3_decimals(G):
     gen, got = run_device(G, "tsm", "bf16", w, d, 2)
     bm = gen.debug_read("bmask").reshape(4, 32, 32, 1)
     ref = oracle("tsm", w, d, 2, bmask=bm)
-    # synthetic label: blobs where the oracle's mask_pred is high (both classes present)
+    # synthetic shadow label (SFW is not shipped): smooth random blobs, independent of the prediction
+    blobs = make_inputs(4, seed=99)["img"][..., 0]
     for i in (0, 2):
         mp_ref = ref["dif"][i] * d["face"][i]
-        label = (mp_ref > np.quantile(mp_ref, 0.8)).astype(np.float32)
+        label = (blobs[i] > np.quantile(blobs[i], 0.7)).astype(np.float32)
         a = sfw_auc(label, got["dif"][i] * d["face"][i])
         b = sfw_auc(label, mp_ref)
-        assert round(a, 3) == round(b, 3) or abs(a - b) < 5e-4, (a, b)
+        assert 0.05 < b < 0.95
+        assert abs(a - b) < 5e-4, (a, b)          # equal to 3 decimals
     gen.close()
 
 
