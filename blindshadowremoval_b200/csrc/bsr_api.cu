@@ -33,7 +33,9 @@ struct Layer {
   std::vector<float> w_host, b_host;   // canonical fp32 [tap][cin][cout], [cout]
   float* w_dev = nullptr;              // same, on device (CUDA-core kernels)
   float* b_dev = nullptr;              // bias padded with zeros to a multiple of 16 (+256 slack)
-  TcWeights tc;                        // bf16 K-major packing + tensor map (conv_tc.cuh)
+  TcWeights tc;                        // bf16 K-major packing + step program + tensor map (conv_tc.cuh)
+  TcWeights tc_phase[4];               // wide transposed convs: one plain gather conv per sub-pixel phase
+  bool phases_ready = false;
 };
 
 struct DebugBuf { float* dev = nullptr; size_t n = 0; };
@@ -56,6 +58,8 @@ struct bsr_handle {
   char *X1 = nullptr, *CAT3 = nullptr, *CAT2 = nullptr, *XA = nullptr, *XB = nullptr, *T1 = nullptr, *T2 = nullptr,
        *Y = nullptr, *QK = nullptr, *VT = nullptr, *O = nullptr, *UP3 = nullptr, *F1 = nullptr, *F2 = nullptr,
        *CAT1 = nullptr, *C16 = nullptr, *PIMG = nullptr;
+  float *GS32 = nullptr;
+  int num_sms = 148;
   float *RAW = nullptr, *DIFGS = nullptr, *UVS = nullptr, *OFF = nullptr, *BMASK = nullptr, *DIFSMALL = nullptr,
         *SH = nullptr;
   int* errflag = nullptr;    // device flag set by kernels whose mbarrier wait timed out
@@ -159,6 +163,7 @@ struct ConvCall {
   int H, W;           // input spatial size
   int stride;         // 1 or 2 (ignored for transposed)
   EpiParams e;
+  EpiExtra x;
 };
 
 template <typename TIn, typename T>
@@ -196,16 +201,32 @@ int run_conv(bsr_handle* h, cudaStream_t st, ConvCall c, int n) {
     launch_direct<float, float>(h, st, L, c, n);
     return BSR_OK;
   }
-  if (!h->force_direct && L.tc.ready && !c.in_f32) {
-    int rc = launch_conv_tc(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, h->errflag, st,
-                            &h->launches);
+  const bool special = L.tc.ready && (L.tc.kind == TC_HEADS || L.tc.kind == TC_CLR);
+  if (!h->force_direct && L.tc.ready && !c.in_f32 && (!special || c.x.gs_f32 != nullptr)) {
+    int rc = launch_conv_tc(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, c.x, -1, h->num_sms,
+                            h->errflag, st, &h->launches);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core conv %s: launch failed (%d): %s", c.layer, rc,
                              h->tma.last_error.c_str());
+    return BSR_OK;
+  }
+  if (!h->force_direct && L.phases_ready && !c.in_f32) {
+    for (int ph = 0; ph < 4; ++ph) {
+      int rc = launch_conv_tc(h->tma, L.tc_phase[ph], c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, c.x, ph,
+                              h->num_sms, h->errflag, st, &h->launches);
+      if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core conv %s phase %d: launch failed (%d): %s", c.layer, ph, rc,
+                               h->tma.last_error.c_str());
+    }
     return BSR_OK;
   }
   if (c.in_f32) launch_direct<float, bf16>(h, st, L, c, n);
   else launch_direct<bf16, bf16>(h, st, L, c, n);
   return BSR_OK;
+}
+
+EpiExtra no_extra() {
+  EpiExtra x;
+  memset(&x, 0, sizeof x);
+  return x;
 }
 
 EpiParams epi(void* out, int out_ld, int out_coff, int out_c, int act, int mode = OUT_T) {
@@ -246,23 +267,23 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   snprintf(nm[4], 32, "res%d.w", idx);
   int rc;
   const int ldy = 264;
-  ConvCall c1{nm[0], cur, ld, 0, false, FEAT, FEAT, 1, epi(h->T1, 128, 0, 128, 1)};
+  ConvCall c1{nm[0], cur, ld, 0, false, FEAT, FEAT, 1, epi(h->T1, 128, 0, 128, 1), no_extra()};
   if ((rc = run_conv(h, st, c1, n))) return rc;
-  ConvCall c2{nm[1], h->T1, 128, 0, false, FEAT, FEAT, 1, epi(h->T2, 128, 0, 128, 1)};
+  ConvCall c2{nm[1], h->T1, 128, 0, false, FEAT, FEAT, 1, epi(h->T2, 128, 0, 128, 1), no_extra()};
   if ((rc = run_conv(h, st, c2, n))) return rc;
-  ConvCall c3{nm[2], h->T2, 128, 0, false, FEAT, FEAT, 1, epi(h->Y, ldy, 0, ldy, 0)};
+  ConvCall c3{nm[2], h->T2, 128, 0, false, FEAT, FEAT, 1, epi(h->Y, ldy, 0, ldy, 0), no_extra()};
   if ((rc = run_conv(h, st, c3, n))) return rc;
   EpiParams eq = epi(h->QK, 256, 0, 384, 0, OUT_QKV);
   eq.out2 = h->VT;
   eq.spatial = FEAT * FEAT;
-  ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq};
+  ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq, no_extra()};
   if ((rc = run_conv(h, st, c4, n))) return rc;
   if ((rc = run_attention(h, st, n))) return rc;
   int oc = ld < ldy ? ld : ldy;
   EpiParams ew = epi(nxt, ld, 0, oc, 1);
   ew.res1 = h->Y; ew.res1_ld = ldy; ew.res1_c = 257;
   ew.res2 = cur; ew.res2_ld = ld; ew.res2_c = c_cur;
-  ConvCall c5{nm[4], h->O, 128, 0, false, FEAT, FEAT, 1, ew};
+  ConvCall c5{nm[4], h->O, 128, 0, false, FEAT, FEAT, 1, ew, no_extra()};
   if ((rc = run_conv(h, st, c5, n))) return rc;
   if (ld > oc) {
     Step step(h, st, "res_tail");
@@ -305,21 +326,21 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
       pack_img_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(img, (bf16*)h->PIMG, rows);
       h->launches++;
     }
-    ConvCall cv1{"conv1", h->PIMG, 8, 0, false, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1)};
+    ConvCall cv1{"conv1", h->PIMG, 8, 0, false, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1), no_extra()};
     if ((rc = run_conv(h, st, cv1, n))) return rc;
   } else {
-    ConvCall cv1{"conv1", img, 3, 0, true, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1)};
+    ConvCall cv1{"conv1", img, 3, 0, true, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1), no_extra()};
     if ((rc = run_conv(h, st, cv1, n))) return rc;
   }
   debug_capture(h, st, "x1", h->X1, 32, 0, 32, px256);
-  ConvCall d1{"down1", h->X1, 32, 0, false, IMG, IMG, 2, epi(h->CAT3, 128, 64, 64, 1)};
+  ConvCall d1{"down1", h->X1, 32, 0, false, IMG, IMG, 2, epi(h->CAT3, 128, 64, 64, 1), no_extra()};
   if ((rc = run_conv(h, st, d1, n))) return rc;
   debug_capture(h, st, "x2", h->CAT3, 128, 64, 64, (long long)n * 128 * 128);
-  ConvCall d2{"down2", h->CAT3, 128, 64, false, 128, 128, 2, epi(h->CAT2, 160, 96, 64, 1)};
+  ConvCall d2{"down2", h->CAT3, 128, 64, false, 128, 128, 2, epi(h->CAT2, 160, 96, 64, 1), no_extra()};
   if ((rc = run_conv(h, st, d2, n))) return rc;
   debug_capture(h, st, "x3", h->CAT2, 160, 96, 64, (long long)n * 64 * 64);
   const int ld1 = h->ld1, ld2 = h->ld2;
-  ConvCall d3{"down3", h->CAT2, 160, 96, false, 64, 64, 2, epi(h->XA, ld1, 0, 96, 1)};
+  ConvCall d3{"down3", h->CAT2, 160, 96, false, 64, 64, 2, epi(h->XA, ld1, 0, 96, 1), no_extra()};
   if ((rc = run_conv(h, st, d3, n))) return rc;
   // ---- uv / registration fields at 32x32 (model.py:237; warp.py:137)
   {
@@ -356,18 +377,25 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     debug_capture(h, st, res_names[i], cur, ld1, 0, c_cur, px32);
   }
   // ---- grey decoder (model.py:243-252)
-  ConvCall u1{"up1", cur, ld1, 0, false, FEAT, FEAT, 2, epi(h->CAT2, 160, 0, 96, 1)};
+  ConvCall u1{"up1", cur, ld1, 0, false, FEAT, FEAT, 2, epi(h->CAT2, 160, 0, 96, 1), no_extra()};
   if ((rc = run_conv(h, st, u1, n))) return rc;
   debug_capture(h, st, "up1", h->CAT2, 160, 0, 96, (long long)n * 64 * 64);
-  ConvCall u2{"up2", h->CAT2, 160, 0, false, 64, 64, 2, epi(h->CAT3, 128, 0, 64, 1)};
+  ConvCall u2{"up2", h->CAT2, 160, 0, false, 64, 64, 2, epi(h->CAT3, 128, 0, 64, 1), no_extra()};
   if ((rc = run_conv(h, st, u2, n))) return rc;
   debug_capture(h, st, "up2", h->CAT3, 128, 0, 64, (long long)n * 128 * 128);
-  ConvCall u3{"up3", h->CAT3, 128, 0, false, 128, 128, 2, epi(h->UP3, 64, 0, 64, 1)};
+  ConvCall u3{"up3", h->CAT3, 128, 0, false, 128, 128, 2, epi(h->UP3, 64, 0, 64, 1), no_extra()};
   if ((rc = run_conv(h, st, u3, n))) return rc;
   debug_capture(h, st, "up3", h->UP3, 64, 0, 64, px256);
-  ConvCall hd{"heads", h->UP3, 64, 0, false, IMG, IMG, 1, epi(h->RAW, 2, 0, 2, 0, OUT_F32)};
-  if ((rc = run_conv(h, st, hd, n))) return rc;
-  {
+  const bool fused_tail = h->precision == BSR_PRECISION_BF16 && !h->force_direct && h->layers["heads"].tc.ready &&
+                          h->layers["clr_conv1"].tc.ready;
+  if (fused_tail) {
+    // conv2|conv3 + tanh/grey composition fused in one kernel (model.py:246-252)
+    ConvCall hd{"heads", h->UP3, 64, 0, false, IMG, IMG, 1, epi(nullptr, 0, 0, 2, 0, OUT_F32), no_extra()};
+    hd.x.img = img; hd.x.gs_out = gs; hd.x.mask22_out = mask22; hd.x.difgs = h->DIFGS; hd.x.gs_f32 = h->GS32;
+    if ((rc = run_conv(h, st, hd, n))) return rc;
+  } else {
+    ConvCall hd{"heads", h->UP3, 64, 0, false, IMG, IMG, 1, epi(h->RAW, 2, 0, 2, 0, OUT_F32), no_extra()};
+    if ((rc = run_conv(h, st, hd, n))) return rc;
     Step step(h, st, "compose");
     compose_kernel<T><<<(unsigned)((px256 + 255) / 256), 256, 0, st>>>(h->RAW, img, gs, mask22, h->DIFGS, (T*)h->CAT1,
                                                                        72, 64, px256);
@@ -398,18 +426,26 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     debug_capture(h, st, res_names[i], cur, ld2, 0, c_cur, px32);
   }
   // ---- colour decoder (model.py:264-269, 288)
-  ConvCall k1{"clr_up1", cur, ld2, 0, false, FEAT, FEAT, 2, epi(h->F1, 128, 0, 128, 1)};
+  ConvCall k1{"clr_up1", cur, ld2, 0, false, FEAT, FEAT, 2, epi(h->F1, 128, 0, 128, 1), no_extra()};
   if ((rc = run_conv(h, st, k1, n))) return rc;
   debug_capture(h, st, "clr_up1", h->F1, 128, 0, 128, (long long)n * 64 * 64);
-  ConvCall k2{"clr_up2", h->F1, 128, 0, false, 64, 64, 2, epi(h->F2, 96, 0, 96, 1)};
+  ConvCall k2{"clr_up2", h->F1, 128, 0, false, 64, 64, 2, epi(h->F2, 96, 0, 96, 1), no_extra()};
   if ((rc = run_conv(h, st, k2, n))) return rc;
   debug_capture(h, st, "clr_up2", h->F2, 96, 0, 96, (long long)n * 128 * 128);
-  ConvCall k3{"clr_up3", h->F2, 96, 0, false, 128, 128, 2, epi(h->CAT1, 72, 0, 64, 1)};
-  if ((rc = run_conv(h, st, k3, n))) return rc;
-  debug_capture(h, st, "clr_up3", h->CAT1, 72, 0, 64, px256);
-  ConvCall kc{"clr_conv1", h->CAT1, 72, 0, false, IMG, IMG, 1, epi(h->C16, 16, 0, 16, 1)};
-  if ((rc = run_conv(h, st, kc, n))) return rc;
-  {
+  if (fused_tail) {
+    ConvCall k3{"clr_up3", h->F2, 96, 0, false, 128, 128, 2, epi(h->CAT1, 64, 0, 64, 1), no_extra()};
+    if ((rc = run_conv(h, st, k3, n))) return rc;
+    debug_capture(h, st, "clr_up3", h->CAT1, 64, 0, 64, px256);
+    // clr_conv1 (f on tensor cores + fp32 gs taps) + clr_conv2 + clr_conv3 + final dif in one kernel
+    ConvCall kc{"clr_conv1", h->CAT1, 64, 0, false, IMG, IMG, 1, epi(nullptr, 0, 0, 16, 1), no_extra()};
+    kc.x.img = img; kc.x.gs_f32 = h->GS32; kc.x.rgb_out = rgb; kc.x.dif_out = dif; kc.x.aux = h->layers["clr_conv1"].tc.aux;
+    if ((rc = run_conv(h, st, kc, n))) return rc;
+  } else {
+    ConvCall k3{"clr_up3", h->F2, 96, 0, false, 128, 128, 2, epi(h->CAT1, 72, 0, 64, 1), no_extra()};
+    if ((rc = run_conv(h, st, k3, n))) return rc;
+    debug_capture(h, st, "clr_up3", h->CAT1, 72, 0, 64, px256);
+    ConvCall kc{"clr_conv1", h->CAT1, 72, 0, false, IMG, IMG, 1, epi(h->C16, 16, 0, 16, 1), no_extra()};
+    if ((rc = run_conv(h, st, kc, n))) return rc;
     Step step(h, st, "clr_tail");
     Layer& l2 = h->layers["clr_conv2"];
     Layer& l3 = h->layers["clr_conv3"];
@@ -525,6 +561,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
                 prop.major, prop.minor);
   CK(nullptr, cudaSetDevice(device));
   bsr_handle* h = new bsr_handle();
+  h->num_sms = prop.multiProcessorCount;
   h->variant = variant; h->precision = precision; h->device = device; h->mb = micro_batch;
   h->es = precision == BSR_PRECISION_FP32CHECK ? 4 : 2;
   const char* ev = getenv("BSR_DEBUG_KEEP");
@@ -549,7 +586,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {&h->VT, mb * 1024 * 128 * es}, {&h->O, mb * 1024 * 128 * es}, {&h->UP3, mb * IMG * IMG * 64 * es},
       {&h->F1, mb * 64 * 64 * 128 * es}, {&h->F2, mb * 128 * 128 * 96 * es}, {&h->CAT1, mb * IMG * IMG * 72 * es},
       {&h->C16, mb * IMG * IMG * 16 * es}, {&h->PIMG, mb * IMG * (IMG + 8) * 8 * 2},
-      {(char**)&h->RAW, mb * IMG * IMG * 2 * 4}, {(char**)&h->DIFGS, mb * IMG * IMG * 4},
+      {(char**)&h->RAW, mb * IMG * IMG * 2 * 4}, {(char**)&h->GS32, mb * IMG * IMG * 4}, {(char**)&h->DIFGS, mb * IMG * IMG * 4},
       {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
       {(char**)&h->DIFSMALL, mb * 1024 * 4},
       {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 2 * 291 * 4 : 256},
@@ -598,6 +635,7 @@ int bsr_destroy(bsr_handle* h) {
     if (kv.second.w_dev) cudaFree(kv.second.w_dev);
     if (kv.second.b_dev) cudaFree(kv.second.b_dev);
     kv.second.tc.release();
+    for (auto& tp : kv.second.tc_phase) tp.release();
   }
   for (auto& kv : h->dbg) if (kv.second.dev) cudaFree(kv.second.dev);
   for (auto& e : h->ev) cudaEventDestroy(e);
@@ -640,11 +678,20 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
     memcpy(bp.data(), L.b_host.data(), (size_t)en.cout * 4);
     CK(h, cudaMalloc(&L.b_dev, bn * 4));
     CK(h, cudaMemcpy(L.b_dev, bp.data(), bn * 4, cudaMemcpyHostToDevice));
+    for (auto& tp : L.tc_phase) tp.release();
+    L.phases_ready = false;
     if (h->precision == BSR_PRECISION_BF16) {
       std::string why;
-      if (!pack_tc_weights(h->tma, L.name, L.kh, L.kw, L.cin, L.cout, L.transposed, L.w_host, &L.tc, &why) &&
-          !why.empty())
-        return fail(h, BSR_ECUDA, "packing %s for tensor cores failed: %s", en.name, why.c_str());
+      if (!pack_tc_weights(h->tma, L.name, L.kh, L.kw, L.cin, L.cout, L.transposed, L.w_host, L.b_host, &L.tc, &why)) {
+        if (!why.empty()) return fail(h, BSR_ECUDA, "packing %s for tensor cores failed: %s", en.name, why.c_str());
+        if (L.transposed && !tc_disabled(L.name)) {
+          bool ok = true;
+          for (int ph = 0; ph < 4 && ok; ++ph)
+            ok = pack_tc_weights_phase(h->tma, ph, L.cin, L.cout, L.w_host, &L.tc_phase[ph], &why);
+          if (!ok) return fail(h, BSR_ECUDA, "packing %s (per phase) failed: %s", en.name, why.c_str());
+          L.phases_ready = true;
+        }
+      }
     }
   }
   static const char* required[] = {"conv1", "down1", "down2", "down3", "up1", "up2", "up3", "heads", "clr_up1",
@@ -657,6 +704,23 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
       snprintf(nm, 32, "res%d.%s", i, s);
       if (!h->layers.count(nm)) return fail(h, BSR_EINVAL, "blob lacks layer %s", nm);
     }
+  if (h->precision == BSR_PRECISION_BF16 && h->layers["clr_conv1"].tc.ready) {
+    // weights of the fused colour tail: [9][16] gs taps of clr_conv1 (canonical input channel 64), clr_conv2, clr_conv3
+    Layer& c1 = h->layers["clr_conv1"];
+    Layer& c2 = h->layers["clr_conv2"];
+    Layer& c3 = h->layers["clr_conv3"];
+    if (c2.cin != 16 || c2.cout != 16 || c3.cin != 16 || c3.cout != 3) return fail(h, BSR_EINVAL, "unexpected colour tail shapes");
+    std::vector<float> aux(144 + 256 + 16 + 48 + 3);
+    for (int t = 0; t < 9; ++t)
+      for (int o = 0; o < 16; ++o) aux[t * 16 + o] = c1.w_host[((size_t)t * 65 + 64) * 16 + o];
+    memcpy(&aux[144], c2.w_host.data(), 256 * 4);
+    memcpy(&aux[400], c2.b_host.data(), 16 * 4);
+    memcpy(&aux[416], c3.w_host.data(), 48 * 4);
+    memcpy(&aux[464], c3.b_host.data(), 3 * 4);
+    if (c1.tc.aux) cudaFree(c1.tc.aux);
+    CK(h, cudaMalloc(&c1.tc.aux, aux.size() * 4));
+    CK(h, cudaMemcpy(c1.tc.aux, aux.data(), aux.size() * 4, cudaMemcpyHostToDevice));
+  }
   const int cin_first = h->c_first, cin_second = h->c_second;
   if (h->layers["res0.conv1"].cin != cin_first || h->layers["res3.conv1"].cin != cin_second)
     return fail(h, BSR_EINVAL, "res-stack input widths do not match variant");

@@ -1,18 +1,30 @@
-// Implicit-GEMM convolution on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+// Implicit-GEMM convolution on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM) — persistent,
+// warp-specialised, driven by a per-layer "step program".
 //
-// GEMM view:  D[128 pixels, BN couts] = sum over (tap, 64-channel block) A_tap[128, 64] . W_tap[BN, 64]^T
-//   * A tile  = a BW x BH rectangle of output pixels (BW*BH = 128) of one image; for filter tap
-//     (dy,dx) it is the same rectangle of the NHWC input shifted by (dy,dx), fetched by ONE 4-D TMA
-//     box {64 ch, BW, BH, 1}: out-of-bounds rows/columns/channels are zero-filled by the TMA unit,
-//     which is exactly TF 'SAME' padding (and the channel padding of 99/257/261-wide inputs).
-//     Stride-2 convs use the same box with TMA element strides {1,2,2,1}.
-//   * transposed 3x3/s2 convs (model.py:153) run as 4 sub-pixel phases (blockIdx.z): output
-//     (2i+py, 2j+px) = sum over taps kh = py (mod 2), kw = px (mod 2) of in[i-(kh>>1), j-(kw>>1)] . W[kh,kw]
-//     -> 4/2/2/1 taps, each phase a stride-1 gather GEMM with its own slice of K.
-//   * W is packed once at load time: bf16 [cout_pad][taps * cin_pad64], K-major, fetched by 2-D TMA.
-//   * 128-byte swizzle on both operands; UMMA M=128, N=BN (multiple of 16), K=16 per instruction.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue (TMEM -> registers -> bias / residual adds / LeakyReLU -> global).
+// GEMM view:  D[128 pixels, N couts] = sum over steps  A_step[128, 64] . W_step[N, 64]^T
+//   * A tile  = a BW x BH rectangle of GEMM-space pixels (BW*BH = 128) of one image, shifted by the
+//     step's filter-tap offset (dy,dx), fetched by ONE 4-D TMA box {64 ch, BW, BH, 1} of the NHWC
+//     input: out-of-bounds rows / columns / channels are zero-filled by the TMA unit, which is exactly
+//     TF 'SAME' padding and the channel padding of the 99/257/261-wide tensors.  Stride-2 convs use
+//     the same box with TMA element strides {1,2,2,1}.
+//   * a step  = one A tile + the weight rows that multiply it + up to 2 MMAs into TMEM column ranges.
+//       plain conv      : step = (tap, 64-channel block), one MMA of N = BN;
+//       transposed conv : (model.py:153, 3x3 / stride 2 / SAME)  out[2i+py, 2j+px] = sum over taps
+//                         kh = py, kw = px (mod 2) of in[i-(kh>>1), j-(kw>>1)] . W[kh,kw].  The 4
+//                         sub-pixel phases share their A tiles, so a step = (shift, channel block) and
+//                         its MMAs feed the accumulators [p00 | p10 | p01 | p11] of ALL phases:
+//                         shift(0,0) -> 4 taps (N = 4*cout), (0,-1) -> 2, (-1,0) -> 2, (-1,-1) -> 1;
+//       conv1 (7x7, 3ch): rows of the pre-packed image [N][H][W+8][8]: one step per filter ROW, whose
+//                         64-element K block is the overlapping 8-pixel x 8-channel window;
+//       heads (7x7, 64->2, model.py:204-205): "kw expansion": N = 7(kw) x 2 outputs, K = 7(kh) x 64, one
+//                         image row (2 x 128 pixels) per tile; the horizontal taps are summed in the
+//                         epilogue through shared memory, fused with the grey composition (model.py:246-252).
+//   * W is packed once at load time (bf16, K-major) and fetched by 2-D TMA; 128-byte swizzle on both
+//     operands; UMMA M = 128, K = 16 per instruction.
+// Persistent CTAs (one per SM) loop over tiles; accumulators are double-buffered in TMEM whenever
+// 2 x columns <= 512, so the epilogue of tile t overlaps the TMA/MMA main loop of tile t+1.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = epilogue (TMEM -> registers -> bias / residual adds / LeakyReLU -> global).
 #pragma once
 #include <map>
 #include <string>
@@ -24,48 +36,83 @@
 
 namespace bsr {
 
-constexpr int TC_BM = 128;          // pixels per tile (UMMA M)
-constexpr int TC_BK = 64;           // channels per k-block (128 B of bf16 = one swizzle row)
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_TAPS = 49;
+constexpr int TC_BM = 128;          // pixels per A tile (UMMA M)
+constexpr int TC_BK = 64;           // K elements per step (128 B of bf16 = one swizzle row)
+constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_MAX_STEPS = 64;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4 };
+enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
+
+struct TcMma { int16_t col, n, brow; int16_t first; };
+struct TcStep {
+  int8_t dy, dx;           // A tile shift in input pixels
+  int8_t n_mma, pad0;
+  int16_t a_c0;            // A channel coordinate (elements)
+  int16_t b_rows;          // weight rows fetched for this step
+  int32_t b_k;             // weight K coordinate (elements)
+  int16_t b_row;           // first weight row (plus n-tile offset for plain convs)
+  int16_t a_x0;            // extra GEMM-x offset of the A tile (heads: 0 / 128 for the two row halves)
+  TcMma mma[2];
+};
 
 struct TcWeights {
   bool ready = false;
+  int kind = TC_CONV;
   int kh = 0, kw = 0, cin = 0, cout = 0, transposed = 0;
-  int row_packed = 0;     // conv1: input pre-packed as [N][H][W+8][8] bf16, one k-block = the 7(+1) pixels x 8 ch window
   int cin_pad = 0;        // multiple of 64
-  int bn = 0;             // UMMA N per tile
+  int bn = 0;             // accumulator columns owned by one n-tile (plain conv) / 4*cout (fused convT)
   int n_tiles = 0;
-  int taps = 0;
-  bf16* dev = nullptr;    // [n_tiles*bn][taps*cin_pad]
-  CUtensorMap map;        // 2-D {K_total, rows}, box {64, bn}
-  int8_t tap_kh[TC_MAX_TAPS], tap_kw[TC_MAX_TAPS];   // packing order
-  int phase_begin[5];
+  int b_box_rows = 0;     // rows per weight TMA box
+  int b_stage_rows = 0;   // max weight rows of one step
+  int n_steps = 0;
+  int tile_w = 0;         // forced tile width (heads: 128 with two halves per tile), 0 = auto
+  TcStep steps[TC_MAX_STEPS];
+  bf16* dev = nullptr;
+  float* aux = nullptr;   // EPI_CLR: [9][16] gs weights, [16][16] conv2, [16] b2, [16][3] conv3, [3] b3
+  CUtensorMap map;
   void release() {
     if (dev) cudaFree(dev);
+    if (aux) cudaFree(aux);
     dev = nullptr;
+    aux = nullptr;
     ready = false;
   }
+};
+
+// Extra pointers of the fused epilogues.
+struct EpiExtra {
+  const float* img;        // [N,256,256,3] fp32 network input (grey reference)
+  float* gs_out;           // optional user outputs
+  float* mask22_out;
+  float* difgs;            // fp32 [N,256,256] gs - grey (hole mask input)
+  float* gs_f32;           // fp32 [N,256,256] gs (input of the colour tail)
+  float* rgb_out;
+  float* dif_out;
+  const float* aux;        // EPI_CLR weights (see TcWeights::aux)
 };
 
 struct ConvTcParams {
   int n_img;
   int tiles_x, tiles_y;       // tiles per image in GEMM space
-  int bw, bh;                 // tile rectangle
-  int in_stride;              // 1 or 2: input coordinate = gemm coordinate * in_stride + tap offset
-  int out_scale;              // 1 (conv) or 2 (transposed): output pixel = gemm pixel * out_scale + phase
+  int bw, bh;                 // A-tile rectangle
+  int in_stride;              // 1 or 2: input coordinate = gemm coordinate * in_stride + shift
+  int out_scale;              // 1 (conv) or 2 (transposed)
   int OH, OW;
-  int ncb;                    // 64-channel blocks per tap
-  int bn;
-  int phase_begin[5];
-  int8_t dy[TC_MAX_TAPS], dx[TC_MAX_TAPS];
+  int n_tiles;                // weight n-tiles (plain conv)
+  int bn;                     // accumulator columns per tile
+  int n_groups, group_cols;   // epilogue column groups (fused convT: 4 phases x cout)
+  int group_phase[4];
+  int n_steps;
+  int b_box_rows;
+  int stage_bytes, n_stages, acc_stages;
+  int total_tiles;
+  int epi_mode;
   int* errflag;
+  TcStep steps[TC_MAX_STEPS];
 };
-
-inline size_t conv_tc_smem_bytes(int bn) {
-  return 1024 + (size_t)TC_STAGES * (TC_BM * 128 + (size_t)bn * 128) + 256;
-}
 
 // vectorised helpers for the epilogue ------------------------------------------------------
 __device__ __forceinline__ void add_res16(const void* base, size_t pix, int ld, int c, int climit, float* v) {
@@ -87,39 +134,40 @@ __device__ __forceinline__ void add_res16(const void* base, size_t pix, int ld, 
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB,
-                                                             const ConvTcParams p, const EpiParams e) {
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ ConvTcParams p,
+                                                                const EpiParams e, const EpiExtra x) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)p.bn * 128;
-  const uint32_t sA = smem_base;
-  const uint32_t sB = sA + TC_STAGES * a_bytes;
-  const uint32_t bars = sB + TC_STAGES * b_bytes;            // full[4], empty[4], tmem_full, tmem_ptr
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES, bar_tmem = bars + 16 * TC_STAGES;
-  const uint32_t tmem_slot = bar_tmem + 8;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t a_bytes = TC_BM * 128;
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+  const uint32_t bars = smem_base + (uint32_t)p.n_stages * stage_bytes;
+  // full[8], empty[8], tmem_full[2], tmem_empty[2], tmem slot
+  const uint32_t bar_full = bars, bar_empty = bars + 64, bar_tfull = bars + 128, bar_tempty = bars + 144;
+  const uint32_t tmem_slot = bars + 160;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+  float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 - smem_base));     // EPI_HEADS / EPI_CLR scratch
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int n = blockIdx.x / tiles_per_img;
-  const int tr = blockIdx.x % tiles_per_img;
-  const int gy0 = (tr / p.tiles_x) * p.bh, gx0 = (tr % p.tiles_x) * p.bw;
-  const int ntile = blockIdx.y, phase = blockIdx.z;
-  const int t0 = p.phase_begin[phase], t1 = p.phase_begin[phase + 1];
-  const int niter = (t1 - t0) * p.ncb;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.bn) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(p.bn * p.acc_stages)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tmem, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, TC_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -129,85 +177,230 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
+    // ================= TMA producer =================
     if (lane == 0) {
-      for (int it = 0; it < niter; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-        if (!mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.errflag, 1)) break;
-        const int t = t0 + it / p.ncb, cb = it % p.ncb;
-        mbar_expect_tx(bar_full + 8 * s, a_bytes + b_bytes);
-        tma_load_4d(sA + s * a_bytes, &tmA, bar_full + 8 * s, cb * TC_BK, gx0 * p.in_stride + p.dx[t],
-                    gy0 * p.in_stride + p.dy[t], n);
-        tma_load_2d(sB + s * b_bytes, &tmB, bar_full + 8 * s, (t * p.ncb + cb) * TC_BK, ntile * p.bn);
+      uint32_t it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+        const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
+        const int gy0 = (tr / p.tiles_x) * p.bh, gx0 = (tr % p.tiles_x) * p.bw * (p.epi_mode == EPI_HEADS ? 2 : 1);
+        for (int si = 0; si < p.n_steps; ++si, ++it) {
+          const TcStep& sp = p.steps[si];
+          const uint32_t s = it % (uint32_t)p.n_stages, ph = (it / (uint32_t)p.n_stages) & 1u;
+          ok = mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.errflag, 1);
+          if (!ok) break;
+          const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_bytes;
+          mbar_expect_tx(bar_full + 8 * s, a_bytes + (uint32_t)sp.b_rows * 128u);
+          tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, (gx0 + sp.a_x0) * p.in_stride + sp.dx,
+                      gy0 * p.in_stride + sp.dy, n);
+          const int row0 = sp.b_row + ntile * p.bn;
+          for (int r = 0; r < sp.b_rows; r += p.b_box_rows)
+            tma_load_2d(dstB + (uint32_t)r * 128u, &tmB, bar_full + 8 * s, sp.b_k, row0 + r);
+        }
       }
     }
   } else if (warp == 1) {
+    // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.bn);
+      uint32_t it = 0, tcount = 0;
       bool ok = true;
-      for (int it = 0; it < niter && ok; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-        ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2);
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
+        ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4);
         if (!ok) break;
         tc_fence_after();
-        const uint64_t da = umma_desc_sw128(sA + s * a_bytes), db = umma_desc_sw128(sB + s * b_bytes);
+        const uint32_t acc = tmem_base + as * (uint32_t)p.bn;
+        for (int si = 0; si < p.n_steps; ++si, ++it) {
+          const TcStep& sp = p.steps[si];
+          const uint32_t s = it % (uint32_t)p.n_stages, ph = (it / (uint32_t)p.n_stages) & 1u;
+          ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sA = smem_base + s * stage_bytes, sB = sA + a_bytes;
+          const uint64_t da = umma_desc_sw128(sA);
+          for (int m = 0; m < sp.n_mma; ++m) {
+            const TcMma mm = sp.mma[m];
+            const uint64_t db = umma_desc_sw128(sB + (uint32_t)mm.brow * 128u);
+            const uint32_t idesc = umma_idesc_bf16(TC_BM, mm.n);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(bar_empty + 8 * s);
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_bf16(acc + (uint32_t)mm.col, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        (mm.first && k == 0) ? 0u : 1u);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * as);
       }
-      umma_commit(bar_tmem);
     }
   } else {
-    // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (row = pixel of the tile)
-    const int q = warp & 3;
+    // ================= epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column chunks of parity w/4
+    const int ew = warp - 2;
+    const int q = warp & 3, half = ew >> 2;
     const int r = q * 32 + lane;
-    const int gy = gy0 + r / p.bw, gx = gx0 + r % p.bw;
-    const int oy = gy * p.out_scale + (phase >> 1), ox = gx * p.out_scale + (phase & 1);
-    const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-    const bool ok = mbar_wait(bar_tmem, 0, p.errflag, 3);
-    tc_fence_after();
-    if (ok) {
-      const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
-      const int s_img = gy * p.OW * p.out_scale + gx;      // OUT_QKV only (out_scale 1): pixel index inside the image
-      for (int j = 0; j < p.bn; j += 16) {
-        const int c = ntile * p.bn + j;
-        if (c >= e.out_c) break;               // warp-uniform
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t tcount = 0;
+    bool ok = true;
+    if (p.epi_mode == EPI_CLR) {
+      // stage the colour-tail weights once: [9][16] gs taps, [16][16] w2, [16] b2, [16][3] w3, [3] b3
+      for (int i = threadIdx.x - 64; i < 144 + 256 + 16 + 48 + 3; i += 256) epi_smem[i] = x.aux[i];
+      epi_bar_sync();
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
+      const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
+      const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
+      ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * (uint32_t)p.bn + lane_addr;
+      if (p.epi_mode == EPI_GENERIC) {
+        const int gy = (tr / p.tiles_x) * p.bh + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
+        const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
+        for (int g = 0; g < p.n_groups; ++g) {
+          const int phase = p.group_phase[g];
+          const int oy = gy * p.out_scale + (phase >> 1), ox = gx * p.out_scale + (phase & 1);
+          const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+          for (int j = 0; j < p.group_cols; j += 16) {
+            const int col = g * p.group_cols + j;
+            if (((col >> 4) & 1) != half) continue;
+            const int c = ntile * p.bn * (p.n_groups == 1 ? 1 : 0) + j;
+            if (c >= e.out_c) break;
+            float v[16];
+            tmem_ld16(acc + (uint32_t)col, v);
+            if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);      // bias is zero-padded past cout
+              if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
+              if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
+              if (e.act) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+              }
+              if (e.out_mode == OUT_F32) {
+                float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[i] = v[i];
+              } else if (e.out_mode == OUT_QKV && c >= 256) {
+                // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
+                bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * p.OW + gx);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
+              } else {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+                o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+                o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
+                uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
+                dst[0] = o0;
+                dst[1] = o1;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      } else if (p.epi_mode == EPI_HEADS) {
+        // tile = one image row; accumulator columns [half*16 + kw*2 + o] hold the vertical 7x1 partial sums
+        // Y[x][kw][o]; out[x][o] = sum_kw Y[x+kw-3][kw][o] (zero outside the row) + bias  (model.py:246-247)
+        const int y = tr;
+        const int xg = half * 128 + r;
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, v);
-        if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
+        tmem_ld16(acc + (uint32_t)(half * 16), v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);          // accumulator drained: MMA may start the next row
+        float* rowbuf = epi_smem;                                   // [256 + 6][16], 3 zero columns either side
+        if (threadIdx.x - 64 < 96) {
+          const int i = threadIdx.x - 64;                           // zero the two halos (3 x 16 each)
+          rowbuf[(i < 48 ? 0 : (259 - 3) * 16) + i] = 0.f;
+        }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);      // bias is zero-padded past cout
-          if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
-          if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
-          if (e.act) {
+        for (int i = 0; i < 16; ++i) rowbuf[(xg + 3) * 16 + i] = v[i];
+        epi_bar_sync();
+        float c2 = __ldg(e.bias), c3 = __ldg(e.bias + 1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+        for (int kw = 0; kw < 7; ++kw) {
+          const float2 t = *reinterpret_cast<const float2*>(rowbuf + (xg + kw) * 16 + kw * 2);
+          c2 += t.x;
+          c3 += t.y;
+        }
+        epi_bar_sync();                                             // row buffer free for the next tile
+        const size_t pidx = ((size_t)n * p.OH + y) * p.OW + xg;
+        const float mask = tanhf(c2);
+        const float g = x.img[3 * pidx] * kGrayR + x.img[3 * pidx + 1] * kGrayG + x.img[3 * pidx + 2] * kGrayB;
+        const float gs = g * (1.f + mask) + c3;
+        x.difgs[pidx] = gs - g;
+        x.gs_f32[pidx] = gs;
+        if (x.gs_out) x.gs_out[pidx] = gs;
+        if (x.mask22_out) {
+          x.mask22_out[3 * pidx] = fmaxf(mask, 0.f);
+          x.mask22_out[3 * pidx + 1] = mask * 0.f;
+          x.mask22_out[3 * pidx + 2] = fmaxf(-mask, 0.f);
+        }
+      } else {
+        // EPI_CLR: clr_conv1 over f (tensor cores, 16 couts) + the gs channel of the concat (model.py:267) as a
+        // 3x3 fp32 conv on CUDA cores, then clr_conv2 / clr_conv3 and the final dif (model.py:268-269, 288).
+        // Both epilogue halves hold the same 16 columns: half h handles rows of parity h (idle otherwise).
+        const int gy = (tr / p.tiles_x) * p.bh + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
+        float v[16];
+        tmem_ld16(acc, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        if ((r & 1) == half) {
+          const float* wg = epi_smem;                 // [9][16]
+          const float* w2 = epi_smem + 144;           // [16 in][16 out]
+          const float* b2 = w2 + 256;
+          const float* w3 = b2 + 16;                  // [16 in][3 out]
+          const float* b3 = w3 + 48;
+          const float* gsn = x.gs_f32 + (size_t)n * p.OH * p.OW;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + i);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int yy = gy + t / 3 - 1, xx = gx + t % 3 - 1;
+            if (yy >= 0 && yy < p.OH && xx >= 0 && xx < p.OW) {
+              const float gv = gsn[(size_t)yy * p.OW + xx];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(gv, wg[t * 16 + i], v[i]);
+            }
           }
-          if (e.out_mode == OUT_F32) {
-            float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[i] = v[i];
-          } else if (e.out_mode == OUT_QKV && c >= 256) {
-            // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes of a warp write consecutive tokens
-            bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + s_img;
+          for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+          float hbuf[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
-          } else {
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-            o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-            o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-            o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-            const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
-            uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
-            dst[0] = o0;
-            dst[1] = o1;
+          for (int o = 0; o < 16; ++o) {
+            float s = b2[o];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s = fmaf(v[c], w2[c * 16 + o], s);
+            hbuf[o] = leaky(s);
           }
-        } else {
+          float rgb[3];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
+          for (int o = 0; o < 3; ++o) {
+            float s = b3[o];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s = fmaf(hbuf[c], w3[c * 3 + o], s);
+            rgb[o] = s;
+          }
+          const size_t pidx = ((size_t)n * p.OH + gy) * p.OW + gx;
+          if (x.rgb_out) {
+            x.rgb_out[3 * pidx] = rgb[0];
+            x.rgb_out[3 * pidx + 1] = rgb[1];
+            x.rgb_out[3 * pidx + 2] = rgb[2];
+          }
+          if (x.dif_out) {
+            const float g1 = rgb[0] * kGrayR + rgb[1] * kGrayG + rgb[2] * kGrayB;
+            const float g0 = x.img[3 * pidx] * kGrayR + x.img[3 * pidx + 1] * kGrayG + x.img[3 * pidx + 2] * kGrayB;
+            x.dif_out[pidx] = g1 - g0;
+          }
         }
       }
     }
@@ -215,6 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -223,8 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 inline int configure_tc_kernels_conv() {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)conv_tc_smem_bytes(256));
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -236,126 +429,265 @@ inline uint16_t f32_to_bf16_bits(float f) {
   return (uint16_t)(u >> 16);
 }
 
-// Pack canonical fp32 [tap][cin][cout] into bf16 [cout_pad][taps*cin_pad] (K-major).  Returns false
-// with empty *why when the layer is simply not eligible (kept on the CUDA-core kernel).
-inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, int kw, int cin, int cout, int transposed,
-                            const std::vector<float>& w, TcWeights* out, std::string* why) {
-  why->clear();
-  if (name == "clr_conv2" || name == "clr_conv3") return false;   // fused into the colour tail kernel
-  if (const char* dis = getenv("BSR_TC_DISABLE")) {
-    std::string d = std::string(",") + dis + ",";
-    if (d.find("," + name + ",") != std::string::npos) return false;
-    std::string base = name.substr(0, name.find('.') == std::string::npos ? name.size() : name.find('.'));
-    if (name.find('.') != std::string::npos && d.find(",res." + name.substr(name.find('.') + 1) + ",") != std::string::npos)
-      return false;
-    (void)base;
-  }
-  TcWeights& t = *out;
-  t.kh = kh; t.kw = kw; t.cin = cin; t.cout = cout; t.transposed = transposed;
-  if (name == "conv1") {
-    // 7x7 conv over 3 channels (model.py:203): K per filter ROW = 7 taps x 8 (3 real + 5 zero) channels + one
-    // zero-weight pixel = 64 = one 128-byte swizzle row, fetched as an overlapping window of the packed image.
-    if (kh != 7 || kw != 7 || cin > 8 || transposed) { *why = "conv1 must be 7x7 with <= 8 input channels"; return false; }
-    t.row_packed = 1; t.cin_pad = 64; t.taps = 7; t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1;
-    for (int a = 0; a < 7; ++a) { t.tap_kh[a] = (int8_t)a; t.tap_kw[a] = 3; }
-    t.phase_begin[0] = 0;
-    for (int i = 1; i < 5; ++i) t.phase_begin[i] = 7;
-    const size_t K = 7 * 64, rows = t.bn;
-    std::vector<uint16_t> host(rows * K, 0);
-    for (int a = 0; a < 7; ++a)
-      for (int b = 0; b < 7; ++b)
-        for (int c = 0; c < cin; ++c)
-          for (int o = 0; o < cout; ++o)
-            host[(size_t)o * K + a * 64 + b * 8 + c] = f32_to_bf16_bits(w[((size_t)(a * 7 + b) * cin + c) * cout + o]);
-    if (cudaMalloc(&t.dev, host.size() * 2) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
-    if (cudaMemcpy(t.dev, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
-    uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
-    uint32_t box[2] = {TC_BK, (uint32_t)t.bn};
-    if (!tma.encode_bf16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
-    t.ready = true;
-    return true;
-  }
-  t.cin_pad = (cin + 63) / 64 * 64;
-  t.taps = kh * kw;
-  if (t.taps > TC_MAX_TAPS) return false;
-  if (cout == 384) { t.bn = 128; t.n_tiles = 3; }
-  else if (cout <= 256) { t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1; }
-  else { t.n_tiles = (cout + 255) / 256; t.bn = ((cout + t.n_tiles - 1) / t.n_tiles + 15) / 16 * 16; }
-  // tap order: phase-major for transposed convs
-  int nt = 0;
-  if (!transposed) {
-    for (int a = 0; a < kh; ++a)
-      for (int b = 0; b < kw; ++b) { t.tap_kh[nt] = (int8_t)a; t.tap_kw[nt] = (int8_t)b; ++nt; }
-    t.phase_begin[0] = 0;
-    for (int i = 1; i < 5; ++i) t.phase_begin[i] = nt;
-  } else {
-    if (kh != 3 || kw != 3) { *why = "transposed conv must be 3x3"; return false; }
-    for (int ph = 0; ph < 4; ++ph) {
-      t.phase_begin[ph] = nt;
-      int py = ph >> 1, px = ph & 1;
-      for (int a = py; a < 3; a += 2)
-        for (int b = px; b < 3; b += 2) { t.tap_kh[nt] = (int8_t)a; t.tap_kw[nt] = (int8_t)b; ++nt; }
-    }
-    t.phase_begin[4] = nt;
-  }
-  const size_t K = (size_t)t.taps * t.cin_pad, rows = (size_t)t.n_tiles * t.bn;
-  std::vector<uint16_t> host(rows * K, 0);
-  for (int ti = 0; ti < t.taps; ++ti) {
-    const int src_tap = t.tap_kh[ti] * kw + t.tap_kw[ti];
-    for (int c = 0; c < cin; ++c)
-      for (int o = 0; o < cout; ++o)
-        host[(size_t)o * K + (size_t)ti * t.cin_pad + c] = f32_to_bf16_bits(w[((size_t)src_tap * cin + c) * cout + o]);
-  }
+inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>& host, size_t rows, size_t K,
+                      std::string* why) {
   if (cudaMalloc(&t.dev, host.size() * 2) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   if (cudaMemcpy(t.dev, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
   uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
-  uint32_t box[2] = {TC_BK, (uint32_t)t.bn};
+  uint32_t box[2] = {TC_BK, (uint32_t)t.b_box_rows};
   if (!tma.encode_bf16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
   t.ready = true;
   return true;
 }
 
+inline bool tc_disabled(const std::string& name) {
+  const char* dis = getenv("BSR_TC_DISABLE");
+  if (!dis) return false;
+  std::string d = std::string(",") + dis + ",";
+  return d.find("," + name + ",") != std::string::npos;
+}
+
+// Build the step program and the packed bf16 weight matrix of one layer from canonical fp32
+// [tap][cin][cout].  Returns false with empty *why when the layer stays on the CUDA-core kernel.
+inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, int kw, int cin, int cout, int transposed,
+                            const std::vector<float>& w, const std::vector<float>& bias, TcWeights* out,
+                            std::string* why) {
+  why->clear();
+  if (name == "clr_conv2" || name == "clr_conv3") return false;   // consumed by the fused colour tail
+  if (tc_disabled(name)) return false;
+  TcWeights& t = *out;
+  memset(t.steps, 0, sizeof t.steps);
+  t.kh = kh; t.kw = kw; t.cin = cin; t.cout = cout; t.transposed = transposed;
+  t.tile_w = 0;
+  auto W = [&](int tap, int c, int o) { return w[((size_t)tap * cin + c) * cout + o]; };
+
+  if (name == "conv1") {
+    // 7x7 conv over 3 channels (model.py:203): K per filter ROW = 7 taps x 8 (3 real + 5 zero) channels + one
+    // zero-weight pixel = 64 elements, fetched as an overlapping window of the packed image.
+    if (kh != 7 || kw != 7 || cin > 8 || transposed) { *why = "conv1 must be 7x7 with <= 8 input channels"; return false; }
+    t.kind = TC_ROWPACK; t.cin_pad = 64; t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1;
+    t.b_box_rows = t.bn; t.b_stage_rows = t.bn; t.n_steps = 7;
+    const size_t K = 7 * 64, rows = t.bn;
+    std::vector<uint16_t> host(rows * K, 0);
+    for (int a = 0; a < 7; ++a) {
+      TcStep& s = t.steps[a];
+      s.dy = (int8_t)(a - 3); s.dx = 0; s.a_c0 = 0; s.b_rows = (int16_t)t.bn; s.b_k = a * 64; s.b_row = 0;
+      s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(a == 0)};
+      for (int b = 0; b < 7; ++b)
+        for (int c = 0; c < cin; ++c)
+          for (int o = 0; o < cout; ++o) host[(size_t)o * K + a * 64 + b * 8 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+    }
+    return tc_upload(tma, t, host, rows, K, why);
+  }
+
+  if (name == "heads") {
+    // conv2|conv3 (7x7, 64 -> 2): accumulator column kw*2+o = sum_kh sum_c in[y+kh-3][x][c] * W[kh][kw][c][o]
+    if (kh != 7 || kw != 7 || cin != 64 || cout != 2) { *why = "heads must be 7x7 64->2"; return false; }
+    t.kind = TC_HEADS; t.cin_pad = 64; t.bn = 32; t.n_tiles = 1; t.b_box_rows = 16; t.b_stage_rows = 16;
+    t.n_steps = 14; t.tile_w = 128;
+    const size_t K = 7 * 64, rows = 16;
+    std::vector<uint16_t> host(rows * K, 0);
+    for (int a = 0; a < 7; ++a)
+      for (int b = 0; b < 7; ++b)
+        for (int c = 0; c < 64; ++c)
+          for (int o = 0; o < 2; ++o) host[(size_t)(b * 2 + o) * K + a * 64 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+    for (int hh = 0; hh < 2; ++hh)
+      for (int a = 0; a < 7; ++a) {
+        TcStep& s = t.steps[hh * 7 + a];
+        s.dy = (int8_t)(a - 3); s.dx = 0; s.a_x0 = (int16_t)(hh * 128); s.a_c0 = 0; s.b_rows = 16; s.b_k = a * 64;
+        s.b_row = 0; s.n_mma = 1; s.mma[0] = TcMma{(int16_t)(hh * 16), 16, 0, (int16_t)(a == 0)};
+      }
+    return tc_upload(tma, t, host, rows, K, why);
+  }
+
+  if (name == "clr_conv1") {
+    // canonical input order [f0..f63, gs]: f runs on tensor cores, gs (fp32) in the epilogue
+    if (kh != 3 || kw != 3 || cin != 65 || cout != 16) { *why = "clr_conv1 must be 3x3 65->16"; return false; }
+    t.kind = TC_CLR; t.cin_pad = 64; t.bn = 16; t.n_tiles = 1; t.b_box_rows = 16; t.b_stage_rows = 16; t.n_steps = 9;
+    const size_t K = 9 * 64, rows = 16;
+    std::vector<uint16_t> host(rows * K, 0);
+    for (int tap = 0; tap < 9; ++tap) {
+      TcStep& s = t.steps[tap];
+      s.dy = (int8_t)(tap / 3 - 1); s.dx = (int8_t)(tap % 3 - 1); s.a_c0 = 0; s.b_rows = 16; s.b_k = tap * 64; s.b_row = 0;
+      s.n_mma = 1; s.mma[0] = TcMma{0, 16, 0, (int16_t)(tap == 0)};
+      for (int c = 0; c < 64; ++c)
+        for (int o = 0; o < 16; ++o) host[(size_t)o * K + tap * 64 + c] = f32_to_bf16_bits(W(tap, c, o));
+    }
+    (void)bias;
+    return tc_upload(tma, t, host, rows, K, why);
+  }
+
+  t.cin_pad = (cin + 63) / 64 * 64;
+  const int ncb = t.cin_pad / 64;
+  if (transposed && cout % 16 == 0 && cout <= 96 && 4 * ncb <= TC_MAX_STEPS && !tc_disabled("convt_fused")) {
+    // fused 4-phase transposed conv; accumulator column groups [p00 | p10 | p01 | p11]
+    if (kh != 3 || kw != 3) { *why = "transposed conv must be 3x3"; return false; }
+    t.kind = TC_CONVT_FUSED; t.bn = 4 * cout; t.n_tiles = 1; t.b_box_rows = cout; t.b_stage_rows = 4 * cout;
+    const size_t K = t.cin_pad, rows = 9 * (size_t)cout;
+    std::vector<uint16_t> host(rows * K, 0);
+    // weight row blocks, in order: shift(0,0): taps (0,0),(1,0),(0,1),(1,1); shift(0,-1): (0,2),(1,2);
+    // shift(-1,0): (2,0),(2,1); shift(-1,-1): (2,2)
+    const int order[9][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}, {0, 2}, {1, 2}, {2, 0}, {2, 1}, {2, 2}};
+    for (int b = 0; b < 9; ++b) {
+      const int tap = order[b][0] * 3 + order[b][1];
+      for (int c = 0; c < cin; ++c)
+        for (int o = 0; o < cout; ++o) host[((size_t)b * cout + o) * K + c] = f32_to_bf16_bits(W(tap, c, o));
+    }
+    int ns = 0;
+    const int16_t co = (int16_t)cout;
+    for (int cb = 0; cb < ncb; ++cb) {
+      const int16_t f = (int16_t)(cb == 0);
+      TcStep s;
+      memset(&s, 0, sizeof s);
+      s.a_c0 = (int16_t)(cb * 64); s.b_k = cb * 64;
+      // shift (0,0): all four phases
+      s.dy = 0; s.dx = 0; s.b_row = 0; s.b_rows = (int16_t)(4 * co);
+      if (4 * cout <= 256) { s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)(4 * co), 0, f}; }
+      else { s.n_mma = 2; s.mma[0] = TcMma{0, (int16_t)(2 * co), 0, f}; s.mma[1] = TcMma{(int16_t)(2 * co), (int16_t)(2 * co), (int16_t)(2 * co), f}; }
+      t.steps[ns++] = s;
+      // shift (0,-1): kw = 2 -> phases p00, p10 (adjacent columns)
+      s.dy = 0; s.dx = -1; s.b_row = (int16_t)(4 * co); s.b_rows = (int16_t)(2 * co);
+      s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)(2 * co), 0, 0};
+      t.steps[ns++] = s;
+      // shift (-1,0): kh = 2 -> phases p00 (cols 0) and p01 (cols 2*cout)
+      s.dy = -1; s.dx = 0; s.b_row = (int16_t)(6 * co); s.b_rows = (int16_t)(2 * co);
+      s.n_mma = 2; s.mma[0] = TcMma{0, co, 0, 0}; s.mma[1] = TcMma{(int16_t)(2 * co), co, co, 0};
+      t.steps[ns++] = s;
+      // shift (-1,-1): tap (2,2) -> p00
+      s.dy = -1; s.dx = -1; s.b_row = (int16_t)(8 * co); s.b_rows = co;
+      s.n_mma = 1; s.mma[0] = TcMma{0, co, 0, 0};
+      t.steps[ns++] = s;
+    }
+    t.n_steps = ns;
+    return tc_upload(tma, t, host, rows, K, why);
+  }
+
+  // ---- plain conv, or one launch per phase for wide transposed convs (handled by the caller via `phase`)
+  if (transposed) return false;          // cout > 96 transposed convs: see pack_tc_weights_phase
+  if (kh * kw * ncb > TC_MAX_STEPS) return false;
+  t.kind = TC_CONV;
+  if (cout == 384) { t.bn = 128; t.n_tiles = 3; }
+  else if (cout <= 256) { t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1; }
+  else { t.n_tiles = (cout + 255) / 256; t.bn = ((cout + t.n_tiles - 1) / t.n_tiles + 15) / 16 * 16; }
+  t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
+  const size_t K = (size_t)kh * kw * t.cin_pad, rows = (size_t)t.n_tiles * t.bn;
+  std::vector<uint16_t> host(rows * K, 0);
+  int ns = 0;
+  for (int tap = 0; tap < kh * kw; ++tap) {
+    for (int c = 0; c < cin; ++c)
+      for (int o = 0; o < cout; ++o) host[(size_t)o * K + (size_t)tap * t.cin_pad + c] = f32_to_bf16_bits(W(tap, c, o));
+    for (int cb = 0; cb < ncb; ++cb) {
+      TcStep& s = t.steps[ns];
+      s.dy = (int8_t)(tap / kw); s.dx = (int8_t)(tap % kw);        // SAME-padding offset subtracted at launch
+      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (tap * ncb + cb) * 64; s.b_row = 0;
+      s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
+      ++ns;
+    }
+  }
+  t.n_steps = ns;
+  return tc_upload(tma, t, host, rows, K, why);
+}
+
+// Wide transposed convs (cout > 96: clr_up1) run as 4 launches, one per sub-pixel phase, each a plain
+// gather conv over that phase's taps.
+inline bool pack_tc_weights_phase(TmaEncoder& tma, int phase, int cin, int cout, const std::vector<float>& w,
+                                  TcWeights* out, std::string* why) {
+  TcWeights& t = *out;
+  memset(t.steps, 0, sizeof t.steps);
+  t.kind = TC_CONV; t.kh = 3; t.kw = 3; t.cin = cin; t.cout = cout; t.transposed = 1;
+  t.cin_pad = (cin + 63) / 64 * 64;
+  const int ncb = t.cin_pad / 64, py = phase >> 1, px = phase & 1;
+  t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1; t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
+  std::vector<int> taps;
+  for (int a = py; a < 3; a += 2)
+    for (int b = px; b < 3; b += 2) taps.push_back(a * 3 + b);
+  if ((int)taps.size() * ncb > TC_MAX_STEPS) { *why = "too many steps"; return false; }
+  const size_t K = taps.size() * (size_t)t.cin_pad, rows = t.bn;
+  std::vector<uint16_t> host(rows * K, 0);
+  int ns = 0;
+  for (size_t ti = 0; ti < taps.size(); ++ti) {
+    const int tap = taps[ti];
+    for (int c = 0; c < cin; ++c)
+      for (int o = 0; o < cout; ++o)
+        host[(size_t)o * K + ti * t.cin_pad + c] = f32_to_bf16_bits(w[((size_t)tap * cin + c) * cout + o]);
+    for (int cb = 0; cb < ncb; ++cb) {
+      TcStep& s = t.steps[ns];
+      s.dy = (int8_t)(-((tap / 3) >> 1)); s.dx = (int8_t)(-((tap % 3) >> 1));
+      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (int)((ti * ncb + cb) * 64); s.b_row = 0;
+      s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
+      ++ns;
+    }
+  }
+  t.n_steps = ns;
+  return tc_upload(tma, t, host, rows, K, why);
+}
+
 struct TmapKey {
-  const void* p; int ld, coff, cin, H, W, n, stride, bw, bh;
+  const void* p; int ld, coff, cin, H, W, n, stride, bw, bh, kind;
   bool operator<(const TmapKey& o) const {
-    return std::tie(p, ld, coff, cin, H, W, n, stride, bw, bh) <
-           std::tie(o.p, o.ld, o.coff, o.cin, o.H, o.W, o.n, o.stride, o.bw, o.bh);
+    return std::tie(p, ld, coff, cin, H, W, n, stride, bw, bh, kind) <
+           std::tie(o.p, o.ld, o.coff, o.cin, o.H, o.W, o.n, o.stride, o.bw, o.bh, o.kind);
   }
 };
 
+// phase: -1 = whole layer; 0..3 = single sub-pixel phase of a wide transposed conv (weights from
+// pack_tc_weights_phase).
 inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, int in_ld, int in_coff, int H, int W,
-                          int stride, int n, const EpiParams& e, int* errflag, cudaStream_t st, int* launches) {
+                          int stride, int n, const EpiParams& e, const EpiExtra& x, int phase, int num_sms,
+                          int* errflag, cudaStream_t st, int* launches) {
   static thread_local std::map<TmapKey, CUtensorMap> cache;
-  ConvTcParams p;
+  static thread_local ConvTcParams p;           // 2 KB: keep it off the stack
   memset(&p, 0, sizeof p);
   int GH, GW;
+  int pad_t = 0, pad_l = 0;
   if (t.transposed) {
     GH = H; GW = W; p.in_stride = 1; p.out_scale = 2; p.OH = 2 * H; p.OW = 2 * W;
-    for (int i = 0; i < t.taps; ++i) { p.dy[i] = (int8_t)(-(t.tap_kh[i] >> 1)); p.dx[i] = (int8_t)(-(t.tap_kw[i] >> 1)); }
   } else {
     p.in_stride = stride; p.out_scale = 1;
     p.OH = (H + stride - 1) / stride; p.OW = (W + stride - 1) / stride;
     GH = p.OH; GW = p.OW;
     int tot_h = (p.OH - 1) * stride + t.kh - H; if (tot_h < 0) tot_h = 0;
     int tot_w = (p.OW - 1) * stride + t.kw - W; if (tot_w < 0) tot_w = 0;
-    for (int i = 0; i < t.taps; ++i) { p.dy[i] = (int8_t)(t.tap_kh[i] - tot_h / 2); p.dx[i] = (int8_t)(t.tap_kw[i] - tot_w / 2); }
+    pad_t = tot_h / 2; pad_l = tot_w / 2;        // TF SAME: before = total // 2
   }
-  p.bw = GW < TC_BM ? GW : TC_BM;
+  p.n_steps = t.n_steps;
+  for (int i = 0; i < t.n_steps; ++i) {
+    p.steps[i] = t.steps[i];
+    if (t.kind == TC_CONV && !t.transposed) { p.steps[i].dy -= (int8_t)pad_t; p.steps[i].dx -= (int8_t)pad_l; }
+  }
+  p.bw = t.tile_w ? t.tile_w : (GW < TC_BM ? GW : TC_BM);
   p.bh = TC_BM / p.bw;
-  if (GW % p.bw || GH % p.bh) { tma.last_error = "spatial size not tileable into 128-pixel rectangles"; return -1; }
-  p.tiles_x = GW / p.bw; p.tiles_y = GH / p.bh;
-  p.n_img = n; p.ncb = t.cin_pad / TC_BK; p.bn = t.bn;
-  for (int i = 0; i < 5; ++i) p.phase_begin[i] = t.phase_begin[i];
+  p.epi_mode = t.kind == TC_HEADS ? EPI_HEADS : (t.kind == TC_CLR ? EPI_CLR : EPI_GENERIC);
+  if (t.kind == TC_HEADS) {
+    if (GW != 256) { tma.last_error = "heads kernel needs 256-pixel rows"; return -4; }
+    p.tiles_x = 1; p.tiles_y = GH;
+  } else {
+    if (GW % p.bw || GH % p.bh) { tma.last_error = "spatial size not tileable into 128-pixel rectangles"; return -1; }
+    p.tiles_x = GW / p.bw; p.tiles_y = GH / p.bh;
+  }
+  p.n_img = n; p.bn = t.bn; p.n_tiles = t.n_tiles; p.b_box_rows = t.b_box_rows;
+  if (t.kind == TC_CONVT_FUSED) {
+    p.n_groups = 4; p.group_cols = t.cout;
+    p.group_phase[0] = 0; p.group_phase[1] = 2; p.group_phase[2] = 1; p.group_phase[3] = 3;   // p00 p10 p01 p11
+  } else {
+    p.n_groups = 1; p.group_cols = t.bn;
+    p.group_phase[0] = phase < 0 ? 0 : phase;
+  }
+  p.stage_bytes = TC_BM * 128 + t.b_stage_rows * 128;
+  p.n_stages = TC_SMEM_BUDGET / p.stage_bytes;
+  if (p.n_stages > 8) p.n_stages = 8;
+  if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }
+  p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
+  p.total_tiles = n * p.tiles_x * p.tiles_y * t.n_tiles;
   p.errflag = errflag;
   if ((in_ld % 8) || (in_coff % 8)) { tma.last_error = "input channel stride/offset must be multiples of 8"; return -2; }
-  if (t.row_packed) { for (int i = 0; i < t.taps; ++i) p.dx[i] = 0; }
-  TmapKey key{in, in_ld, in_coff, t.cin, H, W, n, p.in_stride, p.bw, p.bh};
+  TmapKey key{in, in_ld, in_coff, t.cin, H, W, n, p.in_stride, p.bw, p.bh, t.kind};
   auto it = cache.find(key);
   if (it == cache.end()) {
     CUtensorMap m;
-    uint64_t dims[4] = {(uint64_t)t.cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+    uint64_t dims[4] = {(uint64_t)(t.kind == TC_CLR ? 64 : t.cin), (uint64_t)W, (uint64_t)H, (uint64_t)n};
     uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)W * in_ld * 2, (uint64_t)H * W * in_ld * 2};
-    if (t.row_packed) {
+    if (t.kind == TC_ROWPACK) {
       // packed image [N][H][W + 8][8]: window of output column x = 64 contiguous elements starting at packed
       // pixel x (= image pixel x-3); consecutive windows overlap (dim-1 stride 16 B < dim-0 extent 128 B)
       dims[0] = 64;
@@ -367,8 +699,9 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     if (cache.size() > 4096) cache.clear();
     it = cache.emplace(key, m).first;
   }
-  dim3 grid((unsigned)(n * p.tiles_x * p.tiles_y), (unsigned)t.n_tiles, t.transposed ? 4u : 1u);
-  conv_tc_kernel<<<grid, TC_THREADS, conv_tc_smem_bytes(t.bn), st>>>(it->second, t.map, p, e);
+  const size_t smem = 1024 + (size_t)p.n_stages * p.stage_bytes + 192 + (p.epi_mode == EPI_HEADS ? 262 * 16 * 4 : 2048) + 64;
+  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(it->second, t.map, p, e, x);
   (*launches)++;
   return 0;
 }
