@@ -73,7 +73,8 @@ struct bsr_handle {
   // host-path staging
   void* stage = nullptr;
   size_t stage_bytes = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   TmaEncoder tma;
 };
 
@@ -491,13 +492,24 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
   return BSR_OK;
 }
 
+// Host-buffer path: micro-batches are pipelined over three streams (H2D | compute | D2H) with two staging
+// slots, so PCIe transfers in both directions overlap the kernels of the neighbouring micro-batches.
 int forward_host(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
                  float* gs, float* rgb, float* mask22, float* dif) {
   if (!h) return BSR_EINVAL;
   if (n <= 0) return fail(h, BSR_EINVAL, "n must be > 0");
+  if (!h->loaded) return fail(h, BSR_ESTATE, "bsr_load_weights has not been called");
   CK(h, cudaSetDevice(h->device));
-  const size_t p = (size_t)n * IMG * IMG * sizeof(float);
-  size_t need = p * (3 + 3 + (reg ? 6 : 0) + 1 + 3 + 3 + 1);
+  int step = h->mb;
+  if (reg) {
+    if (frame <= 0 || n % frame) return fail(h, BSR_EINVAL, "TSM needs n %% frame == 0");
+    if (frame > h->mb) return fail(h, BSR_EINVAL, "frame %d exceeds micro_batch %d", frame, h->mb);
+    step = h->mb / frame * frame;
+  }
+  const size_t p1 = (size_t)IMG * IMG * sizeof(float);           // one single-channel image plane
+  const size_t in_slot = (size_t)step * p1 * (3 + 3 + (reg ? 6 : 0));
+  const size_t out_slot = (size_t)step * p1 * (1 + 3 + 3 + 1);
+  const size_t need = 2 * (in_slot + out_slot);
   if (need > h->stage_bytes) {
     if (h->stage) cudaFree(h->stage);
     h->stage = nullptr;
@@ -505,27 +517,54 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
     if (cudaMalloc(&h->stage, need) != cudaSuccess) return fail(h, BSR_ENOMEM, "staging allocation of %zu bytes failed", need);
     h->stage_bytes = need;
   }
-  char* s = (char*)h->stage;
-  float* d_img = (float*)s; s += 3 * p;
-  float* d_uv = (float*)s; s += 3 * p;
-  float* d_reg = nullptr;
-  if (reg) { d_reg = (float*)s; s += 6 * p; }
-  float* d_gs = (float*)s; s += p;
-  float* d_rgb = (float*)s; s += 3 * p;
-  float* d_m22 = (float*)s; s += 3 * p;
-  float* d_dif = (float*)s;
-  cudaStream_t st = h->own_stream;
-  CK(h, cudaMemcpyAsync(d_img, img, 3 * p, cudaMemcpyHostToDevice, st));
-  CK(h, cudaMemcpyAsync(d_uv, uv, 3 * p, cudaMemcpyHostToDevice, st));
-  if (reg) CK(h, cudaMemcpyAsync(d_reg, reg, 6 * p, cudaMemcpyHostToDevice, st));
-  int rc = forward_common(h, d_img, d_uv, d_reg, n, frame, share, gs ? d_gs : nullptr, rgb ? d_rgb : nullptr,
-                          mask22 ? d_m22 : nullptr, dif ? d_dif : nullptr, st);
-  if (rc) return rc;
-  if (gs) CK(h, cudaMemcpyAsync(gs, d_gs, p, cudaMemcpyDeviceToHost, st));
-  if (rgb) CK(h, cudaMemcpyAsync(rgb, d_rgb, 3 * p, cudaMemcpyDeviceToHost, st));
-  if (mask22) CK(h, cudaMemcpyAsync(mask22, d_m22, 3 * p, cudaMemcpyDeviceToHost, st));
-  if (dif) CK(h, cudaMemcpyAsync(dif, d_dif, p, cudaMemcpyDeviceToHost, st));
-  CK(h, cudaStreamSynchronize(st));
+  if (!h->s_in) {
+    CK(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CK(h, cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+      CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t s_in = h->s_in, s_c = h->own_stream, s_out = h->s_out;
+  int total_launches = 0, k = 0;
+  for (int i0 = 0; i0 < n; i0 += step, ++k) {
+    const int m = n - i0 < step ? n - i0 : step;
+    const int slot = k & 1;
+    char* sin = (char*)h->stage + slot * in_slot;
+    char* sout = (char*)h->stage + 2 * in_slot + slot * out_slot;
+    float* d_img = (float*)sin;
+    float* d_uv = (float*)(sin + (size_t)step * p1 * 3);
+    float* d_reg = reg ? (float*)(sin + (size_t)step * p1 * 6) : nullptr;
+    float* d_gs = (float*)sout;
+    float* d_rgb = (float*)(sout + (size_t)step * p1);
+    float* d_m22 = (float*)(sout + (size_t)step * p1 * 4);
+    float* d_dif = (float*)(sout + (size_t)step * p1 * 7);
+    const size_t o1 = (size_t)i0 * IMG * IMG, pm = (size_t)m * p1;
+    // the input slot is free once the compute that read it (two micro-batches ago) has finished
+    if (k >= 2) CK(h, cudaStreamWaitEvent(s_in, h->ev_comp[slot], 0));
+    CK(h, cudaMemcpyAsync(d_img, img + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
+    CK(h, cudaMemcpyAsync(d_uv, uv + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
+    if (reg) CK(h, cudaMemcpyAsync(d_reg, reg + o1 * 6, pm * 6, cudaMemcpyHostToDevice, s_in));
+    CK(h, cudaEventRecord(h->ev_in[slot], s_in));
+    CK(h, cudaStreamWaitEvent(s_c, h->ev_in[slot], 0));
+    // the output slot is free once its previous D2H (two micro-batches ago) has finished
+    if (k >= 2) CK(h, cudaStreamWaitEvent(s_c, h->ev_out[slot], 0));
+    int rc = forward_common(h, d_img, d_uv, d_reg, m, frame, share, gs ? d_gs : nullptr, rgb ? d_rgb : nullptr,
+                            mask22 ? d_m22 : nullptr, dif ? d_dif : nullptr, s_c);
+    if (rc) return rc;
+    total_launches += h->launches;
+    CK(h, cudaEventRecord(h->ev_comp[slot], s_c));
+    CK(h, cudaStreamWaitEvent(s_out, h->ev_comp[slot], 0));
+    if (gs) CK(h, cudaMemcpyAsync(gs + o1, d_gs, pm, cudaMemcpyDeviceToHost, s_out));
+    if (rgb) CK(h, cudaMemcpyAsync(rgb + o1 * 3, d_rgb, pm * 3, cudaMemcpyDeviceToHost, s_out));
+    if (mask22) CK(h, cudaMemcpyAsync(mask22 + o1 * 3, d_m22, pm * 3, cudaMemcpyDeviceToHost, s_out));
+    if (dif) CK(h, cudaMemcpyAsync(dif + o1, d_dif, pm, cudaMemcpyDeviceToHost, s_out));
+    CK(h, cudaEventRecord(h->ev_out[slot], s_out));
+  }
+  CK(h, cudaStreamSynchronize(s_out));
+  CK(h, cudaStreamSynchronize(s_c));
+  h->launches = total_launches;
   int flag = 0;
   CK(h, cudaMemcpy(&flag, h->errflag, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag) return fail(h, BSR_ECUDA, "device watchdog: an mbarrier wait timed out (code %d)", flag);
@@ -642,6 +681,13 @@ int bsr_destroy(bsr_handle* h) {
   if (h->arena) cudaFree(h->arena);
   if (h->stage) cudaFree(h->stage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+  }
   delete h;
   return BSR_OK;
 }

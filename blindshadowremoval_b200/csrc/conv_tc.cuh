@@ -55,7 +55,7 @@ struct TcStep {
   int32_t b_k;             // weight K coordinate (elements)
   int16_t b_row;           // first weight row (plus n-tile offset for plain convs)
   int16_t a_x0;            // extra GEMM-x offset of the A tile (heads: 0 / 128 for the two row halves)
-  TcMma mma[2];
+  TcMma mma[8];
 };
 
 struct TcWeights {
@@ -69,15 +69,22 @@ struct TcWeights {
   int b_stage_rows = 0;   // max weight rows of one step
   int n_steps = 0;
   int tile_w = 0;         // forced tile width (heads: 128 with two halves per tile), 0 = auto
+  int rows_per_tile = 1;  // multi-row tiles: R output rows share their input rows (vertical-tap layers)
+  int halves = 1;         // 2: a tile row is 256 pixels = two 128-pixel A tiles
+  int b_resident = 0;     // whole weight matrix stays in shared memory for the life of the CTA
+  int b_total_rows = 0;
   TcStep steps[TC_MAX_STEPS];
+  TcStep* steps_dev = nullptr;
   bf16* dev = nullptr;
   float* aux = nullptr;   // EPI_CLR: [9][16] gs weights, [16][16] conv2, [16] b2, [16][3] conv3, [3] b3
   CUtensorMap map;
   void release() {
     if (dev) cudaFree(dev);
     if (aux) cudaFree(aux);
+    if (steps_dev) cudaFree(steps_dev);
     dev = nullptr;
     aux = nullptr;
+    steps_dev = nullptr;
     ready = false;
   }
 };
@@ -110,8 +117,11 @@ struct ConvTcParams {
   int stage_bytes, n_stages, acc_stages;
   int total_tiles;
   int epi_mode;
+  int rows_per_tile, halves;  // multi-row tiles (groups = rows x halves)
+  int pad_t, pad_l;           // SAME padding subtracted from the step shifts (plain convs)
+  int b_resident, b_total_rows;
   int* errflag;
-  TcStep steps[TC_MAX_STEPS];
+  const TcStep* steps;        // device copy of the step program
 };
 
 // vectorised helpers for the epilogue ------------------------------------------------------
@@ -144,13 +154,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TC_BM * 128;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
-  const uint32_t bars = smem_base + (uint32_t)p.n_stages * stage_bytes;
-  // full[8], empty[8], tmem_full[2], tmem_empty[2], tmem slot
+  const uint32_t sBres = smem_base + (uint32_t)p.n_stages * stage_bytes;            // resident weights (optional)
+  const uint32_t bars = sBres + (p.b_resident ? (uint32_t)p.b_total_rows * 128u : 0u);
+  // full[8], empty[8], tmem_full[2], tmem_empty[2], bres, tmem slot
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_tfull = bars + 128, bar_tempty = bars + 144;
-  const uint32_t tmem_slot = bars + 160;
+  const uint32_t bar_bres = bars + 160, tmem_slot = bars + 168;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
-  float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 - smem_base));     // EPI_HEADS / EPI_CLR scratch
+  TcStep* steps = reinterpret_cast<TcStep*>(smem_al + (bars + 192 - smem_base));
+  float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 + TC_MAX_STEPS * sizeof(TcStep) - smem_base));
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.steps);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(steps);
+    for (int i = threadIdx.x; i < p.n_steps * (int)(sizeof(TcStep) / 4); i += blockDim.x) dst[i] = src[i];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -168,6 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, TC_EPI_WARPS);
     }
+    mbar_init(bar_bres, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -181,22 +199,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       uint32_t it = 0;
       bool ok = true;
+      if (p.b_resident) {
+        mbar_expect_tx(bar_bres, (uint32_t)p.b_total_rows * 128u);
+        for (int r = 0; r < p.b_total_rows; r += p.b_box_rows) tma_load_2d(sBres + (uint32_t)r * 128u, &tmB, bar_bres, 0, r);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
         const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
         const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
-        const int gy0 = (tr / p.tiles_x) * p.bh, gx0 = (tr % p.tiles_x) * p.bw * (p.epi_mode == EPI_HEADS ? 2 : 1);
+        const int gy0 = (tr / p.tiles_x) * p.bh * p.rows_per_tile, gx0 = (tr % p.tiles_x) * p.bw * p.halves;
         for (int si = 0; si < p.n_steps; ++si, ++it) {
-          const TcStep& sp = p.steps[si];
+          const TcStep& sp = steps[si];
           const uint32_t s = it % (uint32_t)p.n_stages, ph = (it / (uint32_t)p.n_stages) & 1u;
           ok = mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.errflag, 1);
           if (!ok) break;
           const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_bytes;
-          mbar_expect_tx(bar_full + 8 * s, a_bytes + (uint32_t)sp.b_rows * 128u);
-          tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, (gx0 + sp.a_x0) * p.in_stride + sp.dx,
-                      gy0 * p.in_stride + sp.dy, n);
-          const int row0 = sp.b_row + ntile * p.bn;
-          for (int r = 0; r < sp.b_rows; r += p.b_box_rows)
-            tma_load_2d(dstB + (uint32_t)r * 128u, &tmB, bar_full + 8 * s, sp.b_k, row0 + r);
+          mbar_expect_tx(bar_full + 8 * s, a_bytes + (p.b_resident ? 0u : (uint32_t)sp.b_rows * 128u));
+          tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, (gx0 + sp.a_x0) * p.in_stride + sp.dx - p.pad_l,
+                      gy0 * p.in_stride + sp.dy - p.pad_t, n);
+          if (!p.b_resident) {
+            const int row0 = sp.b_row + ntile * p.bn;
+            for (int r = 0; r < sp.b_rows; r += p.b_box_rows)
+              tma_load_2d(dstB + (uint32_t)r * 128u, &tmB, bar_full + 8 * s, sp.b_k, row0 + r);
+          }
         }
       }
     }
@@ -205,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
       bool ok = true;
+      if (p.b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
         const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
         ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4);
@@ -212,12 +237,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc_fence_after();
         const uint32_t acc = tmem_base + as * (uint32_t)p.bn;
         for (int si = 0; si < p.n_steps; ++si, ++it) {
-          const TcStep& sp = p.steps[si];
+          const TcStep& sp = steps[si];
           const uint32_t s = it % (uint32_t)p.n_stages, ph = (it / (uint32_t)p.n_stages) & 1u;
           ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t sA = smem_base + s * stage_bytes, sB = sA + a_bytes;
+          const uint32_t sA = smem_base + s * stage_bytes, sB = p.b_resident ? sBres : sA + a_bytes;
           const uint64_t da = umma_desc_sw128(sA);
           for (int m = 0; m < sp.n_mma; ++m) {
             const TcMma mm = sp.mma[m];
@@ -255,10 +280,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc_fence_after();
       const uint32_t acc = tmem_base + as * (uint32_t)p.bn + lane_addr;
       if (p.epi_mode == EPI_GENERIC) {
-        const int gy = (tr / p.tiles_x) * p.bh + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
+        const int gyb = (tr / p.tiles_x) * p.bh * p.rows_per_tile + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
         const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
         for (int g = 0; g < p.n_groups; ++g) {
-          const int phase = p.group_phase[g];
+          const int phase = p.rows_per_tile > 1 ? 0 : p.group_phase[g];
+          const int gy = gyb + (p.rows_per_tile > 1 ? g * p.bh : 0);
           const int oy = gy * p.out_scale + (phase >> 1), ox = gx * p.out_scale + (phase & 1);
           const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
           for (int j = 0; j < p.group_cols; j += 16) {
@@ -307,65 +333,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       } else if (p.epi_mode == EPI_HEADS) {
-        // tile = one image row; accumulator columns [half*16 + kw*2 + o] hold the vertical 7x1 partial sums
-        // Y[x][kw][o]; out[x][o] = sum_kw Y[x+kw-3][kw][o] (zero outside the row) + bias  (model.py:246-247)
-        const int y = tr;
+        // tile = R image rows of 256 pixels; accumulator group (row rr, half) = 16 columns [kw*2 + o] holding the
+        // vertical 7x1 partial sums Y[x][kw][o];  out[x][o] = sum_kw Y[x+kw-3][kw][o] (zero outside the row)
+        // + bias (model.py:246-247), then the grey composition (model.py:250-252).
+        const int y0 = tr * p.rows_per_tile;
         const int xg = half * 128 + r;
-        float v[16];
-        tmem_ld16(acc + (uint32_t)(half * 16), v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);          // accumulator drained: MMA may start the next row
         float* rowbuf = epi_smem;                                   // [256 + 6][16], 3 zero columns either side
         if (threadIdx.x - 64 < 96) {
           const int i = threadIdx.x - 64;                           // zero the two halos (3 x 16 each)
-          rowbuf[(i < 48 ? 0 : (259 - 3) * 16) + i] = 0.f;
+          rowbuf[(i < 48 ? 0 : 256 * 16) + i] = 0.f;
         }
+        const float b2 = __ldg(e.bias), b3 = __ldg(e.bias + 1);
+        for (int rr = 0; rr < p.rows_per_tile; ++rr) {
+          float v[16];
+          tmem_ld16(acc + (uint32_t)((half * p.rows_per_tile + rr) * 16), v);
+          if (rr == p.rows_per_tile - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);        // accumulators drained: MMA may start the next tile
+          }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rowbuf[(xg + 3) * 16 + i] = v[i];
-        epi_bar_sync();
-        float c2 = __ldg(e.bias), c3 = __ldg(e.bias + 1);
+          for (int i = 0; i < 16; ++i) rowbuf[(xg + 3) * 16 + i] = v[i];
+          epi_bar_sync();
+          float c2 = b2, c3 = b3;
 #pragma unroll
-        for (int kw = 0; kw < 7; ++kw) {
-          const float2 t = *reinterpret_cast<const float2*>(rowbuf + (xg + kw) * 16 + kw * 2);
-          c2 += t.x;
-          c3 += t.y;
-        }
-        epi_bar_sync();                                             // row buffer free for the next tile
-        const size_t pidx = ((size_t)n * p.OH + y) * p.OW + xg;
-        const float mask = tanhf(c2);
-        const float g = x.img[3 * pidx] * kGrayR + x.img[3 * pidx + 1] * kGrayG + x.img[3 * pidx + 2] * kGrayB;
-        const float gs = g * (1.f + mask) + c3;
-        x.difgs[pidx] = gs - g;
-        x.gs_f32[pidx] = gs;
-        if (x.gs_out) x.gs_out[pidx] = gs;
-        if (x.mask22_out) {
-          x.mask22_out[3 * pidx] = fmaxf(mask, 0.f);
-          x.mask22_out[3 * pidx + 1] = mask * 0.f;
-          x.mask22_out[3 * pidx + 2] = fmaxf(-mask, 0.f);
+          for (int kw = 0; kw < 7; ++kw) {
+            const float2 t = *reinterpret_cast<const float2*>(rowbuf + (xg + kw) * 16 + kw * 2);
+            c2 += t.x;
+            c3 += t.y;
+          }
+          epi_bar_sync();                                           // row buffer free for the next row
+          const size_t pidx = ((size_t)n * p.OH + (y0 + rr)) * p.OW + xg;
+          const float mask = tanhf(c2);
+          const float g = x.img[3 * pidx] * kGrayR + x.img[3 * pidx + 1] * kGrayG + x.img[3 * pidx + 2] * kGrayB;
+          const float gs = g * (1.f + mask) + c3;
+          x.difgs[pidx] = gs - g;
+          x.gs_f32[pidx] = gs;
+          if (x.gs_out) x.gs_out[pidx] = gs;
+          if (x.mask22_out) {
+            x.mask22_out[3 * pidx] = fmaxf(mask, 0.f);
+            x.mask22_out[3 * pidx + 1] = mask * 0.f;
+            x.mask22_out[3 * pidx + 2] = fmaxf(-mask, 0.f);
+          }
         }
       } else {
-        // EPI_CLR: clr_conv1 over f (tensor cores, 16 couts) + the gs channel of the concat (model.py:267) as a
-        // 3x3 fp32 conv on CUDA cores, then clr_conv2 / clr_conv3 and the final dif (model.py:268-269, 288).
-        // Both epilogue halves hold the same 16 columns: half h handles rows of parity h (idle otherwise).
-        const int gy = (tr / p.tiles_x) * p.bh + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
-        float v[16];
-        tmem_ld16(acc, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-        if ((r & 1) == half) {
-          const float* wg = epi_smem;                 // [9][16]
-          const float* w2 = epi_smem + 144;           // [16 in][16 out]
-          const float* b2 = w2 + 256;
-          const float* w3 = b2 + 16;                  // [16 in][3 out]
-          const float* b3 = w3 + 48;
-          const float* gsn = x.gs_f32 + (size_t)n * p.OH * p.OW;
+        // EPI_CLR: clr_conv1 over f (tensor cores, "kw expansion": group (row rr, half) = 48 columns [kw*16 + o] of
+        // vertical 3x1 partial sums) + the gs channel of the concat (model.py:267) as a 3x3 fp32 conv on CUDA
+        // cores, then clr_conv2 / clr_conv3 and the final dif (model.py:268-269, 288).
+        const int y0 = tr * p.rows_per_tile;
+        const int xg = half * 128 + r;
+        const float* wg = epi_smem;                 // [9][16]
+        const float* w2 = epi_smem + 144;           // [16 in][16 out]
+        const float* b2 = w2 + 256;
+        const float* w3 = b2 + 16;                  // [16 in][3 out]
+        const float* b3 = w3 + 48;
+        float* rowbuf = epi_smem + 512;             // [256 + 2][48], one zero column either side
+        if (threadIdx.x - 64 < 96) {
+          const int i = threadIdx.x - 64;
+          rowbuf[(i < 48 ? 0 : 256 * 48) + i] = 0.f;
+        }
+        const float* gsn = x.gs_f32 + (size_t)n * p.OH * p.OW;
+        for (int rr = 0; rr < p.rows_per_tile; ++rr) {
+          const int gy = y0 + rr;
+          {
+            float* dst = rowbuf + (xg + 1) * 48;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + i);
+            for (int c = 0; c < 48; c += 16) {
+              float v[16];
+              tmem_ld16(acc + (uint32_t)((half * p.rows_per_tile + rr) * 48 + c), v);
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          }
+          if (rr == p.rows_per_tile - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          }
+          epi_bar_sync();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(e.bias + i);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float* src = rowbuf + (xg + kw) * 48 + kw * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(src + i);
+              v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+            }
+          }
+          epi_bar_sync();
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int yy = gy + t / 3 - 1, xx = gx + t % 3 - 1;
+            const int yy = gy + t / 3 - 1, xx = xg + t % 3 - 1;
             if (yy >= 0 && yy < p.OH && xx >= 0 && xx < p.OW) {
               const float gv = gsn[(size_t)yy * p.OW + xx];
 #pragma unroll
@@ -377,20 +438,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           float hbuf[16];
 #pragma unroll
           for (int o = 0; o < 16; ++o) {
-            float s = b2[o];
+            float sacc = b2[o];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) s = fmaf(v[c], w2[c * 16 + o], s);
-            hbuf[o] = leaky(s);
+            for (int c = 0; c < 16; ++c) sacc = fmaf(v[c], w2[c * 16 + o], sacc);
+            hbuf[o] = leaky(sacc);
           }
           float rgb[3];
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
-            float s = b3[o];
+            float sacc = b3[o];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) s = fmaf(hbuf[c], w3[c * 3 + o], s);
-            rgb[o] = s;
+            for (int c = 0; c < 16; ++c) sacc = fmaf(hbuf[c], w3[c * 3 + o], sacc);
+            rgb[o] = sacc;
           }
-          const size_t pidx = ((size_t)n * p.OH + gy) * p.OW + gx;
+          const size_t pidx = ((size_t)n * p.OH + gy) * p.OW + xg;
           if (x.rgb_out) {
             x.rgb_out[3 * pidx] = rgb[0];
             x.rgb_out[3 * pidx + 1] = rgb[1];
@@ -436,6 +497,9 @@ inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>
   uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
   uint32_t box[2] = {TC_BK, (uint32_t)t.b_box_rows};
   if (!tma.encode_bf16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
+  if (cudaMalloc(&t.steps_dev, sizeof t.steps) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
+  if (cudaMemcpy(t.steps_dev, t.steps, sizeof t.steps, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
+  t.b_total_rows = (int)rows;
   t.ready = true;
   return true;
 }
@@ -445,6 +509,19 @@ inline bool tc_disabled(const std::string& name) {
   if (!dis) return false;
   std::string d = std::string(",") + dis + ",";
   return d.find("," + name + ",") != std::string::npos;
+}
+
+// Vertical-tap multi-row tiles: input row j (0 .. R+KH-2) of a tile feeds output row rr = j - kh with filter row kh.
+// Weights are stored in DESCENDING filter-row order (block i <-> kh = KH-1-i) so that, for one input row, the
+// weight blocks of consecutive output rows are consecutive too: all rows that already hold a partial sum are
+// updated by ONE wide MMA (A read from shared memory once), and the row whose first tap this is by a second MMA
+// with accumulate = 0.  Accumulator column of (group base, row rr) = (base + rr) * nb.
+inline void tc_rows_step(TcStep& sp, int j, int R, int KH, int nb, int base) {
+  sp.n_mma = 0;
+  const int lo = j - (KH - 1) > 0 ? j - (KH - 1) : 0, hi = j - 1 < R - 1 ? j - 1 : R - 1;
+  if (hi >= lo)
+    sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + lo) * nb), (int16_t)((hi - lo + 1) * nb), (int16_t)((lo + KH - 1 - j) * nb), 0};
+  if (j <= R - 1) sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + j) * nb), (int16_t)nb, (int16_t)((KH - 1) * nb), 1};
 }
 
 // Build the step program and the packed bf16 weight matrix of one layer from canonical fp32
@@ -465,54 +542,70 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     // 7x7 conv over 3 channels (model.py:203): K per filter ROW = 7 taps x 8 (3 real + 5 zero) channels + one
     // zero-weight pixel = 64 elements, fetched as an overlapping window of the packed image.
     if (kh != 7 || kw != 7 || cin > 8 || transposed) { *why = "conv1 must be 7x7 with <= 8 input channels"; return false; }
-    t.kind = TC_ROWPACK; t.cin_pad = 64; t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1;
-    t.b_box_rows = t.bn; t.b_stage_rows = t.bn; t.n_steps = 7;
-    const size_t K = 7 * 64, rows = t.bn;
+    // Tile = R = 8 output rows x 128 pixels: input row j (of R+6) feeds output row rr = j-kh with filter row kh, so
+    // every packed row is fetched once per tile; the 28 KB of weights stay resident in shared memory.
+    const int R = 8, nb = (cout + 15) / 16 * 16;
+    t.kind = TC_ROWPACK; t.cin_pad = 64; t.bn = R * nb; t.n_tiles = 1;
+    t.b_box_rows = nb; t.b_stage_rows = 0; t.b_resident = 1; t.rows_per_tile = R; t.halves = 1;
+    const size_t K = 64, rows = 7 * (size_t)nb;
     std::vector<uint16_t> host(rows * K, 0);
-    for (int a = 0; a < 7; ++a) {
-      TcStep& s = t.steps[a];
-      s.dy = (int8_t)(a - 3); s.dx = 0; s.a_c0 = 0; s.b_rows = (int16_t)t.bn; s.b_k = a * 64; s.b_row = 0;
-      s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(a == 0)};
+    for (int a = 0; a < 7; ++a)
       for (int b = 0; b < 7; ++b)
         for (int c = 0; c < cin; ++c)
-          for (int o = 0; o < cout; ++o) host[(size_t)o * K + a * 64 + b * 8 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+          for (int o = 0; o < cout; ++o) host[((size_t)(6 - a) * nb + o) * K + b * 8 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+    int ns = 0;
+    for (int j = 0; j < R + 6; ++j) {
+      TcStep& sp = t.steps[ns++];
+      sp.dy = (int8_t)(j - 3); sp.dx = 0; sp.a_c0 = 0; sp.b_rows = 0; sp.b_k = 0; sp.b_row = 0;
+      tc_rows_step(sp, j, R, 7, nb, 0);
     }
+    t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
   }
 
   if (name == "heads") {
     // conv2|conv3 (7x7, 64 -> 2): accumulator column kw*2+o = sum_kh sum_c in[y+kh-3][x][c] * W[kh][kw][c][o]
     if (kh != 7 || kw != 7 || cin != 64 || cout != 2) { *why = "heads must be 7x7 64->2"; return false; }
-    t.kind = TC_HEADS; t.cin_pad = 64; t.bn = 32; t.n_tiles = 1; t.b_box_rows = 16; t.b_stage_rows = 16;
-    t.n_steps = 14; t.tile_w = 128;
-    const size_t K = 7 * 64, rows = 16;
+    const int R = 8;
+    t.kind = TC_HEADS; t.cin_pad = 64; t.bn = R * 2 * 16; t.n_tiles = 1; t.b_box_rows = 16; t.b_stage_rows = 0;
+    t.b_resident = 1; t.rows_per_tile = R; t.halves = 2; t.tile_w = 128;
+    const size_t K = 64, rows = 7 * 16;
     std::vector<uint16_t> host(rows * K, 0);
     for (int a = 0; a < 7; ++a)
       for (int b = 0; b < 7; ++b)
         for (int c = 0; c < 64; ++c)
-          for (int o = 0; o < 2; ++o) host[(size_t)(b * 2 + o) * K + a * 64 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+          for (int o = 0; o < 2; ++o) host[((size_t)(6 - a) * 16 + b * 2 + o) * K + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+    int ns = 0;
     for (int hh = 0; hh < 2; ++hh)
-      for (int a = 0; a < 7; ++a) {
-        TcStep& s = t.steps[hh * 7 + a];
-        s.dy = (int8_t)(a - 3); s.dx = 0; s.a_x0 = (int16_t)(hh * 128); s.a_c0 = 0; s.b_rows = 16; s.b_k = a * 64;
-        s.b_row = 0; s.n_mma = 1; s.mma[0] = TcMma{(int16_t)(hh * 16), 16, 0, (int16_t)(a == 0)};
+      for (int j = 0; j < R + 6; ++j) {
+        TcStep& sp = t.steps[ns++];
+        sp.dy = (int8_t)(j - 3); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
+        tc_rows_step(sp, j, R, 7, 16, hh * R);
       }
+    t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
   }
 
   if (name == "clr_conv1") {
     // canonical input order [f0..f63, gs]: f runs on tensor cores, gs (fp32) in the epilogue
     if (kh != 3 || kw != 3 || cin != 65 || cout != 16) { *why = "clr_conv1 must be 3x3 65->16"; return false; }
-    t.kind = TC_CLR; t.cin_pad = 64; t.bn = 16; t.n_tiles = 1; t.b_box_rows = 16; t.b_stage_rows = 16; t.n_steps = 9;
-    const size_t K = 9 * 64, rows = 16;
+    const int R = 2;
+    t.kind = TC_CLR; t.cin_pad = 64; t.bn = R * 2 * 48; t.n_tiles = 1; t.b_box_rows = 48; t.b_stage_rows = 0;
+    t.b_resident = 1; t.rows_per_tile = R; t.halves = 2; t.tile_w = 128;
+    const size_t K = 64, rows = 3 * 48;
     std::vector<uint16_t> host(rows * K, 0);
-    for (int tap = 0; tap < 9; ++tap) {
-      TcStep& s = t.steps[tap];
-      s.dy = (int8_t)(tap / 3 - 1); s.dx = (int8_t)(tap % 3 - 1); s.a_c0 = 0; s.b_rows = 16; s.b_k = tap * 64; s.b_row = 0;
-      s.n_mma = 1; s.mma[0] = TcMma{0, 16, 0, (int16_t)(tap == 0)};
-      for (int c = 0; c < 64; ++c)
-        for (int o = 0; o < 16; ++o) host[(size_t)o * K + tap * 64 + c] = f32_to_bf16_bits(W(tap, c, o));
-    }
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 64; ++c)
+          for (int o = 0; o < 16; ++o) host[((size_t)(2 - a) * 48 + b * 16 + o) * K + c] = f32_to_bf16_bits(W(a * 3 + b, c, o));
+    int ns = 0;
+    for (int hh = 0; hh < 2; ++hh)
+      for (int j = 0; j < R + 2; ++j) {
+        TcStep& sp = t.steps[ns++];
+        sp.dy = (int8_t)(j - 1); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
+        tc_rows_step(sp, j, R, 3, 48, hh * R);
+      }
+    t.n_steps = ns;
     (void)bias;
     return tc_upload(tma, t, host, rows, K, why);
   }
@@ -651,16 +744,19 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     pad_t = tot_h / 2; pad_l = tot_w / 2;        // TF SAME: before = total // 2
   }
   p.n_steps = t.n_steps;
-  for (int i = 0; i < t.n_steps; ++i) {
-    p.steps[i] = t.steps[i];
-    if (t.kind == TC_CONV && !t.transposed) { p.steps[i].dy -= (int8_t)pad_t; p.steps[i].dx -= (int8_t)pad_l; }
-  }
+  p.steps = t.steps_dev;
+  if (t.kind == TC_CONV && !t.transposed) { p.pad_t = pad_t; p.pad_l = pad_l; }
+  p.rows_per_tile = t.rows_per_tile; p.halves = t.halves;
+  p.b_resident = t.b_resident; p.b_total_rows = t.b_total_rows;
   p.bw = t.tile_w ? t.tile_w : (GW < TC_BM ? GW : TC_BM);
   p.bh = TC_BM / p.bw;
   p.epi_mode = t.kind == TC_HEADS ? EPI_HEADS : (t.kind == TC_CLR ? EPI_CLR : EPI_GENERIC);
-  if (t.kind == TC_HEADS) {
-    if (GW != 256) { tma.last_error = "heads kernel needs 256-pixel rows"; return -4; }
-    p.tiles_x = 1; p.tiles_y = GH;
+  if (t.halves == 2) {
+    if (GW != 256 || GH % t.rows_per_tile) { tma.last_error = "row-tile kernels need 256-pixel rows"; return -4; }
+    p.tiles_x = 1; p.tiles_y = GH / t.rows_per_tile;
+  } else if (t.rows_per_tile > 1) {
+    if (GW % p.bw || GH % t.rows_per_tile || p.bh != 1) { tma.last_error = "multi-row tiles need full 128-pixel rows"; return -4; }
+    p.tiles_x = GW / p.bw; p.tiles_y = GH / t.rows_per_tile;
   } else {
     if (GW % p.bw || GH % p.bh) { tma.last_error = "spatial size not tileable into 128-pixel rectangles"; return -1; }
     p.tiles_x = GW / p.bw; p.tiles_y = GH / p.bh;
@@ -669,12 +765,16 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   if (t.kind == TC_CONVT_FUSED) {
     p.n_groups = 4; p.group_cols = t.cout;
     p.group_phase[0] = 0; p.group_phase[1] = 2; p.group_phase[2] = 1; p.group_phase[3] = 3;   // p00 p10 p01 p11
+  } else if (t.rows_per_tile > 1) {
+    p.n_groups = t.rows_per_tile; p.group_cols = t.bn / t.rows_per_tile;      // TC_ROWPACK: one group per output row
   } else {
     p.n_groups = 1; p.group_cols = t.bn;
     p.group_phase[0] = phase < 0 ? 0 : phase;
   }
+  const int epi_bytes = p.epi_mode == EPI_HEADS ? 262 * 16 * 4 : (p.epi_mode == EPI_CLR ? 2048 + 258 * 48 * 4 : 0);
+  const int fixed_bytes = 1024 + (t.b_resident ? t.b_total_rows * 128 : 0) + 192 + (int)(TC_MAX_STEPS * sizeof(TcStep)) + epi_bytes + 64;
   p.stage_bytes = TC_BM * 128 + t.b_stage_rows * 128;
-  p.n_stages = TC_SMEM_BUDGET / p.stage_bytes;
+  p.n_stages = (TC_SMEM_BUDGET + 20 * 1024 - fixed_bytes) / p.stage_bytes;
   if (p.n_stages > 8) p.n_stages = 8;
   if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }
   p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
@@ -699,7 +799,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     if (cache.size() > 4096) cache.clear();
     it = cache.emplace(key, m).first;
   }
-  const size_t smem = 1024 + (size_t)p.n_stages * p.stage_bytes + 192 + (p.epi_mode == EPI_HEADS ? 262 * 16 * 4 : 2048) + 64;
+  const size_t smem = (size_t)fixed_bytes + (size_t)p.n_stages * p.stage_bytes;
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(it->second, t.map, p, e, x);
   (*launches)++;
