@@ -761,7 +761,8 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
       for (int o = 0; o < 16; ++o) aux[t * 16 + o] = c1.w_host[((size_t)t * 65 + 64) * 16 + o];
     memcpy(&aux[144], c2.w_host.data(), 256 * 4);
     memcpy(&aux[400], c2.b_host.data(), 16 * 4);
-    memcpy(&aux[416], c3.w_host.data(), 48 * 4);
+    for (int c = 0; c < 16; ++c)
+      for (int o = 0; o < 3; ++o) aux[416 + o * 16 + c] = c3.w_host[c * 3 + o];       // transposed: [3 out][16 in]
     memcpy(&aux[464], c3.b_host.data(), 3 * 4);
     if (c1.tc.aux) cudaFree(c1.tc.aux);
     CK(h, cudaMalloc(&c1.tc.aux, aux.size() * 4));

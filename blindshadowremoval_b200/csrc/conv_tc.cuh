@@ -73,6 +73,8 @@ struct TcWeights {
   int halves = 1;         // 2: a tile row is 256 pixels = two 128-pixel A tiles
   int b_resident = 0;     // whole weight matrix stays in shared memory for the life of the CTA
   int b_total_rows = 0;
+  int b_res_kblocks = 1;
+  int can_reside = 0;
   TcStep steps[TC_MAX_STEPS];
   TcStep* steps_dev = nullptr;
   bf16* dev = nullptr;
@@ -120,6 +122,7 @@ struct ConvTcParams {
   int rows_per_tile, halves;  // multi-row tiles (groups = rows x halves)
   int pad_t, pad_l;           // SAME padding subtracted from the step shifts (plain convs)
   int b_resident, b_total_rows;
+  int b_res_kblocks;          // resident weights: number of 64-element K blocks kept ([kblock][row] layout)
   int* errflag;
   const TcStep* steps;        // device copy of the step program
 };
@@ -145,6 +148,20 @@ __device__ __forceinline__ void add_res16(const void* base, size_t pix, int ld, 
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Programmatic dependent launch: everything before pdl_wait() (barrier init, TMEM alloc, weight / bias staging)
+// overlaps the tail of the previous kernel in the stream; nothing produced by that kernel is touched before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ void add_bf16x16(const uint4& a, const uint4& b, float* v) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] += __low2float(t);
+    v[2 * i + 1] += __high2float(t);
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -155,7 +172,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t a_bytes = TC_BM * 128;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
   const uint32_t sBres = smem_base + (uint32_t)p.n_stages * stage_bytes;            // resident weights (optional)
-  const uint32_t bars = sBres + (p.b_resident ? (uint32_t)p.b_total_rows * 128u : 0u);
+  // NOTE: for multi-row kinds b_k is 0 and b_row 0, so the resident address reduces to sBres + mma.brow rows.
+  const uint32_t bars = sBres + (p.b_resident ? (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u : 0u);
   // full[8], empty[8], tmem_full[2], tmem_empty[2], bres, tmem slot
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_tfull = bars + 128, bar_tempty = bars + 144;
   const uint32_t bar_bres = bars + 160, tmem_slot = bars + 168;
@@ -193,16 +211,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
       bool ok = true;
-      if (p.b_resident) {
-        mbar_expect_tx(bar_bres, (uint32_t)p.b_total_rows * 128u);
-        for (int r = 0; r < p.b_total_rows; r += p.b_box_rows) tma_load_2d(sBres + (uint32_t)r * 128u, &tmB, bar_bres, 0, r);
+      if (p.b_resident) {          // weights are static: fetched before the dependency wait
+        mbar_expect_tx(bar_bres, (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u);
+        for (int kb = 0; kb < p.b_res_kblocks; ++kb)
+          for (int r = 0; r < p.b_total_rows; r += p.b_box_rows)
+            tma_load_2d(sBres + (uint32_t)(kb * p.b_total_rows + r) * 128u, &tmB, bar_bres, kb * TC_BK, r);
       }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
         const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
         const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
@@ -242,7 +264,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t sA = smem_base + s * stage_bytes, sB = p.b_resident ? sBres : sA + a_bytes;
+          const uint32_t sA = smem_base + s * stage_bytes;
+          const uint32_t sB = p.b_resident
+                                  ? sBres + (uint32_t)((sp.b_k >> 6) * p.b_total_rows + sp.b_row + (tile % p.n_tiles) * p.bn) * 128u
+                                  : sA + a_bytes;
           const uint64_t da = umma_desc_sw128(sA);
           for (int m = 0; m < sp.n_mma; ++m) {
             const TcMma mm = sp.mma[m];
@@ -266,85 +291,133 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t tcount = 0;
     bool ok = true;
-    if (p.epi_mode == EPI_CLR) {
-      // stage the colour-tail weights once: [9][16] gs taps, [16][16] w2, [16] b2, [16][3] w3, [3] b3
-      for (int i = threadIdx.x - 64; i < 144 + 256 + 16 + 48 + 3; i += 256) epi_smem[i] = x.aux[i];
-      epi_bar_sync();
-    }
+    // static data first (bias, colour-tail weights): not produced by the previous kernel
+    float* bias_s = epi_smem;                   // [512] (the device bias buffer is zero-padded past cout)
+    float* epi_work = epi_smem + 512;
+    for (int i = threadIdx.x - 64; i < 512; i += 256) bias_s[i] = __ldg(e.bias + i);
+    if (p.epi_mode == EPI_CLR)
+      for (int i = threadIdx.x - 64; i < 144 + 256 + 16 + 48 + 3; i += 256) epi_work[i] = x.aux[i];
+    epi_bar_sync();
+    pdl_wait();
+    const bool has_res = e.res1 != nullptr || e.res2 != nullptr;
     for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
       const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
       const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
       const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
-      ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
-      if (!ok) break;
-      tc_fence_after();
       const uint32_t acc = tmem_base + as * (uint32_t)p.bn + lane_addr;
       if (p.epi_mode == EPI_GENERIC) {
         const int gyb = (tr / p.tiles_x) * p.bh * p.rows_per_tile + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
         const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
-        for (int g = 0; g < p.n_groups; ++g) {
+        const int cbase = p.n_groups == 1 ? ntile * p.bn : 0;
+        // residual / skip operands of this thread's first 5 chunks are fetched BEFORE the accumulator wait, so their
+        // global-load latency hides behind the MMA main loop (plain convs only: one pixel per thread)
+        uint4 rb1[5][2], rb2[5][2];
+        uint32_t m1 = 0, m2 = 0;
+        if (has_res && p.n_groups == 1) {
+          const size_t pix0 = ((size_t)n * p.OH + gyb) * p.OW + gx;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int col = (2 * k + half) * 16, c = cbase + col;
+            if (col < p.bn && c + 16 <= e.out_c) {
+              if (e.res1 != nullptr && c + 16 <= e.res1_c) {
+                const uint4* src = reinterpret_cast<const uint4*>((const bf16*)e.res1 + pix0 * e.res1_ld + c);
+                rb1[k][0] = src[0]; rb1[k][1] = src[1]; m1 |= 1u << k;
+              }
+              if (e.res2 != nullptr && c + 16 <= e.res2_c) {
+                const uint4* src = reinterpret_cast<const uint4*>((const bf16*)e.res2 + pix0 * e.res2_ld + c);
+                rb2[k][0] = src[0]; rb2[k][1] = src[1]; m2 |= 1u << k;
+              }
+            }
+          }
+        }
+        ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        if (!ok) break;
+        tc_fence_after();
+        const int total_cols = p.n_groups * p.group_cols;
+        auto chunk = [&](const int col, const bool pf1, const uint4& r1a, const uint4& r1b, const bool pf2,
+                         const uint4& r2a, const uint4& r2b) {
+          const int g = col / p.group_cols, j = col - g * p.group_cols;
+          const int c = cbase + j;
+          if (c >= e.out_c) return;
           const int phase = p.rows_per_tile > 1 ? 0 : p.group_phase[g];
           const int gy = gyb + (p.rows_per_tile > 1 ? g * p.bh : 0);
           const int oy = gy * p.out_scale + (phase >> 1), ox = gx * p.out_scale + (phase & 1);
           const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-          for (int j = 0; j < p.group_cols; j += 16) {
-            const int col = g * p.group_cols + j;
-            if (((col >> 4) & 1) != half) continue;
-            const int c = ntile * p.bn * (p.n_groups == 1 ? 1 : 0) + j;
-            if (c >= e.out_c) break;
-            float v[16];
-            tmem_ld16(acc + (uint32_t)col, v);
-            if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
+          float v[16];
+          tmem_ld16(acc + (uint32_t)col, v);
+          if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);      // bias is zero-padded past cout
-              if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
-              if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
-              if (e.act) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-              }
-              if (e.out_mode == OUT_F32) {
-                float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) dst[i] = v[i];
-              } else if (e.out_mode == OUT_QKV && c >= 256) {
-                // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
-                bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * p.OW + gx);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
-              } else {
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-                o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-                o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-                const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
-                uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
-                dst[0] = o0;
-                dst[1] = o1;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
+            if (pf1) add_bf16x16(r1a, r1b, v);
+            else if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
+            if (pf2) add_bf16x16(r2a, r2b, v);
+            else if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
+            if (e.act) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
+            }
+            if (e.out_mode == OUT_F32) {
+              float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dst[i] = v[i];
+            } else if (e.out_mode == OUT_QKV && c >= 256) {
+              // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
+              bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * p.OW + gx);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
+            } else {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+              o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+              o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+              o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+              const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
+              uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
+              dst[0] = o0;
+              dst[1] = o1;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
           }
+        };
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int col = (2 * k + half) * 16;
+          if (col < total_cols) chunk(col, (m1 >> k) & 1u, rb1[k][0], rb1[k][1], (m2 >> k) & 1u, rb2[k][0], rb2[k][1]);
         }
+#pragma unroll 1
+        for (int col = (10 + half) * 16; col < total_cols; col += 32) chunk(col, false, rb1[0][0], rb1[0][1], false, rb2[0][0], rb2[0][1]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       } else if (p.epi_mode == EPI_HEADS) {
-        // tile = R image rows of 256 pixels; accumulator group (row rr, half) = 16 columns [kw*2 + o] holding the
+        // tile = R image rows of 256 pixels; accumulator group (half, row rr) = 16 columns [kw*2 + o] holding the
         // vertical 7x1 partial sums Y[x][kw][o];  out[x][o] = sum_kw Y[x+kw-3][kw][o] (zero outside the row)
         // + bias (model.py:246-247), then the grey composition (model.py:250-252).
         const int y0 = tr * p.rows_per_tile;
         const int xg = half * 128 + r;
-        float* rowbuf = epi_smem;                                   // [256 + 6][16], 3 zero columns either side
+        float* rowbuf = epi_work;                                   // [256 + 6][16], 3 zero columns either side
         if (threadIdx.x - 64 < 96) {
           const int i = threadIdx.x - 64;                           // zero the two halos (3 x 16 each)
           rowbuf[(i < 48 ? 0 : 256 * 16) + i] = 0.f;
         }
-        const float b2 = __ldg(e.bias), b3 = __ldg(e.bias + 1);
+        const float b2 = bias_s[0], b3 = bias_s[1];
+        const size_t p0 = ((size_t)n * p.OH + y0) * p.OW + xg;
+        float i0 = x.img[3 * p0], i1 = x.img[3 * p0 + 1], i2 = x.img[3 * p0 + 2];     // prefetched one row ahead
+        ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        if (!ok) break;
+        tc_fence_after();
         for (int rr = 0; rr < p.rows_per_tile; ++rr) {
+          const size_t pidx = p0 + (size_t)rr * p.OW;
+          const float g = i0 * kGrayR + i1 * kGrayG + i2 * kGrayB;
+          if (rr + 1 < p.rows_per_tile) {
+            const size_t pn = pidx + p.OW;
+            i0 = x.img[3 * pn]; i1 = x.img[3 * pn + 1]; i2 = x.img[3 * pn + 2];
+          }
           float v[16];
           tmem_ld16(acc + (uint32_t)((half * p.rows_per_tile + rr) * 16), v);
           if (rr == p.rows_per_tile - 1) {
@@ -353,7 +426,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);        // accumulators drained: MMA may start the next tile
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) rowbuf[(xg + 3) * 16 + i] = v[i];
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(rowbuf + (xg + 3) * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           epi_bar_sync();
           float c2 = b2, c3 = b3;
 #pragma unroll
@@ -363,9 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             c3 += t.y;
           }
           epi_bar_sync();                                           // row buffer free for the next row
-          const size_t pidx = ((size_t)n * p.OH + (y0 + rr)) * p.OW + xg;
           const float mask = tanhf(c2);
-          const float g = x.img[3 * pidx] * kGrayR + x.img[3 * pidx + 1] * kGrayG + x.img[3 * pidx + 2] * kGrayB;
           const float gs = g * (1.f + mask) + c3;
           x.difgs[pidx] = gs - g;
           x.gs_f32[pidx] = gs;
@@ -377,24 +449,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
         }
       } else {
-        // EPI_CLR: clr_conv1 over f (tensor cores, "kw expansion": group (row rr, half) = 48 columns [kw*16 + o] of
+        // EPI_CLR: clr_conv1 over f (tensor cores, "kw expansion": group (half, row rr) = 48 columns [kw*16 + o] of
         // vertical 3x1 partial sums) + the gs channel of the concat (model.py:267) as a 3x3 fp32 conv on CUDA
         // cores, then clr_conv2 / clr_conv3 and the final dif (model.py:268-269, 288).
         const int y0 = tr * p.rows_per_tile;
         const int xg = half * 128 + r;
-        const float* wg = epi_smem;                 // [9][16]
-        const float* w2 = epi_smem + 144;           // [16 in][16 out]
-        const float* b2 = w2 + 256;
-        const float* w3 = b2 + 16;                  // [16 in][3 out]
-        const float* b3 = w3 + 48;
-        float* rowbuf = epi_smem + 512;             // [256 + 2][48], one zero column either side
+        const float4* wg4 = reinterpret_cast<const float4*>(epi_work);            // [9][16]
+        const float4* w24 = reinterpret_cast<const float4*>(epi_work + 144);      // [16 in][16 out]
+        const float4* b24 = reinterpret_cast<const float4*>(epi_work + 400);
+        const float4* w3t4 = reinterpret_cast<const float4*>(epi_work + 416);     // [3 out][16 in]
+        const float* b3 = epi_work + 464;
+        float* rowbuf = epi_work + 512;             // [256 + 2][48], one zero column either side
         if (threadIdx.x - 64 < 96) {
           const int i = threadIdx.x - 64;
           rowbuf[(i < 48 ? 0 : 256 * 48) + i] = 0.f;
         }
         const float* gsn = x.gs_f32 + (size_t)n * p.OH * p.OW;
+        ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        if (!ok) break;
+        tc_fence_after();
         for (int rr = 0; rr < p.rows_per_tile; ++rr) {
           const int gy = y0 + rr;
+          const size_t pidx = ((size_t)n * p.OH + gy) * p.OW + xg;
+          // issue the 9 gs taps and the input pixel first: their latency overlaps the TMEM / smem exchange below
+          float gv[9];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int yy = gy + t / 3 - 1, xx = xg + t % 3 - 1;
+            gv[t] = (yy >= 0 && yy < p.OH && xx >= 0 && xx < p.OW) ? gsn[(size_t)yy * p.OW + xx] : 0.f;
+          }
+          const float i0 = x.img[3 * pidx], i1 = x.img[3 * pidx + 1], i2 = x.img[3 * pidx + 2];
           {
             float* dst = rowbuf + (xg + 1) * 48;
 #pragma unroll
@@ -413,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           epi_bar_sync();
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __ldg(e.bias + i);
+          for (int i = 0; i < 16; ++i) v[i] = bias_s[i];
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const float* src = rowbuf + (xg + kw) * 48 + kw * 16;
@@ -426,32 +510,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           epi_bar_sync();
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int yy = gy + t / 3 - 1, xx = xg + t % 3 - 1;
-            if (yy >= 0 && yy < p.OH && xx >= 0 && xx < p.OW) {
-              const float gv = gsn[(size_t)yy * p.OW + xx];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(gv, wg[t * 16 + i], v[i]);
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = wg4[t * 4 + i];
+              v[4 * i] = fmaf(gv[t], w.x, v[4 * i]); v[4 * i + 1] = fmaf(gv[t], w.y, v[4 * i + 1]);
+              v[4 * i + 2] = fmaf(gv[t], w.z, v[4 * i + 2]); v[4 * i + 3] = fmaf(gv[t], w.w, v[4 * i + 3]);
             }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
           float hbuf[16];
 #pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            float sacc = b2[o];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) sacc = fmaf(v[c], w2[c * 16 + o], sacc);
-            hbuf[o] = leaky(sacc);
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = b24[i];
+            hbuf[4 * i] = b.x; hbuf[4 * i + 1] = b.y; hbuf[4 * i + 2] = b.z; hbuf[4 * i + 3] = b.w;
           }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = w24[c * 4 + i];
+              hbuf[4 * i] = fmaf(v[c], w.x, hbuf[4 * i]); hbuf[4 * i + 1] = fmaf(v[c], w.y, hbuf[4 * i + 1]);
+              hbuf[4 * i + 2] = fmaf(v[c], w.z, hbuf[4 * i + 2]); hbuf[4 * i + 3] = fmaf(v[c], w.w, hbuf[4 * i + 3]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hbuf[i] = leaky(hbuf[i]);
           float rgb[3];
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             float sacc = b3[o];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) sacc = fmaf(hbuf[c], w3[c * 3 + o], sacc);
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = w3t4[o * 4 + i];
+              sacc = fmaf(hbuf[4 * i], w.x, sacc); sacc = fmaf(hbuf[4 * i + 1], w.y, sacc);
+              sacc = fmaf(hbuf[4 * i + 2], w.z, sacc); sacc = fmaf(hbuf[4 * i + 3], w.w, sacc);
+            }
             rgb[o] = sacc;
           }
-          const size_t pidx = ((size_t)n * p.OH + gy) * p.OW + xg;
           if (x.rgb_out) {
             x.rgb_out[3 * pidx] = rgb[0];
             x.rgb_out[3 * pidx + 1] = rgb[1];
@@ -459,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           if (x.dif_out) {
             const float g1 = rgb[0] * kGrayR + rgb[1] * kGrayG + rgb[2] * kGrayB;
-            const float g0 = x.img[3 * pidx] * kGrayR + x.img[3 * pidx + 1] * kGrayG + x.img[3 * pidx + 2] * kGrayB;
+            const float g0 = i0 * kGrayR + i1 * kGrayG + i2 * kGrayB;
             x.dif_out[pidx] = g1 - g0;
           }
         }
@@ -500,6 +596,13 @@ inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>
   if (cudaMalloc(&t.steps_dev, sizeof t.steps) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   if (cudaMemcpy(t.steps_dev, t.steps, sizeof t.steps, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
   t.b_total_rows = (int)rows;
+  if (!t.b_resident && t.kind != TC_ROWPACK && t.kind != TC_HEADS && t.kind != TC_CLR && rows * K * 2 <= 150 * 1024 &&
+      !getenv("BSR_NO_RESIDENT")) {
+    // small weight matrices MAY stay resident in shared memory ([kblock][row] layout, no per-step weight TMA);
+    // decided per launch: it only pays when a CTA processes many tiles
+    t.can_reside = 1;
+    t.b_res_kblocks = (int)(K / TC_BK);
+  }
   t.ready = true;
   return true;
 }
@@ -747,7 +850,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.steps = t.steps_dev;
   if (t.kind == TC_CONV && !t.transposed) { p.pad_t = pad_t; p.pad_l = pad_l; }
   p.rows_per_tile = t.rows_per_tile; p.halves = t.halves;
-  p.b_resident = t.b_resident; p.b_total_rows = t.b_total_rows;
+  p.b_total_rows = t.b_total_rows;
   p.bw = t.tile_w ? t.tile_w : (GW < TC_BM ? GW : TC_BM);
   p.bh = TC_BM / p.bw;
   p.epi_mode = t.kind == TC_HEADS ? EPI_HEADS : (t.kind == TC_CLR ? EPI_CLR : EPI_GENERIC);
@@ -771,14 +874,18 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     p.n_groups = 1; p.group_cols = t.bn;
     p.group_phase[0] = phase < 0 ? 0 : phase;
   }
-  const int epi_bytes = p.epi_mode == EPI_HEADS ? 262 * 16 * 4 : (p.epi_mode == EPI_CLR ? 2048 + 258 * 48 * 4 : 0);
-  const int fixed_bytes = 1024 + (t.b_resident ? t.b_total_rows * 128 : 0) + 192 + (int)(TC_MAX_STEPS * sizeof(TcStep)) + epi_bytes + 64;
-  p.stage_bytes = TC_BM * 128 + t.b_stage_rows * 128;
+  p.total_tiles = n * p.tiles_x * p.tiles_y * t.n_tiles;
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const bool resident = t.b_resident || (t.can_reside && p.total_tiles >= 6 * grid);
+  p.b_resident = resident ? 1 : 0;
+  const int epi_bytes = 2048 + (p.epi_mode == EPI_HEADS ? 262 * 16 * 4 : (p.epi_mode == EPI_CLR ? 2048 + 258 * 48 * 4 : 0));
+  p.b_res_kblocks = t.b_res_kblocks;
+  const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * t.b_total_rows * 128 : 0) + 192 + (int)(TC_MAX_STEPS * sizeof(TcStep)) + epi_bytes + 64;
+  p.stage_bytes = TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128);
   p.n_stages = (TC_SMEM_BUDGET + 20 * 1024 - fixed_bytes) / p.stage_bytes;
   if (p.n_stages > 8) p.n_stages = 8;
   if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }
   p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
-  p.total_tiles = n * p.tiles_x * p.tiles_y * t.n_tiles;
   p.errflag = errflag;
   if ((in_ld % 8) || (in_coff % 8)) { tma.last_error = "input channel stride/offset must be multiples of 8"; return -2; }
   TmapKey key{in, in_ld, in_coff, t.cin, H, W, n, p.in_stride, p.bw, p.bh, t.kind};
@@ -800,8 +907,19 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     it = cache.emplace(key, m).first;
   }
   const size_t smem = (size_t)fixed_bytes + (size_t)p.n_stages * p.stage_bytes;
-  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(it->second, t.map, p, e, x);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, it->second, t.map, p, e, x);
+  if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }
   (*launches)++;
   return 0;
 }
