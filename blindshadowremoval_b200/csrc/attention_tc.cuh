@@ -9,7 +9,8 @@
 // logits of this network make an exact (not running) max the safest choice as well.
 // Layouts: QK[n][1024][256] = theta | phi (bf16);  VT[n][128][1024] = g transposed (so every UMMA
 // operand is K-major);  O[n][1024][128].
-// Warp roles (192 threads): warp 0 TMA, warp 1 TMEM alloc + MMA issue, warps 2-5 softmax / epilogue.
+// Warp roles (192 threads): warps 0-3 softmax / epilogue, warp 4 TMA, warp 5 TMEM alloc + MMA issue (the
+// single-thread roles get the highest warp ids: the warp arbiter favours high ids).
 #pragma once
 #include <map>
 #include <tuple>
@@ -58,14 +59,14 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
     mbar_init(b_ofull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS0 = tmem, tO = tmem + 256;
 
-  if (warp == 0) {
+  if (warp == 4) {
     if (lane == 0) {
       mbar_expect_tx(b_q, AT_TILE);
       tma_load_3d(sQ, &tmQK, b_q, 0, q0, n);
@@ -88,14 +89,14 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 128);
-      bool ok = mbar_wait(b_q, 0, errflag, 13);
+      bool ok = mbar_wait(b_q, 0, errflag, 13, true);
       auto issue_pv = [&](int j) -> bool {
         const int vs = j & 1, vf = j >> 1;
-        if (!mbar_wait(b_pfull, (uint32_t)(j & 1), errflag, 14)) return false;
-        if (!mbar_wait(b_vfull + 8 * vs, (uint32_t)(vf & 1), errflag, 15)) return false;
+        if (!mbar_wait(b_pfull, (uint32_t)(j & 1), errflag, 14, true)) return false;
+        if (!mbar_wait(b_vfull + 8 * vs, (uint32_t)(vf & 1), errflag, 15, true)) return false;
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
@@ -111,9 +112,9 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
       };
       for (int it = 0; it < 2 * AT_NK && ok; ++it) {
         const int s = it & 1, f = it >> 1;
-        ok = mbar_wait(b_kfull + 8 * s, (uint32_t)(f & 1), errflag, 16);
+        ok = mbar_wait(b_kfull + 8 * s, (uint32_t)(f & 1), errflag, 16, true);
         if (!ok) break;
-        ok = mbar_wait(b_sempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 17);
+        ok = mbar_wait(b_sempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 17, true);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 512);

@@ -629,7 +629,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
       {(char**)&h->DIFSMALL, mb * 1024 * 4},
       {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 2 * 291 * 4 : 256},
-      {(char**)&h->errflag, 256}};
+      {(char**)&h->errflag, 16384}};
   size_t total = 0;
   for (auto& r : reqs) total += align256(r.bytes);
   if (cudaMalloc(&h->arena, total) != cudaSuccess) {
@@ -840,6 +840,16 @@ int bsr_debug_read(bsr_handle* h, const char* name, float* host_out, size_t capa
     CK(h, cudaMemcpy(&flag, h->errflag, sizeof(int), cudaMemcpyDeviceToHost));
     if (n_elems) *n_elems = 1;
     if (host_out && capacity >= 1) host_out[0] = (float)flag;
+    return BSR_OK;
+  }
+  if (!strcmp(name, "timers")) {       // BSR_ABLATE=8: 64 launches x 16 cycle counters (see conv_tc.cuh)
+    if (n_elems) *n_elems = 1024;
+    if (!host_out) return BSR_OK;
+    if (capacity < 1024) return fail(h, BSR_EINVAL, "capacity too small");
+    std::vector<long long> t(1024);
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(t.data(), (char*)h->errflag + 128, 1024 * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 1024; ++i) host_out[i] = (float)t[i];
     return BSR_OK;
   }
   auto it = h->dbg.find(name);

@@ -23,8 +23,9 @@
 //     operands; UMMA M = 128, K = 16 per instruction.
 // Persistent CTAs (one per SM) loop over tiles; accumulators are double-buffered in TMEM whenever
 // 2 x columns <= 512, so the epilogue of tile t overlaps the TMA/MMA main loop of tile t+1.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-9 = epilogue (TMEM -> registers -> bias / residual adds / LeakyReLU -> global).
+// Warp roles (576 threads): warps 0-15 = epilogue (TMEM -> registers -> bias / residual adds / LeakyReLU ->
+// global), warp 16 = TMA producer, warp 17 = TMEM allocator + MMA issuer.  The two single-thread roles get the
+// HIGHEST warp ids on purpose: the warp arbiter favours high ids, and a starved MMA issuer stalls everything.
 #pragma once
 #include <map>
 #include <string>
@@ -38,8 +39,8 @@ namespace bsr {
 
 constexpr int TC_BM = 128;          // pixels per A tile (UMMA M)
 constexpr int TC_BK = 64;           // K elements per step (128 B of bf16 = one swizzle row)
-constexpr int TC_THREADS = 320;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 576;
+constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MAX_STEPS = 64;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
@@ -123,6 +124,8 @@ struct ConvTcParams {
   int pad_t, pad_l;           // SAME padding subtracted from the step shifts (plain convs)
   int b_resident, b_total_rows;
   int b_res_kblocks;          // resident weights: number of 64-element K blocks kept ([kblock][row] layout)
+  int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
+  long long* timers;          // [16] per launch (CTA 0): role wait / total cycle counters when ablate & 8
   int* errflag;
   const TcStep* steps;        // device copy of the step program
 };
@@ -147,7 +150,9 @@ __device__ __forceinline__ void add_res16(const void* base, size_t pix, int ld, 
   }
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barriers of the epilogue warps: 1 = all 512 epilogue threads, 2 + slot = the 256 threads of one row slot
+__device__ __forceinline__ void epi_bar_all() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_slot(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(2 + slot) : "memory"); }
 // Programmatic dependent launch: everything before pdl_wait() (barrier init, TMEM alloc, weight / bias staging)
 // overlaps the tail of the previous kernel in the stream; nothing produced by that kernel is touched before it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -163,6 +168,7 @@ __device__ __forceinline__ void add_bf16x16(const uint4& a, const uint4& b, floa
   }
 }
 
+template <int EPI, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ ConvTcParams p,
@@ -172,7 +178,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t a_bytes = TC_BM * 128;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
   const uint32_t sBres = smem_base + (uint32_t)p.n_stages * stage_bytes;            // resident weights (optional)
-  // NOTE: for multi-row kinds b_k is 0 and b_row 0, so the resident address reduces to sBres + mma.brow rows.
   const uint32_t bars = sBres + (p.b_resident ? (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u : 0u);
   // full[8], empty[8], tmem_full[2], tmem_empty[2], bres, tmem slot
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_tfull = bars + 128, bar_tempty = bars + 144;
@@ -189,8 +194,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int n_tiles = p.n_tiles, total_tiles = p.total_tiles, n_steps = p.n_steps;
+  const uint32_t n_stages = (uint32_t)p.n_stages, acc_stages = (uint32_t)p.acc_stages;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(p.bn * p.acc_stages)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)p.bn * acc_stages) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -206,119 +213,171 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     mbar_init(bar_bres, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+  if (warp == TC_EPI_WARPS) {
+    // ================= TMA producer (whole warp converged; one elected lane issues) =================
+    {
       uint32_t it = 0;
       bool ok = true;
-      if (p.b_resident) {          // weights are static: fetched before the dependency wait
+      const bool leader = elect_one();
+      const int in_stride = p.in_stride, pad_l = p.pad_l, pad_t = p.pad_t, b_resident = p.b_resident;
+      const int b_box_rows = p.b_box_rows, bn = p.bn, ablate = p.ablate;
+      const int tiles_x = p.tiles_x, tile_h = p.bh * p.rows_per_tile, tile_w = p.bw * p.halves;
+      if (b_resident && leader) {          // weights are static: fetched before the dependency wait
         mbar_expect_tx(bar_bres, (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u);
         for (int kb = 0; kb < p.b_res_kblocks; ++kb)
-          for (int r = 0; r < p.b_total_rows; r += p.b_box_rows)
+          for (int r = 0; r < p.b_total_rows; r += b_box_rows)
             tma_load_2d(sBres + (uint32_t)(kb * p.b_total_rows + r) * 128u, &tmB, bar_bres, kb * TC_BK, r);
       }
+      const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
+      long long t_wait = 0, t_dep = 0, t_tma = 0;
+      const long long t_start = clock64();
       pdl_wait();
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-        const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
+      t_dep = clock64() - t_start;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int ntile = tile % n_tiles, mt = tile / n_tiles;
         const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
-        const int gy0 = (tr / p.tiles_x) * p.bh * p.rows_per_tile, gx0 = (tr % p.tiles_x) * p.bw * p.halves;
-        for (int si = 0; si < p.n_steps; ++si, ++it) {
+        const int gy0 = (tr / tiles_x) * tile_h, gx0 = (tr % tiles_x) * tile_w;
+        const int xbase = gx0 * in_stride - pad_l, ybase = gy0 * in_stride - pad_t, brow_base = ntile * bn;
+        for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
-          const uint32_t s = it % (uint32_t)p.n_stages, ph = (it / (uint32_t)p.n_stages) & 1u;
+          const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+          const long long tw = clock64();
           ok = mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.errflag, 1);
+          const long long tp0 = clock64();
+          t_wait += tp0 - tw;
           if (!ok) break;
           const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_bytes;
-          mbar_expect_tx(bar_full + 8 * s, a_bytes + (p.b_resident ? 0u : (uint32_t)sp.b_rows * 128u));
-          tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, (gx0 + sp.a_x0) * p.in_stride + sp.dx - p.pad_l,
-                      gy0 * p.in_stride + sp.dy - p.pad_t, n);
-          if (!p.b_resident) {
-            const int row0 = sp.b_row + ntile * p.bn;
-            for (int r = 0; r < sp.b_rows; r += p.b_box_rows)
-              tma_load_2d(dstB + (uint32_t)r * 128u, &tmB, bar_full + 8 * s, sp.b_k, row0 + r);
+          if (leader) {
+            if (ablate & 4) {
+              mbar_expect_tx(bar_full + 8 * s, b_resident ? 0u : (uint32_t)sp.b_rows * 128u);
+            } else {
+              mbar_expect_tx(bar_full + 8 * s, a_bytes + (b_resident ? 0u : (uint32_t)sp.b_rows * 128u));
+              tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, xbase + sp.a_x0 * in_stride + sp.dx, ybase + sp.dy, n);
+            }
+            if (!b_resident) {
+              const int row0 = sp.b_row + brow_base;
+              for (int r = 0; r < sp.b_rows; r += b_box_rows)
+                tma_load_2d(dstB + (uint32_t)r * 128u, &tmB, bar_full + 8 * s, sp.b_k, row0 + r);
+            }
           }
+          __syncwarp();
+          t_tma += clock64() - tp0;
         }
       }
+      if (tm) { p.timers[15] = t_tma; p.timers[0] = clock64() - t_start; p.timers[1] = t_wait; p.timers[2] = t_dep; p.timers[3] = it; }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ================= MMA issuer (whole warp converged; one elected lane issues) =================
+    {
       uint32_t it = 0, tcount = 0;
       bool ok = true;
-      if (p.b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
-        const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
-        ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4);
+      const bool leader = elect_one();
+      const int b_resident = p.b_resident, b_total_rows = p.b_total_rows, bn = p.bn, ablate = p.ablate;
+      const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
+      long long t_wfull = 0, t_wtempty = 0, t_fence = 0, t_issue = 0, t_commit = 0;
+      const long long t_start = clock64();
+      if (b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
+      const long long t_res = clock64() - t_start;
+      const uint32_t idesc_m = umma_idesc_bf16(TC_BM, 0);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
+        const long long tw0 = clock64();
+        ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4, true);
+        t_wtempty += clock64() - tw0;
         if (!ok) break;
         tc_fence_after();
-        const uint32_t acc = tmem_base + as * (uint32_t)p.bn;
-        for (int si = 0; si < p.n_steps; ++si, ++it) {
+        const uint32_t acc = tmem_base + as * (uint32_t)bn;
+        const int brow_base = (tile % n_tiles) * bn;
+        for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
-          const uint32_t s = it % (uint32_t)p.n_stages, ph = (it / (uint32_t)p.n_stages) & 1u;
-          ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2);
+          const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+          const long long tw1 = clock64();
+          ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2, true);
+          const long long tc0 = clock64();
+          t_wfull += tc0 - tw1;
           if (!ok) break;
           tc_fence_after();
+          const long long tc1 = clock64();
+          t_fence += tc1 - tc0;
           const uint32_t sA = smem_base + s * stage_bytes;
-          const uint32_t sB = p.b_resident
-                                  ? sBres + (uint32_t)((sp.b_k >> 6) * p.b_total_rows + sp.b_row + (tile % p.n_tiles) * p.bn) * 128u
-                                  : sA + a_bytes;
-          const uint64_t da = umma_desc_sw128(sA);
-          for (int m = 0; m < sp.n_mma; ++m) {
-            const TcMma mm = sp.mma[m];
-            const uint64_t db = umma_desc_sw128(sB + (uint32_t)mm.brow * 128u);
-            const uint32_t idesc = umma_idesc_bf16(TC_BM, mm.n);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k)
-              umma_bf16(acc + (uint32_t)mm.col, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                        (mm.first && k == 0) ? 0u : 1u);
+          const uint32_t sB = b_resident ? sBres + (uint32_t)((sp.b_k >> 6) * b_total_rows + sp.b_row + brow_base) * 128u
+                                         : sA + a_bytes;
+          const uint32_t a_lo = umma_desc_lo(sA), b_lo0 = umma_desc_lo(sB);
+          const int nm = (ablate & 2) ? 0 : sp.n_mma;
+          if (leader) {
+            for (int m = 0; m < nm; ++m) {
+              const TcMma mm = sp.mma[m];
+              const uint32_t b_lo = b_lo0 + (uint32_t)mm.brow * 8u;          // 128-byte rows, address >> 4
+              const uint32_t idesc = idesc_m | ((uint32_t)(mm.n >> 3) << 17);
+              const uint32_t d = acc + (uint32_t)mm.col;
+              umma_bf16_lo(d, a_lo, b_lo, idesc, mm.first ? 0u : 1u);
+              umma_bf16_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
+              umma_bf16_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
+              umma_bf16_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
+            }
           }
-          umma_commit(bar_empty + 8 * s);
+          const long long tc2 = clock64();
+          t_issue += tc2 - tc1;
+          if (leader) umma_commit(bar_empty + 8 * s);
+          __syncwarp();
+          t_commit += clock64() - tc2;
         }
-        umma_commit(bar_tfull + 8 * as);
+        if (leader) umma_commit(bar_tfull + 8 * as);
+        __syncwarp();
       }
+      if (tm) { p.timers[12] = t_fence; p.timers[13] = t_issue; p.timers[14] = t_commit; }
+      if (tm) { p.timers[4] = clock64() - t_start; p.timers[5] = t_wfull; p.timers[6] = t_wtempty; p.timers[7] = t_res; p.timers[8] = tcount; }
     }
   } else {
-    // ================= epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., column chunks of parity w/4
-    const int ew = warp - 2;
-    const int q = warp & 3, half = ew >> 2;
+    // ================= epilogue: 16 warps.  warp ew reads TMEM lanes 32*(warp%4).. (hardware rule) =================
+    const int ew = warp;
+    const int q = warp & 3;                       // TMEM lane quarter = rows 32q .. 32q+31 of the A tile
+    const int cg = ew >> 2;                       // 0..3: column-chunk group (GENERIC) / row slot + half (HEADS, CLR)
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int ethread = threadIdx.x;
     uint32_t tcount = 0;
     bool ok = true;
     // static data first (bias, colour-tail weights): not produced by the previous kernel
     float* bias_s = epi_smem;                   // [512] (the device bias buffer is zero-padded past cout)
     float* epi_work = epi_smem + 512;
-    for (int i = threadIdx.x - 64; i < 512; i += 256) bias_s[i] = __ldg(e.bias + i);
-    if (p.epi_mode == EPI_CLR)
-      for (int i = threadIdx.x - 64; i < 144 + 256 + 16 + 48 + 3; i += 256) epi_work[i] = x.aux[i];
-    epi_bar_sync();
+    for (int i = ethread; i < 512; i += TC_EPI_WARPS * 32) bias_s[i] = __ldg(e.bias + i);
+    if (EPI == EPI_CLR)
+      for (int i = ethread; i < 144 + 256 + 16 + 48 + 3; i += TC_EPI_WARPS * 32) epi_work[i] = x.aux[i];
+    epi_bar_all();
     pdl_wait();
-    const bool has_res = e.res1 != nullptr || e.res2 != nullptr;
-    for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x, ++tcount) {
-      const int ntile = tile % p.n_tiles, mt = tile / p.n_tiles;
+    const int OH = p.OH, OW = p.OW, bn = p.bn, rows_per_tile = p.rows_per_tile;
+    const bool tm = (p.ablate & 8) && blockIdx.x == 0 && ethread == 0;
+    long long t_wtfull = 0;
+    const long long t_start = clock64();
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
+      const int ntile = tile % n_tiles, mt = tile / n_tiles;
       const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
-      const uint32_t as = tcount % (uint32_t)p.acc_stages, aph = (tcount / (uint32_t)p.acc_stages) & 1u;
-      const uint32_t acc = tmem_base + as * (uint32_t)p.bn + lane_addr;
-      if (p.epi_mode == EPI_GENERIC) {
-        const int gyb = (tr / p.tiles_x) * p.bh * p.rows_per_tile + r / p.bw, gx = (tr % p.tiles_x) * p.bw + r % p.bw;
+      const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
+      const uint32_t acc = tmem_base + as * (uint32_t)bn + lane_addr;
+      if (EPI == EPI_GENERIC) {
+        const int bw = p.bw, bh = p.bh, out_scale = p.out_scale, group_cols = p.group_cols;
+        const int gyb = (tr / p.tiles_x) * bh * rows_per_tile + r / bw, gx = (tr % p.tiles_x) * bw + r % bw;
         const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
-        const int cbase = p.n_groups == 1 ? ntile * p.bn : 0;
-        // residual / skip operands of this thread's first 5 chunks are fetched BEFORE the accumulator wait, so their
+        const int cbase = p.n_groups == 1 ? ntile * bn : 0;
+        const int total_cols = p.n_groups * group_cols;
+        // residual / skip operands of this thread's first 3 chunks are fetched BEFORE the accumulator wait, so their
         // global-load latency hides behind the MMA main loop (plain convs only: one pixel per thread)
-        uint4 rb1[5][2], rb2[5][2];
+        uint4 rb1[3][2], rb2[3][2];
         uint32_t m1 = 0, m2 = 0;
-        if (has_res && p.n_groups == 1) {
-          const size_t pix0 = ((size_t)n * p.OH + gyb) * p.OW + gx;
+        if (RES) {
+          const size_t pix0 = ((size_t)n * OH + gyb) * OW + gx;
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            const int col = (2 * k + half) * 16, c = cbase + col;
-            if (col < p.bn && c + 16 <= e.out_c) {
+          for (int k = 0; k < 3; ++k) {
+            const int col = (4 * k + cg) * 16, c = cbase + col;
+            if (col < bn && c + 16 <= e.out_c) {
               if (e.res1 != nullptr && c + 16 <= e.res1_c) {
                 const uint4* src = reinterpret_cast<const uint4*>((const bf16*)e.res1 + pix0 * e.res1_ld + c);
                 rb1[k][0] = src[0]; rb1[k][1] = src[1]; m1 |= 1u << k;
@@ -330,97 +389,120 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
         }
+        const long long tw2 = clock64();
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        t_wtfull += clock64() - tw2;
         if (!ok) break;
         tc_fence_after();
-        const int total_cols = p.n_groups * p.group_cols;
+        // running (group, column-in-group) of this warp's chunk; chunks advance by 4 x 16 columns
+        int g = 0, j = cg * 16;
+        while (j >= group_cols) { j -= group_cols; ++g; }
+        int g_cur = -1;
+        size_t pix = 0;
+        int gy = 0;
         auto chunk = [&](const int col, const bool pf1, const uint4& r1a, const uint4& r1b, const bool pf2,
                          const uint4& r2a, const uint4& r2b) {
-          const int g = col / p.group_cols, j = col - g * p.group_cols;
-          const int c = cbase + j;
-          if (c >= e.out_c) return;
-          const int phase = p.rows_per_tile > 1 ? 0 : p.group_phase[g];
-          const int gy = gyb + (p.rows_per_tile > 1 ? g * p.bh : 0);
-          const int oy = gy * p.out_scale + (phase >> 1), ox = gx * p.out_scale + (phase & 1);
-          const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-          float v[16];
-          tmem_ld16(acc + (uint32_t)col, v);
-          if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
-            if (pf1) add_bf16x16(r1a, r1b, v);
-            else if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
-            if (pf2) add_bf16x16(r2a, r2b, v);
-            else if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
-            if (e.act) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-            }
-            if (e.out_mode == OUT_F32) {
-              float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) dst[i] = v[i];
-            } else if (e.out_mode == OUT_QKV && c >= 256) {
-              // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
-              bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * p.OW + gx);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
-            } else {
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-              o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-              o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-              o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-              const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
-              uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
-              dst[0] = o0;
-              dst[1] = o1;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
+          if (g != g_cur) {          // per-group output pixel (sub-pixel phase or row), computed once per group
+            g_cur = g;
+            const int phase = rows_per_tile > 1 ? 0 : p.group_phase[g];
+            gy = gyb + (rows_per_tile > 1 ? g * bh : 0);
+            const int oy = gy * out_scale + (phase >> 1), ox = gx * out_scale + (phase & 1);
+            pix = ((size_t)n * OH + oy) * OW + ox;
           }
-        };
+          const int c = cbase + j;
+          if (c < e.out_c) {
+            float v[16];
+            tmem_ld16(acc + (uint32_t)col, v);
+            if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int col = (2 * k + half) * 16;
-          if (col < total_cols) chunk(col, (m1 >> k) & 1u, rb1[k][0], rb1[k][1], (m2 >> k) & 1u, rb2[k][0], rb2[k][1]);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+              if (RES) {
+                if (pf1) add_bf16x16(r1a, r1b, v);
+                else if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
+                if (pf2) add_bf16x16(r2a, r2b, v);
+                else if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
+              }
+              if (e.act) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);      // leaky, alpha < 1
+              }
+              if (e.out_mode == OUT_F32) {
+                float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[i] = v[i];
+              } else if (e.out_mode == OUT_QKV && c >= 256) {
+                // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
+                bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * OW + gx);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
+              } else {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+                o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+                o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
+                uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
+                if (!(p.ablate & 1)) {
+                  dst[0] = o0;
+                  dst[1] = o1;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
+            }
+          }
+          j += 64;
+          while (j >= group_cols) { j -= group_cols; ++g; }
+        };
+        int col = cg * 16;
+        if (RES) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (col < total_cols) chunk(col, (m1 >> k) & 1u, rb1[k][0], rb1[k][1], (m2 >> k) & 1u, rb2[k][0], rb2[k][1]);
+            col += 64;
+          }
         }
 #pragma unroll 1
-        for (int col = (10 + half) * 16; col < total_cols; col += 32) chunk(col, false, rb1[0][0], rb1[0][1], false, rb2[0][0], rb2[0][1]);
+        for (; col < total_cols; col += 64) chunk(col, false, rb1[0][0], rb1[0][1], false, rb2[0][0], rb2[0][1]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-      } else if (p.epi_mode == EPI_HEADS) {
+      } else if (EPI == EPI_HEADS) {
         // tile = R image rows of 256 pixels; accumulator group (half, row rr) = 16 columns [kw*2 + o] holding the
         // vertical 7x1 partial sums Y[x][kw][o];  out[x][o] = sum_kw Y[x+kw-3][kw][o] (zero outside the row)
         // + bias (model.py:246-247), then the grey composition (model.py:250-252).
-        const int y0 = tr * p.rows_per_tile;
+        // 16 warps = 2 row slots x 2 halves x 4 lane quarters: two image rows are finished concurrently.
+        const int half = cg & 1, slot = cg >> 1;
+        const int y0 = tr * rows_per_tile;
         const int xg = half * 128 + r;
-        float* rowbuf = epi_work;                                   // [256 + 6][16], 3 zero columns either side
-        if (threadIdx.x - 64 < 96) {
-          const int i = threadIdx.x - 64;                           // zero the two halos (3 x 16 each)
+        float* rowbuf = epi_work + slot * (262 * 16);               // [256 + 6][16], 3 zero columns either side
+        const int st = ethread - slot * 256 - (ethread >= 256 && slot == 0 ? 0 : 0);
+        if ((ethread & 255) < 96) {
+          const int i = ethread & 255;                              // zero the two halos (3 x 16 each) of my slot's buffer
           rowbuf[(i < 48 ? 0 : 256 * 16) + i] = 0.f;
         }
+        (void)st;
         const float b2 = bias_s[0], b3 = bias_s[1];
-        const size_t p0 = ((size_t)n * p.OH + y0) * p.OW + xg;
+        const size_t p0 = ((size_t)n * OH + y0 + slot) * OW + xg;
         float i0 = x.img[3 * p0], i1 = x.img[3 * p0 + 1], i2 = x.img[3 * p0 + 2];     // prefetched one row ahead
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
         if (!ok) break;
         tc_fence_after();
-        for (int rr = 0; rr < p.rows_per_tile; ++rr) {
-          const size_t pidx = p0 + (size_t)rr * p.OW;
+        for (int rr = slot; rr < rows_per_tile; rr += 2) {
+          const size_t pidx = p0 + (size_t)(rr - slot) * OW;
           const float g = i0 * kGrayR + i1 * kGrayG + i2 * kGrayB;
-          if (rr + 1 < p.rows_per_tile) {
-            const size_t pn = pidx + p.OW;
+          if (rr + 2 < rows_per_tile) {
+            const size_t pn = pidx + 2 * (size_t)OW;
             i0 = x.img[3 * pn]; i1 = x.img[3 * pn + 1]; i2 = x.img[3 * pn + 2];
           }
           float v[16];
-          tmem_ld16(acc + (uint32_t)((half * p.rows_per_tile + rr) * 16), v);
-          if (rr == p.rows_per_tile - 1) {
+          tmem_ld16(acc + (uint32_t)((half * rows_per_tile + rr) * 16), v);
+          if (rr + 2 >= rows_per_tile) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);        // accumulators drained: MMA may start the next tile
@@ -428,7 +510,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             *reinterpret_cast<float4*>(rowbuf + (xg + 3) * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          epi_bar_sync();
+          epi_bar_slot(slot);
           float c2 = b2, c3 = b3;
 #pragma unroll
           for (int kw = 0; kw < 7; ++kw) {
@@ -436,7 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             c2 += t.x;
             c3 += t.y;
           }
-          epi_bar_sync();                                           // row buffer free for the next row
+          epi_bar_slot(slot);                                       // row buffer free for the next row
           const float mask = tanhf(c2);
           const float gs = g * (1.f + mask) + c3;
           x.difgs[pidx] = gs - g;
@@ -452,119 +534,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // EPI_CLR: clr_conv1 over f (tensor cores, "kw expansion": group (half, row rr) = 48 columns [kw*16 + o] of
         // vertical 3x1 partial sums) + the gs channel of the concat (model.py:267) as a 3x3 fp32 conv on CUDA
         // cores, then clr_conv2 / clr_conv3 and the final dif (model.py:268-269, 288).
-        const int y0 = tr * p.rows_per_tile;
+        // 16 warps = 2 row slots x 2 halves x 4 lane quarters (rows_per_tile = 2: one row per slot).
+        const int half = cg & 1, slot = cg >> 1;
+        const int y0 = tr * rows_per_tile;
         const int xg = half * 128 + r;
         const float4* wg4 = reinterpret_cast<const float4*>(epi_work);            // [9][16]
         const float4* w24 = reinterpret_cast<const float4*>(epi_work + 144);      // [16 in][16 out]
         const float4* b24 = reinterpret_cast<const float4*>(epi_work + 400);
         const float4* w3t4 = reinterpret_cast<const float4*>(epi_work + 416);     // [3 out][16 in]
         const float* b3 = epi_work + 464;
-        float* rowbuf = epi_work + 512;             // [256 + 2][48], one zero column either side
-        if (threadIdx.x - 64 < 96) {
-          const int i = threadIdx.x - 64;
+        float* rowbuf = epi_work + 512 + slot * (258 * 48);   // [256 + 2][48], one zero column either side
+        if ((ethread & 255) < 96) {
+          const int i = ethread & 255;
           rowbuf[(i < 48 ? 0 : 256 * 48) + i] = 0.f;
         }
-        const float* gsn = x.gs_f32 + (size_t)n * p.OH * p.OW;
+        const float* gsn = x.gs_f32 + (size_t)n * OH * OW;
+        // issue the 9 gs taps and the input pixel first: their latency overlaps the accumulator wait
+        float gv[9];
+        const int gy = y0 + slot;
+        const size_t pidx = ((size_t)n * OH + gy) * OW + xg;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int yy = gy + t / 3 - 1, xx = xg + t % 3 - 1;
+          gv[t] = (yy >= 0 && yy < OH && xx >= 0 && xx < OW) ? gsn[(size_t)yy * OW + xx] : 0.f;
+        }
+        const float i0 = x.img[3 * pidx], i1 = x.img[3 * pidx + 1], i2 = x.img[3 * pidx + 2];
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
         if (!ok) break;
         tc_fence_after();
-        for (int rr = 0; rr < p.rows_per_tile; ++rr) {
-          const int gy = y0 + rr;
-          const size_t pidx = ((size_t)n * p.OH + gy) * p.OW + xg;
-          // issue the 9 gs taps and the input pixel first: their latency overlaps the TMEM / smem exchange below
-          float gv[9];
+        {
+          float* dst = rowbuf + (xg + 1) * 48;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int yy = gy + t / 3 - 1, xx = xg + t % 3 - 1;
-            gv[t] = (yy >= 0 && yy < p.OH && xx >= 0 && xx < p.OW) ? gsn[(size_t)yy * p.OW + xx] : 0.f;
+          for (int c = 0; c < 48; c += 16) {
+            float v[16];
+            tmem_ld16(acc + (uint32_t)((half * rows_per_tile + slot) * 48 + c), v);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
-          const float i0 = x.img[3 * pidx], i1 = x.img[3 * pidx + 1], i2 = x.img[3 * pidx + 2];
-          {
-            float* dst = rowbuf + (xg + 1) * 48;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        epi_bar_slot(slot);
+        float v[16];
 #pragma unroll
-            for (int c = 0; c < 48; c += 16) {
-              float v[16];
-              tmem_ld16(acc + (uint32_t)((half * p.rows_per_tile + rr) * 48 + c), v);
+        for (int i = 0; i < 16; ++i) v[i] = bias_s[i];
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* src = rowbuf + (xg + kw) * 48 + kw * 16;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(src + i);
+            v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
           }
-          if (rr == p.rows_per_tile - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-          }
-          epi_bar_sync();
-          float v[16];
+        }
+        epi_bar_slot(slot);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = bias_s[i];
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float* src = rowbuf + (xg + kw) * 48 + kw * 16;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(src + i);
-              v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-            }
-          }
-          epi_bar_sync();
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 w = wg4[t * 4 + i];
-              v[4 * i] = fmaf(gv[t], w.x, v[4 * i]); v[4 * i + 1] = fmaf(gv[t], w.y, v[4 * i + 1]);
-              v[4 * i + 2] = fmaf(gv[t], w.z, v[4 * i + 2]); v[4 * i + 3] = fmaf(gv[t], w.w, v[4 * i + 3]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = leaky(v[i]);
-          float hbuf[16];
+        for (int t = 0; t < 9; ++t) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 b = b24[i];
-            hbuf[4 * i] = b.x; hbuf[4 * i + 1] = b.y; hbuf[4 * i + 2] = b.z; hbuf[4 * i + 3] = b.w;
+            const float4 w = wg4[t * 4 + i];
+            v[4 * i] = fmaf(gv[t], w.x, v[4 * i]); v[4 * i + 1] = fmaf(gv[t], w.y, v[4 * i + 1]);
+            v[4 * i + 2] = fmaf(gv[t], w.z, v[4 * i + 2]); v[4 * i + 3] = fmaf(gv[t], w.w, v[4 * i + 3]);
           }
+        }
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
+        float hbuf[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 w = w24[c * 4 + i];
-              hbuf[4 * i] = fmaf(v[c], w.x, hbuf[4 * i]); hbuf[4 * i + 1] = fmaf(v[c], w.y, hbuf[4 * i + 1]);
-              hbuf[4 * i + 2] = fmaf(v[c], w.z, hbuf[4 * i + 2]); hbuf[4 * i + 3] = fmaf(v[c], w.w, hbuf[4 * i + 3]);
-            }
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = b24[i];
+          hbuf[4 * i] = b.x; hbuf[4 * i + 1] = b.y; hbuf[4 * i + 2] = b.z; hbuf[4 * i + 3] = b.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 w = w24[c * 4 + i];
+            hbuf[4 * i] = fmaf(v[c], w.x, hbuf[4 * i]); hbuf[4 * i + 1] = fmaf(v[c], w.y, hbuf[4 * i + 1]);
+            hbuf[4 * i + 2] = fmaf(v[c], w.z, hbuf[4 * i + 2]); hbuf[4 * i + 3] = fmaf(v[c], w.w, hbuf[4 * i + 3]);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) hbuf[i] = leaky(hbuf[i]);
-          float rgb[3];
+        for (int i = 0; i < 16; ++i) hbuf[i] = fmaxf(hbuf[i], kLeaky * hbuf[i]);
+        float rgb[3];
 #pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            float sacc = b3[o];
+        for (int o = 0; o < 3; ++o) {
+          // four independent partial sums keep the FMA chain short
+          float s0 = b3[o], s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 w = w3t4[o * 4 + i];
-              sacc = fmaf(hbuf[4 * i], w.x, sacc); sacc = fmaf(hbuf[4 * i + 1], w.y, sacc);
-              sacc = fmaf(hbuf[4 * i + 2], w.z, sacc); sacc = fmaf(hbuf[4 * i + 3], w.w, sacc);
-            }
-            rgb[o] = sacc;
+          for (int i = 0; i < 4; ++i) {
+            const float4 w = w3t4[o * 4 + i];
+            s0 = fmaf(hbuf[4 * i], w.x, s0); s1 = fmaf(hbuf[4 * i + 1], w.y, s1);
+            s2 = fmaf(hbuf[4 * i + 2], w.z, s2); s3 = fmaf(hbuf[4 * i + 3], w.w, s3);
           }
-          if (x.rgb_out) {
-            x.rgb_out[3 * pidx] = rgb[0];
-            x.rgb_out[3 * pidx + 1] = rgb[1];
-            x.rgb_out[3 * pidx + 2] = rgb[2];
-          }
-          if (x.dif_out) {
-            const float g1 = rgb[0] * kGrayR + rgb[1] * kGrayG + rgb[2] * kGrayB;
-            const float g0 = i0 * kGrayR + i1 * kGrayG + i2 * kGrayB;
-            x.dif_out[pidx] = g1 - g0;
-          }
+          rgb[o] = (s0 + s1) + (s2 + s3);
+        }
+        if (x.rgb_out) {
+          x.rgb_out[3 * pidx] = rgb[0];
+          x.rgb_out[3 * pidx + 1] = rgb[1];
+          x.rgb_out[3 * pidx + 2] = rgb[2];
+        }
+        if (x.dif_out) {
+          const float g1 = rgb[0] * kGrayR + rgb[1] * kGrayG + rgb[2] * kGrayB;
+          const float g0 = i0 * kGrayR + i1 * kGrayG + i2 * kGrayB;
+          x.dif_out[pidx] = g1 - g0;
         }
       }
     }
+    if (tm) { p.timers[9] = clock64() - t_start; p.timers[10] = t_wtfull; p.timers[11] = tcount; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_EPI_WARPS + 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -574,7 +656,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------
 // host side
 inline int configure_tc_kernels_conv() {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<EPI_GENERIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_HEADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_CLR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -878,8 +963,10 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const bool resident = t.b_resident || (t.can_reside && p.total_tiles >= 6 * grid);
   p.b_resident = resident ? 1 : 0;
-  const int epi_bytes = 2048 + (p.epi_mode == EPI_HEADS ? 262 * 16 * 4 : (p.epi_mode == EPI_CLR ? 2048 + 258 * 48 * 4 : 0));
+  const int epi_bytes = 2048 + (p.epi_mode == EPI_HEADS ? 2 * 262 * 16 * 4 : (p.epi_mode == EPI_CLR ? 2048 + 2 * 258 * 48 * 4 : 0));
   p.b_res_kblocks = t.b_res_kblocks;
+  { const char* ab = getenv("BSR_ABLATE"); p.ablate = ab ? atoi(ab) : 0; }
+  p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
   const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * t.b_total_rows * 128 : 0) + 192 + (int)(TC_MAX_STEPS * sizeof(TcStep)) + epi_bytes + 64;
   p.stage_bytes = TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128);
   p.n_stages = (TC_SMEM_BUDGET + 20 * 1024 - fixed_bytes) / p.stage_bytes;
@@ -918,7 +1005,11 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, it->second, t.map, p, e, x);
+  cudaError_t le;
+  if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x);
+  else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x);
+  else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x);
+  else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }
   (*launches)++;
   return 0;

@@ -88,17 +88,32 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware (it does not burn issue slots
+// of its scheduler) and is woken by the completing arrive or after `ns` nanoseconds.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Wait with a watchdog: a protocol bug shows up as an error flag instead of a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* errflag, int code) {
+// `hot` = latency-critical single-thread roles (MMA issuer); everyone else sleeps in hardware between probes.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* errflag, int code, bool hot = false) {
   if (mbar_try_wait(bar, parity)) return true;
   const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 2000000000ull) {
+  uint32_t spins = 0;
+  while (true) {
+    if (hot ? mbar_try_wait(bar, parity) : mbar_try_wait_sleep(bar, parity, 20000u)) return true;
+    if ((++spins & 63u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
       if (errflag) atomicExch(errflag, code);
       return false;
     }
   }
-  return true;
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -122,6 +137,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// One lane of a fully converged warp (the compiler keeps warp-uniform operands in uniform registers for the
+// elected lane's tcgen05 / TMA instructions instead of emitting per-instruction waterfall loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- tcgen05
@@ -166,6 +193,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                        // descriptor version
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
+}
+
+// Descriptor built from its two 32-bit halves: lo = (addr >> 4) | LBO field, hi = SBO | version | swizzle (constant).
+constexpr uint32_t kUmmaDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
+      : "memory");
 }
 
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (lane = row).

@@ -1,0 +1,32 @@
+"""Per-launch role timers (BSR_ABLATE=8): where does a persistent conv CTA spend its cycles?"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["BSR_ABLATE"] = str(8 | int(os.environ.get("ABL", "0")))
+os.environ["BSR_DEBUG_KEEP"] = "1"
+from blindshadowremoval_b200.generator import Generator  # noqa: E402
+from blindshadowremoval_b200.synthetic import make_inputs  # noqa: E402
+
+mb = 32
+gen = Generator("gsc", "bf16", device=0, micro_batch=mb, seed=1234)
+d = make_inputs(mb, 0)
+img, uv = torch.from_numpy(d["img"]).cuda(), torch.from_numpy(d["uv"]).cuda()
+for _ in range(3):
+    gen(img, uv, None, want=("con_rgb", "dif"))
+torch.cuda.synchronize()
+t = gen.debug_read("timers").reshape(64, 16)
+names = {1: "conv1", 2: "down1", 3: "down2", 4: "down3", 7: "r0.c1", 8: "r0.c2", 9: "r0.c3", 10: "r0.qkv", 12: "r0.w",
+         25: "up1", 26: "up2", 27: "up3", 28: "heads", 52: "clr_up2", 53: "clr_up3", 54: "clr_conv1"}
+print("launch  name       | producer: total wait_empty dep_wait steps | mma: total wait_full wait_tempty wait_res tiles | epi: total wait_tfull tiles")
+for i in range(64):
+    if t[i, 0] == 0 and t[i, 4] == 0:
+        continue
+    print("%3d %-10s | %9d %9d %8d %5d | %9d %9d %9d %8d %4d | %9d %9d %4d" % (
+        i, names.get(i, ""), t[i, 0], t[i, 1], t[i, 2], t[i, 3], t[i, 4], t[i, 5], t[i, 6], t[i, 7], t[i, 8], t[i, 9],
+        t[i, 10], t[i, 11]))
+    print("      mma: fence %d issue %d commit %d | producer tma-issue %d" % (t[i, 12], t[i, 13], t[i, 14], t[i, 15]))
