@@ -30,7 +30,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--variant", default="gsc", choices=["gsc", "tsm"])
     ap.add_argument("--frame", type=int, default=2)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32check"])
