@@ -84,12 +84,29 @@ def layer_work(variant):
 
 
 def sample_clocks(stop, out):
+    """Clocks / throttle reasons during the timed region: NVML in-process (20 ms period), nvidia-smi as fallback."""
+    idx = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        R = pynvml
+        bits = [("hw_slowdown", R.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", R.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", R.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", R.nvmlClocksThrottleReasonSwPowerCap)]
+        while not stop.is_set():
+            mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            out.append([str(mhz), str(mx)] + ["Active" if rs & b else "Not Active" for _, b in bits])
+            stop.wait(0.02)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    idx = os.environ.get("LOCAL_RANK", "0")
     while not stop.is_set():
         try:
-            r = subprocess.run(["nvidia-smi", "-i", idx, "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+            r = subprocess.run(["nvidia-smi", "-i", str(idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                capture_output=True, text=True, timeout=5)
             f = [x.strip() for x in r.stdout.strip().split(",")]
             if len(f) >= 6:
@@ -317,10 +334,19 @@ def main():
         total_ms = sum(r["ms_per_forward"] for r in rows)
         top = rows[0]
         unit_work = work.get(top["layer"], work.get("res0.attention"))
+        traffic = None
+        try:      # dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj["layers"].get(top["layer"]) or tj["layers"].get("res0." + top["layer"])
+            if ent:
+                traffic = {"bytes_per_launch": ent["dram_bytes"], "images_per_launch": tj["images_per_launch"],
+                           "bytes_per_image": round(ent["dram_bytes"] / tj["images_per_launch"]), "source": tj["source"]}
+        except Exception:
+            pass
         roof = {"kernel": top["layer"], "bound": top["bound"],
                 "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
                 "peak": peaks["bf16_tflops_sustained"] if top["bound"] == "tensor" else peaks["hbm_gbs"],
-                "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
+                "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": traffic,
                 "peak_source": peaks["src"] + (" sustained" if top["bound"] == "tensor" else ""),
                 "share_of_forward": round(top["ms_per_forward"] / total_ms, 4), "images_per_launch": mb,
                 "algorithmic_bytes_per_image": unit_work[1], "algorithmic_flops_per_image": unit_work[0],

@@ -65,6 +65,10 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS0 = tmem, tO = tmem + 256;
+  // programmatic dependent launch: the prologue above overlapped the tail of the qkv conv; everything below
+  // reads its output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 4) {
     if (lane == 0) {
@@ -243,7 +247,19 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
     if (cache.size() > 256) cache.clear();
     it = cache.emplace(key, std::make_pair(mq, mv)).first;
   }
-  attention_tc_kernel<<<dim3(AT_S / AT_BQ, n), 192, kAttnTcSmem, st>>>(it->second.first, it->second.second, o, errflag);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(AT_S / AT_BQ, n);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = kAttnTcSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, attention_tc_kernel, it->second.first, it->second.second, o, errflag);
+  if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
   return 0;
 }
 

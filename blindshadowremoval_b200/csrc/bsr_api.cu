@@ -527,9 +527,25 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
     }
   }
   cudaStream_t s_in = h->s_in, s_c = h->own_stream, s_out = h->s_out;
-  int total_launches = 0, k = 0;
-  for (int i0 = 0; i0 < n; i0 += step, ++k) {
-    const int m = n - i0 < step ? n - i0 : step;
+  // Chunk schedule: ramp up and down (step/4, step/2, step ... step, step/2, step/4) so that the H2D of the
+  // first chunk and the D2H of the last one - the only transfers that cannot overlap compute - are short.
+  const int unit = reg ? frame : 1;
+  auto round_unit = [&](int v) { v = v / unit * unit; return v < unit ? unit : v; };
+  std::vector<int> sched;
+  {
+    int left = n;
+    const int q4 = round_unit(step / 4), q2 = round_unit(step / 2);
+    std::vector<int> head, tail;
+    if (n >= 3 * step) { head = {q4, q2}; tail = {q2, q4}; }
+    for (int v : head) { sched.push_back(v); left -= v; }
+    int tail_sum = 0;
+    for (int v : tail) tail_sum += v;
+    while (left - tail_sum > 0) { int v = left - tail_sum < step ? left - tail_sum : step; sched.push_back(v); left -= v; }
+    for (int v : tail) { sched.push_back(v); left -= v; }
+  }
+  int total_launches = 0, k = 0, i0 = 0;
+  for (size_t ci = 0; ci < sched.size(); i0 += sched[ci], ++ci, ++k) {
+    const int m = sched[ci];
     const int slot = k & 1;
     char* sin = (char*)h->stage + slot * in_slot;
     char* sout = (char*)h->stage + 2 * in_slot + slot * out_slot;
