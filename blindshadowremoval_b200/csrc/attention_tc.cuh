@@ -9,8 +9,8 @@
 // logits of this network make an exact (not running) max the safest choice as well.
 // Layouts: QK[n][1024][256] = theta | phi (bf16);  VT[n][128][1024] = g transposed (so every UMMA
 // operand is K-major);  O[n][1024][128].
-// Warp roles (192 threads): warps 0-3 softmax / epilogue, warp 4 TMA, warp 5 TMEM alloc + MMA issue (the
-// single-thread roles get the highest warp ids: the warp arbiter favours high ids).
+// Warp roles (320 threads): warps 0-7 softmax / epilogue (4 TMEM lane quarters x 2 column halves), warp 8 TMA,
+// warp 9 TMEM alloc + MMA issue (single-thread roles get the highest warp ids: the arbiter favours high ids).
 #pragma once
 #include <map>
 #include <tuple>
@@ -24,11 +24,13 @@ namespace bsr {
 constexpr int AT_S = 1024, AT_D = 128, AT_BQ = 128, AT_BK = 128;
 constexpr int AT_NK = AT_S / AT_BK;                   // 8 key tiles
 constexpr uint32_t AT_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 bf16] as two 16 KB k-blocks
-constexpr size_t kAttnTcSmem = 1024 + 6 * (size_t)AT_TILE + 256;   // Q, K x2, V x2, P
+constexpr size_t kAttnTcSmem = 1024 + 6 * (size_t)AT_TILE + 192 + 1024 + 64;   // Q, K x2, V x2, P, barriers, exchange
 
-__global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
-                                                           const __grid_constant__ CUtensorMap tmVT,
-                                                           bf16* __restrict__ o, int* errflag) {
+constexpr int AT_THREADS = 320;      // warps 0-7 softmax / epilogue, warp 8 TMA, warp 9 TMEM alloc + MMA issue
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
+                                                                     const __grid_constant__ CUtensorMap tmVT,
+                                                                     bf16* __restrict__ o, int* errflag) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = sQ + AT_TILE, sV = sK + 2 * AT_TILE, sP = sV + 2 * AT_TILE;
@@ -36,8 +38,10 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
   const uint32_t b_q = bars, b_kfull = bars + 8, b_kempty = bars + 24, b_vfull = bars + 40, b_vempty = bars + 56,
                  b_sfull = bars + 72, b_sempty = bars + 88, b_pfull = bars + 104, b_pempty = bars + 112,
                  b_ofull = bars + 120, tmem_slot = bars + 128;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  uint8_t* sP_gen = smem_raw + (sP - smem_u32(smem_raw));
+  uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
+  uint8_t* sP_gen = smem_al + (sP - base);
+  float* xch = reinterpret_cast<float*>(smem_al + (bars + 192 - base));      // [2][128] row max / row sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, n = blockIdx.y;
@@ -52,14 +56,14 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
       mbar_init(b_vfull + 8 * s, 1);
       mbar_init(b_vempty + 8 * s, 1);
       mbar_init(b_sfull + 8 * s, 1);
-      mbar_init(b_sempty + 8 * s, 4);
+      mbar_init(b_sempty + 8 * s, 8);
     }
-    mbar_init(b_pfull, 4);
+    mbar_init(b_pfull, 8);
     mbar_init(b_pempty, 1);
     mbar_init(b_ofull, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -70,89 +74,103 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (warp == 8) {
+    // ================= TMA producer (converged warp, elected lane issues) =================
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(b_q, AT_TILE);
       tma_load_3d(sQ, &tmQK, b_q, 0, q0, n);
       tma_load_3d(sQ + AT_TILE / 2, &tmQK, b_q, 64, q0, n);
-      bool ok = true;
-      for (int it = 0; it < 2 * AT_NK && ok; ++it) {
-        const int s = it & 1, f = it >> 1, j = it & (AT_NK - 1);
-        ok = mbar_wait(b_kempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 11);
-        if (!ok) break;
+    }
+    bool ok = true;
+    for (int it = 0; it < 2 * AT_NK && ok; ++it) {
+      const int s = it & 1, f = it >> 1, j = it & (AT_NK - 1);
+      ok = mbar_wait(b_kempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 11);
+      if (!ok) break;
+      if (leader) {
         mbar_expect_tx(b_kfull + 8 * s, AT_TILE);
         tma_load_3d(sK + s * AT_TILE, &tmQK, b_kfull + 8 * s, 128, j * AT_BK, n);
         tma_load_3d(sK + s * AT_TILE + AT_TILE / 2, &tmQK, b_kfull + 8 * s, 192, j * AT_BK, n);
-        if (it >= AT_NK) {
-          const int vs = j & 1, vf = j >> 1;
-          ok = mbar_wait(b_vempty + 8 * vs, (uint32_t)(vf & 1) ^ 1u, errflag, 12);
-          if (!ok) break;
+      }
+      if (it >= AT_NK) {
+        const int vs = j & 1, vf = j >> 1;
+        ok = mbar_wait(b_vempty + 8 * vs, (uint32_t)(vf & 1) ^ 1u, errflag, 12);
+        if (!ok) break;
+        if (leader) {
           mbar_expect_tx(b_vfull + 8 * vs, AT_TILE);
           tma_load_3d(sV + vs * AT_TILE, &tmVT, b_vfull + 8 * vs, j * AT_BK, 0, n);
           tma_load_3d(sV + vs * AT_TILE + AT_TILE / 2, &tmVT, b_vfull + 8 * vs, j * AT_BK + 64, 0, n);
         }
       }
+      __syncwarp();
     }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 128);
-      bool ok = mbar_wait(b_q, 0, errflag, 13, true);
-      auto issue_pv = [&](int j) -> bool {
-        const int vs = j & 1, vf = j >> 1;
-        if (!mbar_wait(b_pfull, (uint32_t)(j & 1), errflag, 14, true)) return false;
-        if (!mbar_wait(b_vfull + 8 * vs, (uint32_t)(vf & 1), errflag, 15, true)) return false;
-        tc_fence_after();
+  } else if (warp == 9) {
+    // ================= MMA issuer (converged warp, elected lane issues) =================
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    bool ok = mbar_wait(b_q, 0, errflag, 13, true);
+    auto issue_pv = [&](int j) -> bool {
+      const int vs = j & 1, vf = j >> 1;
+      if (!mbar_wait(b_pfull, (uint32_t)(j & 1), errflag, 14, true)) return false;
+      if (!mbar_wait(b_vfull + 8 * vs, (uint32_t)(vf & 1), errflag, 15, true)) return false;
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t da = umma_desc_sw128(sP + kb * (AT_TILE / 2));
-          const uint64_t db = umma_desc_sw128(sV + vs * AT_TILE + kb * (AT_TILE / 2));
+          const uint32_t a_lo = umma_desc_lo(sP + kb * (AT_TILE / 2));
+          const uint32_t b_lo = umma_desc_lo(sV + vs * AT_TILE + kb * (AT_TILE / 2));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tO, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (j | kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_lo(tO, a_lo + 2 * k, b_lo + 2 * k, idesc, (j | kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(b_pempty);
         umma_commit(b_vempty + 8 * vs);
-        return true;
-      };
-      for (int it = 0; it < 2 * AT_NK && ok; ++it) {
-        const int s = it & 1, f = it >> 1;
-        ok = mbar_wait(b_kfull + 8 * s, (uint32_t)(f & 1), errflag, 16, true);
-        if (!ok) break;
-        ok = mbar_wait(b_sempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 17, true);
-        if (!ok) break;
-        tc_fence_after();
+      }
+      __syncwarp();
+      return true;
+    };
+    for (int it = 0; it < 2 * AT_NK && ok; ++it) {
+      const int s = it & 1, f = it >> 1;
+      ok = mbar_wait(b_kfull + 8 * s, (uint32_t)(f & 1), errflag, 16, true);
+      if (!ok) break;
+      ok = mbar_wait(b_sempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 17, true);
+      if (!ok) break;
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t da = umma_desc_sw128(sQ + kb * (AT_TILE / 2));
-          const uint64_t db = umma_desc_sw128(sK + s * AT_TILE + kb * (AT_TILE / 2));
+          const uint32_t a_lo = umma_desc_lo(sQ + kb * (AT_TILE / 2));
+          const uint32_t b_lo = umma_desc_lo(sK + s * AT_TILE + kb * (AT_TILE / 2));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tS0 + (uint32_t)s * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_lo(tS0 + (uint32_t)s * 128, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(b_kempty + 8 * s);
         umma_commit(b_sfull + 8 * s);
-        if (it > AT_NK) ok = issue_pv(it - AT_NK - 1);
       }
-      if (ok) ok = issue_pv(AT_NK - 1);
-      umma_commit(b_ofull);
+      __syncwarp();
+      if (it > AT_NK) ok = issue_pv(it - AT_NK - 1);
     }
+    if (ok) ok = issue_pv(AT_NK - 1);
+    if (leader) umma_commit(b_ofull);
+    __syncwarp();
   } else {
-    const int q = warp & 3;
+    // ================= softmax / epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
+    const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float kLog2e = 1.4426950408889634f;
     float mx = -INFINITY;
     bool ok = true;
-    // ---- pass 1: exact row max
+    // ---- pass 1: exact row max (each warp over its 64 columns, combined through smem at the end)
     for (int it = 0; it < AT_NK && ok; ++it) {
       const int s = it & 1, f = it >> 1;
       ok = mbar_wait(b_sfull + 8 * s, (uint32_t)(f & 1), errflag, 18);
       if (!ok) break;
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         float v[32];
-        tmem_ld32(tS0 + lane_addr + (uint32_t)(s * 128 + c), v);
+        tmem_ld32(tS0 + lane_addr + (uint32_t)(s * 128 + h * 64 + c), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
       }
@@ -160,6 +178,10 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(b_sempty + 8 * s);
     }
+    xch[h * 128 + row] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(xch[row], xch[128 + row]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // ---- pass 2: p = exp(s - max), P -> smem (bf16, 128B-swizzled K-major), row sum
     const float mneg = -mx * kLog2e;
     float sum = 0.f;
@@ -170,20 +192,19 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
       ok = mbar_wait(b_pempty, (uint32_t)(j & 1) ^ 1u, errflag, 20);
       if (!ok) break;
       tc_fence_after();
+      uint8_t* blk = sP_gen + h * (AT_TILE / 2) + row * 128;        // keys h*64 .. +63 = k-block h
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         float v[32];
-        tmem_ld32(tS0 + lane_addr + (uint32_t)(s * 128 + c), v);
+        tmem_ld32(tS0 + lane_addr + (uint32_t)(s * 128 + h * 64 + c), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           v[i] = exp2f(fmaf(v[i], kLog2e, mneg));
           sum += v[i];
         }
-        // keys c..c+31 -> k-block c/64, 16-byte chunks (c%64)/8 .. +3
-        uint8_t* blk = sP_gen + (c >> 6) * (AT_TILE / 2) + row * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int ch = ((c & 63) >> 3) + g;
+          const int ch = (c >> 3) + g;                                // 16-byte chunk inside the 128-byte row
           uint4 w;
           w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
           w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
@@ -200,16 +221,19 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
         mbar_arrive(b_pfull);
       }
     }
-    // ---- epilogue: O / sum -> bf16
+    xch[h * 128 + row] = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum = xch[row] + xch[128 + row];
+    // ---- epilogue: O / sum -> bf16 (each warp its 64 output channels)
     if (ok) ok = mbar_wait(b_ofull, 0, errflag, 21);
     tc_fence_after();
     if (ok) {
       const float inv = 1.f / sum;
-      bf16* dst = o + ((size_t)n * AT_S + q0 + row) * AT_D;
+      bf16* dst = o + ((size_t)n * AT_S + q0 + row) * AT_D + h * 64;
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         float v[32];
-        tmem_ld32(tO + lane_addr + (uint32_t)c, v);
+        tmem_ld32(tO + lane_addr + (uint32_t)(h * 64 + c), v);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 w;
@@ -224,7 +248,7 @@ __global__ void __launch_bounds__(192) attention_tc_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -250,7 +274,7 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(AT_S / AT_BQ, n);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(AT_THREADS);
   cfg.dynamicSmemBytes = kAttnTcSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

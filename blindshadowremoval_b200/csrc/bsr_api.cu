@@ -102,6 +102,8 @@ int fail(bsr_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 inline int pad8(int c) { return (c + 7) / 8 * 8; }
+inline int pad16(int c) { return (c + 15) / 16 * 16; }
+constexpr int kLdY = 272;      // 257 res-block channels padded to a multiple of 16: every epilogue chunk is a full vector chunk
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,7 +269,7 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   snprintf(nm[3], 32, "res%d.qkv", idx);
   snprintf(nm[4], 32, "res%d.w", idx);
   int rc;
-  const int ldy = 264;
+  const int ldy = kLdY;
   ConvCall c1{nm[0], cur, ld, 0, false, FEAT, FEAT, 1, epi(h->T1, 128, 0, 128, 1), no_extra()};
   if ((rc = run_conv(h, st, c1, n))) return rc;
   ConvCall c2{nm[1], h->T1, 128, 0, false, FEAT, FEAT, 1, epi(h->T2, 128, 0, 128, 1), no_extra()};
@@ -282,8 +284,11 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   if ((rc = run_attention(h, st, n))) return rc;
   int oc = ld < ldy ? ld : ldy;
   EpiParams ew = epi(nxt, ld, 0, oc, 1);
-  ew.res1 = h->Y; ew.res1_ld = ldy; ew.res1_c = 257;
-  ew.res2 = cur; ew.res2_ld = ld; ew.res2_c = c_cur;
+  // residual widths are the PADDED widths: padding channels of Y / cur are kept at zero, so adding them is exact
+  // and keeps every 16-channel chunk on the vectorised path
+  ew.res1 = h->Y; ew.res1_ld = ldy; ew.res1_c = ldy;
+  ew.res2 = cur; ew.res2_ld = ld; ew.res2_c = ld;
+  (void)c_cur;
   ConvCall c5{nm[4], h->O, 128, 0, false, FEAT, FEAT, 1, ew, no_extra()};
   if ((rc = run_conv(h, st, c5, n))) return rc;
   if (ld > oc) {
@@ -627,9 +632,10 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->force_direct = ev ? atoi(ev) : 0;
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
-  h->ld1 = pad8(h->c_first > 257 ? h->c_first : 257);
-  if (h->ld1 < 264) h->ld1 = 264;
-  h->ld2 = pad8(h->c_second);
+  h->ld1 = pad16(h->c_first > 257 ? h->c_first : 257);
+  if (h->ld1 < kLdY) h->ld1 = kLdY;
+  h->ld2 = pad16(h->c_second);
+  if (h->ld2 < kLdY) h->ld2 = kLdY;
   // ---- workspace: one arena, carved with 256-byte alignment
   const size_t es = h->es, mb = micro_batch;
   const size_t ldmax = h->ld1 > h->ld2 ? h->ld1 : h->ld2;
@@ -637,7 +643,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   std::vector<Req> reqs = {
       {&h->X1, mb * IMG * IMG * 32 * es}, {&h->CAT3, mb * 128 * 128 * 128 * es}, {&h->CAT2, mb * 64 * 64 * 160 * es},
       {&h->XA, mb * 1024 * ldmax * es}, {&h->XB, mb * 1024 * ldmax * es}, {&h->T1, mb * 1024 * 128 * es},
-      {&h->T2, mb * 1024 * 128 * es}, {&h->Y, mb * 1024 * 264 * es}, {&h->QK, mb * 1024 * 256 * es},
+      {&h->T2, mb * 1024 * 128 * es}, {&h->Y, mb * 1024 * kLdY * es}, {&h->QK, mb * 1024 * 256 * es},
       {&h->VT, mb * 1024 * 128 * es}, {&h->O, mb * 1024 * 128 * es}, {&h->UP3, mb * IMG * IMG * 64 * es},
       {&h->F1, mb * 64 * 64 * 128 * es}, {&h->F2, mb * 128 * 128 * 96 * es}, {&h->CAT1, mb * IMG * IMG * 72 * es},
       {&h->C16, mb * IMG * IMG * 16 * es}, {&h->PIMG, mb * IMG * (IMG + 8) * 8 * 2},
