@@ -7,8 +7,9 @@ HDRS := $(wildcard $(CSRC)/*.cuh) include/bsr.h
 
 $(OUT): $(CSRC)/bsr_api.cu $(HDRS)
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared -Xptxas -v \
-	    --expt-relaxed-constexpr -o $@ $(CSRC)/bsr_api.cu 2> build.log || (cat build.log; exit 1)
+	    --expt-relaxed-constexpr $(EXTRA) -o $@ $(CSRC)/bsr_api.cu 2> build.log || (cat build.log; exit 1)
 	@grep -E "error|warning" build.log | grep -v "ptxas info" | head -20 || true
 
+# role-timer build for tools/role_timers.py:  make clean && make EXTRA=-DBSR_ROLE_TIMERS
 clean:
 	rm -f $(OUT) build.log

@@ -35,6 +35,14 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// Role timers (tools/role_timers.py) are compiled in only with -DBSR_ROLE_TIMERS: the clock reads sit on the
+// single-thread producer / MMA critical paths.
+#ifdef BSR_ROLE_TIMERS
+#define BSR_CLK() clock64()
+#else
+#define BSR_CLK() 0ll
+#endif
+
 namespace bsr {
 
 constexpr int TC_BM = 128;          // pixels per A tile (UMMA M)
@@ -50,7 +58,8 @@ enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
 struct TcMma { int16_t col, n, brow; int16_t first; };
 struct TcStep {
   int8_t dy, dx;           // A tile shift in input pixels
-  int8_t n_mma, pad0;
+  int8_t n_mma;
+  int8_t n_a;              // 64-wide K blocks fetched by this step (1 or 2): A sub-tiles at a_c0, a_c0+64
   int16_t a_c0;            // A channel coordinate (elements)
   int16_t b_rows;          // weight rows fetched for this step
   int32_t b_k;             // weight K coordinate (elements)
@@ -67,7 +76,8 @@ struct TcWeights {
   int bn = 0;             // accumulator columns owned by one n-tile (plain conv) / 4*cout (fused convT)
   int n_tiles = 0;
   int b_box_rows = 0;     // rows per weight TMA box
-  int b_stage_rows = 0;   // max weight rows of one step
+  int b_stage_rows = 0;   // max weight rows of one step (per K block)
+  int a_sub = 1;          // max K blocks per step
   int n_steps = 0;
   int tile_w = 0;         // forced tile width (heads: 128 with two halves per tile), 0 = auto
   int rows_per_tile = 1;  // multi-row tiles: R output rows share their input rows (vertical-tap layers)
@@ -122,6 +132,7 @@ struct ConvTcParams {
   int epi_mode;
   int rows_per_tile, halves;  // multi-row tiles (groups = rows x halves)
   int pad_t, pad_l;           // SAME padding subtracted from the step shifts (plain convs)
+  int a_sub;                  // A sub-tiles per stage (max n_a over the steps)
   int b_resident, b_total_rows;
   int b_res_kblocks;          // resident weights: number of 64-element K blocks kept ([kblock][row] layout)
   int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
@@ -228,6 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool leader = elect_one();
       const int in_stride = p.in_stride, pad_l = p.pad_l, pad_t = p.pad_t, b_resident = p.b_resident;
       const int b_box_rows = p.b_box_rows, bn = p.bn, ablate = p.ablate;
+      const uint32_t a_sub = (uint32_t)p.a_sub, b_kb_stride = (uint32_t)(p.stage_bytes / 128 - p.a_sub * TC_BM) / (uint32_t)p.a_sub;
       const int tiles_x = p.tiles_x, tile_h = p.bh * p.rows_per_tile, tile_w = p.bw * p.halves;
       if (b_resident && leader) {          // weights are static: fetched before the dependency wait
         mbar_expect_tx(bar_bres, (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u);
@@ -237,9 +249,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
       long long t_wait = 0, t_dep = 0, t_tma = 0;
-      const long long t_start = clock64();
+      const long long t_start = BSR_CLK();
       pdl_wait();
-      t_dep = clock64() - t_start;
+      t_dep = BSR_CLK() - t_start;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int ntile = tile % n_tiles, mt = tile / n_tiles;
         const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
@@ -248,30 +260,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
           const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
-          const long long tw = clock64();
+          const long long tw = BSR_CLK();
           ok = mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.errflag, 1);
-          const long long tp0 = clock64();
+          const long long tp0 = BSR_CLK();
           t_wait += tp0 - tw;
           if (!ok) break;
-          const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_bytes;
+          const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_sub * a_bytes;
           if (leader) {
+            const uint32_t na = (uint32_t)sp.n_a;
+            const uint32_t bbytes = b_resident ? 0u : na * (uint32_t)sp.b_rows * 128u;
             if (ablate & 4) {
-              mbar_expect_tx(bar_full + 8 * s, b_resident ? 0u : (uint32_t)sp.b_rows * 128u);
+              mbar_expect_tx(bar_full + 8 * s, bbytes);
             } else {
-              mbar_expect_tx(bar_full + 8 * s, a_bytes + (b_resident ? 0u : (uint32_t)sp.b_rows * 128u));
-              tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, xbase + sp.a_x0 * in_stride + sp.dx, ybase + sp.dy, n);
+              mbar_expect_tx(bar_full + 8 * s, na * a_bytes + bbytes);
+              const int ax = xbase + sp.a_x0 * in_stride + sp.dx, ay = ybase + sp.dy;
+              tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, ax, ay, n);
+              if (na == 2) tma_load_4d(dstA + a_bytes, &tmA, bar_full + 8 * s, sp.a_c0 + TC_BK, ax, ay, n);
             }
             if (!b_resident) {
               const int row0 = sp.b_row + brow_base;
-              for (int r = 0; r < sp.b_rows; r += b_box_rows)
-                tma_load_2d(dstB + (uint32_t)r * 128u, &tmB, bar_full + 8 * s, sp.b_k, row0 + r);
+              for (uint32_t kb = 0; kb < na; ++kb)
+                for (int r = 0; r < sp.b_rows; r += b_box_rows)
+                  tma_load_2d(dstB + (kb * b_kb_stride + (uint32_t)r) * 128u, &tmB, bar_full + 8 * s,
+                              sp.b_k + (int)kb * TC_BK, row0 + r);
             }
           }
           __syncwarp();
-          t_tma += clock64() - tp0;
+          t_tma += BSR_CLK() - tp0;
         }
       }
-      if (tm) { p.timers[15] = t_tma; p.timers[0] = clock64() - t_start; p.timers[1] = t_wait; p.timers[2] = t_dep; p.timers[3] = it; }
+      if (tm) { p.timers[15] = t_tma; p.timers[0] = BSR_CLK() - t_start; p.timers[1] = t_wait; p.timers[2] = t_dep; p.timers[3] = it; }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ================= MMA issuer (whole warp converged; one elected lane issues) =================
@@ -280,17 +298,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       bool ok = true;
       const bool leader = elect_one();
       const int b_resident = p.b_resident, b_total_rows = p.b_total_rows, bn = p.bn, ablate = p.ablate;
+      const uint32_t a_sub = (uint32_t)p.a_sub;
+      // distance (in 16-byte units) between the weight rows of the two K blocks of a step
+      const uint32_t b_kb_lo = b_resident ? (uint32_t)b_total_rows * 8u
+                                          : ((uint32_t)(p.stage_bytes / 128 - p.a_sub * TC_BM) / (uint32_t)p.a_sub) * 8u;
       const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
       long long t_wfull = 0, t_wtempty = 0, t_fence = 0, t_issue = 0, t_commit = 0;
-      const long long t_start = clock64();
+      const long long t_start = BSR_CLK();
       if (b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
-      const long long t_res = clock64() - t_start;
+      const long long t_res = BSR_CLK() - t_start;
       const uint32_t idesc_m = umma_idesc_bf16(TC_BM, 0);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
         const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
-        const long long tw0 = clock64();
+        const long long tw0 = BSR_CLK();
         ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4, true);
-        t_wtempty += clock64() - tw0;
+        t_wtempty += BSR_CLK() - tw0;
         if (!ok) break;
         tc_fence_after();
         const uint32_t acc = tmem_base + as * (uint32_t)bn;
@@ -298,19 +320,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
           const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
-          const long long tw1 = clock64();
+          const long long tw1 = BSR_CLK();
           ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2, true);
-          const long long tc0 = clock64();
+          const long long tc0 = BSR_CLK();
           t_wfull += tc0 - tw1;
           if (!ok) break;
           tc_fence_after();
-          const long long tc1 = clock64();
+          const long long tc1 = BSR_CLK();
           t_fence += tc1 - tc0;
           const uint32_t sA = smem_base + s * stage_bytes;
           const uint32_t sB = b_resident ? sBres + (uint32_t)((sp.b_k >> 6) * b_total_rows + sp.b_row + brow_base) * 128u
-                                         : sA + a_bytes;
+                                         : sA + a_sub * a_bytes;
           const uint32_t a_lo = umma_desc_lo(sA), b_lo0 = umma_desc_lo(sB);
           const int nm = (ablate & 2) ? 0 : sp.n_mma;
+          const uint32_t na = (uint32_t)sp.n_a;
           if (leader) {
             for (int m = 0; m < nm; ++m) {
               const TcMma mm = sp.mma[m];
@@ -321,19 +344,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               umma_bf16_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
               umma_bf16_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
               umma_bf16_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
+              if (na == 2) {       // second 64-wide K block of the step
+                const uint32_t a1 = a_lo + (a_bytes >> 4), b1 = b_lo + b_kb_lo;
+                umma_bf16_lo(d, a1, b1, idesc, 1u);
+                umma_bf16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
+                umma_bf16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
+                umma_bf16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
+              }
             }
           }
-          const long long tc2 = clock64();
+          const long long tc2 = BSR_CLK();
           t_issue += tc2 - tc1;
           if (leader) umma_commit(bar_empty + 8 * s);
           __syncwarp();
-          t_commit += clock64() - tc2;
+          t_commit += BSR_CLK() - tc2;
         }
         if (leader) umma_commit(bar_tfull + 8 * as);
         __syncwarp();
       }
       if (tm) { p.timers[12] = t_fence; p.timers[13] = t_issue; p.timers[14] = t_commit; }
-      if (tm) { p.timers[4] = clock64() - t_start; p.timers[5] = t_wfull; p.timers[6] = t_wtempty; p.timers[7] = t_res; p.timers[8] = tcount; }
+      if (tm) { p.timers[4] = BSR_CLK() - t_start; p.timers[5] = t_wfull; p.timers[6] = t_wtempty; p.timers[7] = t_res; p.timers[8] = tcount; }
     }
   } else {
     // ================= epilogue: 16 warps.  warp ew reads TMEM lanes 32*(warp%4).. (hardware rule) =================
@@ -356,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int OH = p.OH, OW = p.OW, bn = p.bn, rows_per_tile = p.rows_per_tile;
     const bool tm = (p.ablate & 8) && blockIdx.x == 0 && ethread == 0;
     long long t_wtfull = 0;
-    const long long t_start = clock64();
+    const long long t_start = BSR_CLK();
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
       const int ntile = tile % n_tiles, mt = tile / n_tiles;
       const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
@@ -389,9 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
         }
-        const long long tw2 = clock64();
+        const long long tw2 = BSR_CLK();
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
-        t_wtfull += clock64() - tw2;
+        t_wtfull += BSR_CLK() - tw2;
         if (!ok) break;
         tc_fence_after();
         // running (group, column-in-group) of this warp's chunk; chunks advance by 4 x 16 columns
@@ -642,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-    if (tm) { p.timers[9] = clock64() - t_start; p.timers[10] = t_wtfull; p.timers[11] = tcount; }
+    if (tm) { p.timers[9] = BSR_CLK() - t_start; p.timers[10] = t_wtfull; p.timers[11] = tcount; }
   }
   tc_fence_before();
   __syncthreads();
@@ -678,6 +708,7 @@ inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>
   uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
   uint32_t box[2] = {TC_BK, (uint32_t)t.b_box_rows};
   if (!tma.encode_bf16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
+  for (int i = 0; i < TC_MAX_STEPS; ++i) if (t.steps[i].n_a == 0) t.steps[i].n_a = 1;
   if (cudaMalloc(&t.steps_dev, sizeof t.steps) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   if (cudaMemcpy(t.steps_dev, t.steps, sizeof t.steps, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
   t.b_total_rows = (int)rows;
@@ -723,7 +754,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   TcWeights& t = *out;
   memset(t.steps, 0, sizeof t.steps);
   t.kh = kh; t.kw = kw; t.cin = cin; t.cout = cout; t.transposed = transposed;
-  t.tile_w = 0;
+  t.tile_w = 0; t.a_sub = 1; t.rows_per_tile = 1; t.halves = 1; t.b_resident = 0; t.can_reside = 0; t.b_res_kblocks = 1;
   auto W = [&](int tap, int c, int o) { return w[((size_t)tap * cin + c) * cout + o]; };
 
   if (name == "conv1") {
@@ -816,11 +847,15 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     }
     int ns = 0;
     const int16_t co = (int16_t)cout;
-    for (int cb = 0; cb < ncb; ++cb) {
+    // two K blocks per step only if two such stages still fit the shared-memory budget when weights stream
+    const bool pair_k = !getenv("BSR_NO_KPAIR") && 2 * 2 * (TC_BM * 128 + 4 * cout * 128) <= TC_SMEM_BUDGET;
+    for (int cb = 0; cb < ncb;) {
+      const int na = (pair_k && ncb - cb >= 2) ? 2 : 1;
       const int16_t f = (int16_t)(cb == 0);
       TcStep s;
       memset(&s, 0, sizeof s);
-      s.a_c0 = (int16_t)(cb * 64); s.b_k = cb * 64;
+      s.a_c0 = (int16_t)(cb * 64); s.b_k = cb * 64; s.n_a = (int8_t)na;
+      if (na == 2) t.a_sub = 2;
       // shift (0,0): all four phases
       s.dy = 0; s.dx = 0; s.b_row = 0; s.b_rows = (int16_t)(4 * co);
       if (4 * cout <= 256) { s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)(4 * co), 0, f}; }
@@ -838,6 +873,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       s.dy = -1; s.dx = -1; s.b_row = (int16_t)(8 * co); s.b_rows = co;
       s.n_mma = 1; s.mma[0] = TcMma{0, co, 0, 0};
       t.steps[ns++] = s;
+      cb += na;
     }
     t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
@@ -847,6 +883,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   if (transposed) return false;          // cout > 96 transposed convs: see pack_tc_weights_phase
   if (kh * kw * ncb > TC_MAX_STEPS) return false;
   t.kind = TC_CONV;
+  const bool pair_k = !getenv("BSR_NO_KPAIR");
   if (cout == 384) { t.bn = 128; t.n_tiles = 3; }
   else if (cout <= 256) { t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1; }
   else { t.n_tiles = (cout + 255) / 256; t.bn = ((cout + t.n_tiles - 1) / t.n_tiles + 15) / 16 * 16; }
@@ -857,12 +894,15 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   for (int tap = 0; tap < kh * kw; ++tap) {
     for (int c = 0; c < cin; ++c)
       for (int o = 0; o < cout; ++o) host[(size_t)o * K + (size_t)tap * t.cin_pad + c] = f32_to_bf16_bits(W(tap, c, o));
-    for (int cb = 0; cb < ncb; ++cb) {
+    for (int cb = 0; cb < ncb;) {
+      const int na = (pair_k && ncb - cb >= 2) ? 2 : 1;
       TcStep& s = t.steps[ns];
       s.dy = (int8_t)(tap / kw); s.dx = (int8_t)(tap % kw);        // SAME-padding offset subtracted at launch
-      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (tap * ncb + cb) * 64; s.b_row = 0;
+      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (tap * ncb + cb) * 64; s.b_row = 0; s.n_a = (int8_t)na;
       s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
+      if (na == 2) t.a_sub = 2;
       ++ns;
+      cb += na;
     }
   }
   t.n_steps = ns;
@@ -875,6 +915,7 @@ inline bool pack_tc_weights_phase(TmaEncoder& tma, int phase, int cin, int cout,
                                   TcWeights* out, std::string* why) {
   TcWeights& t = *out;
   memset(t.steps, 0, sizeof t.steps);
+  t.a_sub = 1; t.rows_per_tile = 1; t.halves = 1; t.b_resident = 0; t.can_reside = 0; t.b_res_kblocks = 1; t.tile_w = 0;
   t.kind = TC_CONV; t.kh = 3; t.kw = 3; t.cin = cin; t.cout = cout; t.transposed = 1;
   t.cin_pad = (cin + 63) / 64 * 64;
   const int ncb = t.cin_pad / 64, py = phase >> 1, px = phase & 1;
@@ -891,12 +932,15 @@ inline bool pack_tc_weights_phase(TmaEncoder& tma, int phase, int cin, int cout,
     for (int c = 0; c < cin; ++c)
       for (int o = 0; o < cout; ++o)
         host[(size_t)o * K + ti * t.cin_pad + c] = f32_to_bf16_bits(w[((size_t)tap * cin + c) * cout + o]);
-    for (int cb = 0; cb < ncb; ++cb) {
+    for (int cb = 0; cb < ncb;) {
+      const int na = (!getenv("BSR_NO_KPAIR") && ncb - cb >= 2) ? 2 : 1;
       TcStep& s = t.steps[ns];
       s.dy = (int8_t)(-((tap / 3) >> 1)); s.dx = (int8_t)(-((tap % 3) >> 1));
-      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (int)((ti * ncb + cb) * 64); s.b_row = 0;
+      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (int)((ti * ncb + cb) * 64); s.b_row = 0; s.n_a = (int8_t)na;
       s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
+      if (na == 2) t.a_sub = 2;
       ++ns;
+      cb += na;
     }
   }
   t.n_steps = ns;
@@ -968,7 +1012,8 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   { const char* ab = getenv("BSR_ABLATE"); p.ablate = ab ? atoi(ab) : 0; }
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
   const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * t.b_total_rows * 128 : 0) + 192 + (int)(TC_MAX_STEPS * sizeof(TcStep)) + epi_bytes + 64;
-  p.stage_bytes = TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128);
+  p.a_sub = t.a_sub;
+  p.stage_bytes = t.a_sub * (TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128));
   p.n_stages = (TC_SMEM_BUDGET + 20 * 1024 - fixed_bytes) / p.stage_bytes;
   if (p.n_stages > 8) p.n_stages = 8;
   if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }

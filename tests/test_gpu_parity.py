@@ -159,6 +159,51 @@ def test_host_path_equals_device_path_and_micro_batching(G):
     gen2.close()
 
 
+def test_host_path_ramped_schedule_and_tsm_ragged_micro_batches(G):
+    """Host path with n >= 3 micro-batches uses the ramped chunk schedule (step/4, step/2, step.., step/2, step/4);
+    every split must give the bits of a single-micro-batch run.  TSM: micro-batches hold whole chunks only."""
+    w, d = case("gsc", 2, 1)
+    big = {k: np.concatenate([v] * 7)[:13] for k, v in d.items()}                 # 13 images, micro-batch 4 -> ramp
+    gen = G.Generator("gsc", "bf16", device=0, micro_batch=4, weights=w)
+    _, rgb, _, dif = gen(big["img"], big["uv"], None, want=("con_rgb", "dif"))
+    ref = G.Generator("gsc", "bf16", device=0, micro_batch=13, weights=w)
+    t = {k: torch.from_numpy(v).cuda() for k, v in big.items()}
+    _, rgb1, _, dif1 = ref(t["img"], t["uv"], None, want=("con_rgb", "dif"))
+    assert np.array_equal(rgb, rgb1.cpu().numpy()) and np.array_equal(dif, dif1.cpu().numpy())
+    gen.close()
+    ref.close()
+    wt, dt = case("tsm", 10, 10)
+    six = {k: np.concatenate([v[:2]] * 9) for k, v in dt.items()}                 # 9 chunks of frame=2
+    a = G.Generator("tsm", "bf16", device=0, micro_batch=5, weights=wt)          # 5 -> 2 chunks (4 images) per micro-batch
+    _, rgb_a, _, _ = a(six["img"], six["uv"], six["reg"], frame=2, want=("con_rgb",))
+    b = G.Generator("tsm", "bf16", device=0, micro_batch=18, weights=wt)
+    tt = {k: torch.from_numpy(v).cuda() for k, v in six.items()}
+    _, rgb_b, _, _ = b(tt["img"], tt["uv"], tt["reg"], frame=2, want=("con_rgb",))
+    assert np.array_equal(rgb_a, rgb_b.cpu().numpy())
+    assert np.array_equal(rgb_a[0:2], rgb_a[16:18])                               # identical chunks -> identical results
+    a.close()
+    b.close()
+
+
+def test_layer_times_and_launch_count(G):
+    os.environ["BSR_PROFILE"] = "1"
+    try:
+        gen = G.Generator("gsc", "bf16", device=0, micro_batch=2, seed=3)
+    finally:
+        os.environ.pop("BSR_PROFILE")
+    d = make_inputs(2, 1)
+    gen(torch.from_numpy(d["img"]).cuda(), torch.from_numpy(d["uv"]).cuda(), None)
+    torch.cuda.synchronize()
+    times = gen.layer_times()
+    names = [n for n, _ in times]
+    assert gen.launch_count() == 55 and len(times) >= 45
+    for must in ("conv1", "down1", "res0.conv2", "res5.w", "attention", "up3", "heads", "clr_up3", "clr_conv1"):
+        assert must in names, must
+    assert all(ms > 0 for _, ms in times)
+    assert gen.workspace_bytes() > 2 * 30e6
+    gen.close()
+
+
 def test_tsm_chunks_are_independent_and_share_flag(G):
     w, d = case("tsm", 4, 2)
     gen, both = run_device(G, "tsm", "bf16", w, d, 2, micro_batch=4)
@@ -170,8 +215,14 @@ def test_tsm_chunks_are_independent_and_share_flag(G):
     bm = gen3.debug_read("bmask").reshape(4, 32, 32, 1)
     ref = oracle("tsm", w, d, 2, bmask=bm, share=False)
     assert np.abs(ns["con_rgb"] - ref["con_rgb"]).max() <= FP32_TOL
+    # the same branch on the tensor-core path
+    gen4, nsb = run_device(G, "tsm", "bf16", w, d, 2, share=False)
+    bm4 = gen4.debug_read("bmask").reshape(4, 32, 32, 1)
+    ref4 = oracle("tsm", w, d, 2, bmask=bm4, share=False)
+    assert psnr(np.clip(nsb["con_rgb"], 0, 1), np.clip(ref4["con_rgb"], 0, 1)) >= BF16_PSNR_DB
     gen.close()
     gen3.close()
+    gen4.close()
 
 
 def test_errors_and_optional_outputs(G):
