@@ -55,11 +55,12 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4 };
 enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
 
-struct TcMma { int16_t col, n, brow; int16_t first; };
+struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overwrite (first tap), bit 1 = A sub-tile
 struct TcStep {
   int8_t dy, dx;           // A tile shift in input pixels
   int8_t n_mma;
-  int8_t n_a;              // 64-wide K blocks fetched by this step (1 or 2): A sub-tiles at a_c0, a_c0+64
+  int8_t n_a;              // 1: one A tile; 2: two 64-wide K blocks (A sub-tiles at a_c0, a_c0+64, same MMAs over both);
+                           // 3: two input ROWS (A sub-tiles at dy, dy+1), each MMA names its sub-tile (TcMma.first bit 1)
   int16_t a_c0;            // A channel coordinate (elements)
   int16_t b_rows;          // weight rows fetched for this step
   int32_t b_k;             // weight K coordinate (elements)
@@ -267,15 +268,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (!ok) break;
           const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_sub * a_bytes;
           if (leader) {
-            const uint32_t na = (uint32_t)sp.n_a;
+            const uint32_t rowmode = sp.n_a == 3, na = rowmode ? 1u : (uint32_t)sp.n_a, nsub = sp.n_a >= 2 ? 2u : 1u;
             const uint32_t bbytes = b_resident ? 0u : na * (uint32_t)sp.b_rows * 128u;
             if (ablate & 4) {
               mbar_expect_tx(bar_full + 8 * s, bbytes);
             } else {
-              mbar_expect_tx(bar_full + 8 * s, na * a_bytes + bbytes);
+              mbar_expect_tx(bar_full + 8 * s, nsub * a_bytes + bbytes);
               const int ax = xbase + sp.a_x0 * in_stride + sp.dx, ay = ybase + sp.dy;
               tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, ax, ay, n);
-              if (na == 2) tma_load_4d(dstA + a_bytes, &tmA, bar_full + 8 * s, sp.a_c0 + TC_BK, ax, ay, n);
+              if (nsub == 2)
+                tma_load_4d(dstA + a_bytes, &tmA, bar_full + 8 * s, sp.a_c0 + (rowmode ? 0 : TC_BK), ax, ay + (int)rowmode, n);
             }
             if (!b_resident) {
               const int row0 = sp.b_row + brow_base;
@@ -340,10 +342,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t b_lo = b_lo0 + (uint32_t)mm.brow * 8u;          // 128-byte rows, address >> 4
               const uint32_t idesc = idesc_m | ((uint32_t)(mm.n >> 3) << 17);
               const uint32_t d = acc + (uint32_t)mm.col;
-              umma_bf16_lo(d, a_lo, b_lo, idesc, mm.first ? 0u : 1u);
-              umma_bf16_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
-              umma_bf16_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
-              umma_bf16_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
+              const uint32_t a0 = a_lo + ((mm.first & 2) ? (a_bytes >> 4) : 0u);     // row mode: second input row
+              umma_bf16_lo(d, a0, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
+              umma_bf16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
+              umma_bf16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
+              umma_bf16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
               if (na == 2) {       // second 64-wide K block of the step
                 const uint32_t a1 = a_lo + (a_bytes >> 4), b1 = b_lo + b_kb_lo;
                 umma_bf16_lo(d, a1, b1, idesc, 1u);
@@ -735,12 +738,21 @@ inline bool tc_disabled(const std::string& name) {
 // weight blocks of consecutive output rows are consecutive too: all rows that already hold a partial sum are
 // updated by ONE wide MMA (A read from shared memory once), and the row whose first tap this is by a second MMA
 // with accumulate = 0.  Accumulator column of (group base, row rr) = (base + rr) * nb.
-inline void tc_rows_step(TcStep& sp, int j, int R, int KH, int nb, int base) {
-  sp.n_mma = 0;
+inline void tc_rows_sub(TcStep& sp, int j, int R, int KH, int nb, int base, int sub) {
   const int lo = j - (KH - 1) > 0 ? j - (KH - 1) : 0, hi = j - 1 < R - 1 ? j - 1 : R - 1;
+  const int16_t sb = (int16_t)(sub << 1);
   if (hi >= lo)
-    sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + lo) * nb), (int16_t)((hi - lo + 1) * nb), (int16_t)((lo + KH - 1 - j) * nb), 0};
-  if (j <= R - 1) sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + j) * nb), (int16_t)nb, (int16_t)((KH - 1) * nb), 1};
+    sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + lo) * nb), (int16_t)((hi - lo + 1) * nb), (int16_t)((lo + KH - 1 - j) * nb), sb};
+  if (j <= R - 1) sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + j) * nb), (int16_t)nb, (int16_t)((KH - 1) * nb), (int16_t)(sb | 1)};
+}
+// One step = input rows j and j+1 (two A sub-tiles, TMA boxes at dy and dy+1) when `pair` and both rows exist.
+inline void tc_rows_step(TcStep& sp, int j, int R, int KH, int nb, int base, bool pair) {
+  sp.n_mma = 0;
+  tc_rows_sub(sp, j, R, KH, nb, base, 0);
+  if (pair && j + 1 < R + KH - 1) {
+    sp.n_a = 3;
+    tc_rows_sub(sp, j + 1, R, KH, nb, base, 1);
+  }
 }
 
 // Build the step program and the packed bf16 weight matrix of one layer from canonical fp32
@@ -773,10 +785,12 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
         for (int c = 0; c < cin; ++c)
           for (int o = 0; o < cout; ++o) host[((size_t)(6 - a) * nb + o) * K + b * 8 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
     int ns = 0;
-    for (int j = 0; j < R + 6; ++j) {
+    const bool rpair = !getenv("BSR_NO_RPAIR");
+    if (rpair) t.a_sub = 2;
+    for (int j = 0; j < R + 6; j += rpair ? 2 : 1) {
       TcStep& sp = t.steps[ns++];
       sp.dy = (int8_t)(j - 3); sp.dx = 0; sp.a_c0 = 0; sp.b_rows = 0; sp.b_k = 0; sp.b_row = 0;
-      tc_rows_step(sp, j, R, 7, nb, 0);
+      tc_rows_step(sp, j, R, 7, nb, 0, rpair);
     }
     t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
@@ -795,11 +809,13 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
         for (int c = 0; c < 64; ++c)
           for (int o = 0; o < 2; ++o) host[((size_t)(6 - a) * 16 + b * 2 + o) * K + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
     int ns = 0;
+    const bool rpair = !getenv("BSR_NO_RPAIR");
+    if (rpair) t.a_sub = 2;
     for (int hh = 0; hh < 2; ++hh)
-      for (int j = 0; j < R + 6; ++j) {
+      for (int j = 0; j < R + 6; j += rpair ? 2 : 1) {
         TcStep& sp = t.steps[ns++];
         sp.dy = (int8_t)(j - 3); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
-        tc_rows_step(sp, j, R, 7, 16, hh * R);
+        tc_rows_step(sp, j, R, 7, 16, hh * R, rpair);
       }
     t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
@@ -818,11 +834,13 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
         for (int c = 0; c < 64; ++c)
           for (int o = 0; o < 16; ++o) host[((size_t)(2 - a) * 48 + b * 16 + o) * K + c] = f32_to_bf16_bits(W(a * 3 + b, c, o));
     int ns = 0;
+    const bool rpair = !getenv("BSR_NO_RPAIR");
+    if (rpair) t.a_sub = 2;
     for (int hh = 0; hh < 2; ++hh)
-      for (int j = 0; j < R + 2; ++j) {
+      for (int j = 0; j < R + 2; j += rpair ? 2 : 1) {
         TcStep& sp = t.steps[ns++];
         sp.dy = (int8_t)(j - 1); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
-        tc_rows_step(sp, j, R, 3, 48, hh * R);
+        tc_rows_step(sp, j, R, 3, 48, hh * R, rpair);
       }
     t.n_steps = ns;
     (void)bias;
