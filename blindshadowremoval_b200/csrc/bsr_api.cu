@@ -444,7 +444,7 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     debug_capture(h, st, "clr_up3", h->CAT1, 64, 0, 64, px256);
     // clr_conv1 (f on tensor cores + fp32 gs taps) + clr_conv2 + clr_conv3 + final dif in one kernel
     ConvCall kc{"clr_conv1", h->CAT1, 64, 0, false, IMG, IMG, 1, epi(nullptr, 0, 0, 16, 1), no_extra()};
-    kc.x.img = img; kc.x.gs_f32 = h->GS32; kc.x.rgb_out = rgb; kc.x.dif_out = dif; kc.x.aux = h->layers["clr_conv1"].tc.aux;
+    kc.x.img = img; kc.x.gs_f32 = h->GS32; kc.x.rgb_out = rgb; kc.x.dif_out = dif;
     if ((rc = run_conv(h, st, kc, n))) return rc;
   } else {
     ConvCall k3{"clr_up3", h->F2, 96, 0, false, 128, 128, 2, epi(h->CAT1, 72, 0, 64, 1), no_extra()};
@@ -778,17 +778,16 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
     Layer& c2 = h->layers["clr_conv2"];
     Layer& c3 = h->layers["clr_conv3"];
     if (c2.cin != 16 || c2.cout != 16 || c3.cin != 16 || c3.cout != 3) return fail(h, BSR_EINVAL, "unexpected colour tail shapes");
-    std::vector<float> aux(144 + 256 + 16 + 48 + 3);
+    if (!c1.tc.clr) c1.tc.clr = new ClrWeights();
+    ClrWeights& cw = *c1.tc.clr;
+    memset(&cw, 0, sizeof cw);
     for (int t = 0; t < 9; ++t)
-      for (int o = 0; o < 16; ++o) aux[t * 16 + o] = c1.w_host[((size_t)t * 65 + 64) * 16 + o];
-    memcpy(&aux[144], c2.w_host.data(), 256 * 4);
-    memcpy(&aux[400], c2.b_host.data(), 16 * 4);
+      for (int o = 0; o < 16; ++o) cw.wg[t * 16 + o] = c1.w_host[((size_t)t * 65 + 64) * 16 + o];
+    memcpy(cw.w2, c2.w_host.data(), 256 * 4);
+    memcpy(cw.b2, c2.b_host.data(), 16 * 4);
     for (int c = 0; c < 16; ++c)
-      for (int o = 0; o < 3; ++o) aux[416 + o * 16 + c] = c3.w_host[c * 3 + o];       // transposed: [3 out][16 in]
-    memcpy(&aux[464], c3.b_host.data(), 3 * 4);
-    if (c1.tc.aux) cudaFree(c1.tc.aux);
-    CK(h, cudaMalloc(&c1.tc.aux, aux.size() * 4));
-    CK(h, cudaMemcpy(c1.tc.aux, aux.data(), aux.size() * 4, cudaMemcpyHostToDevice));
+      for (int o = 0; o < 3; ++o) cw.w3t[o * 16 + c] = c3.w_host[c * 3 + o];       // transposed: [3 out][16 in]
+    memcpy(cw.b3, c3.b_host.data(), 3 * 4);
   }
   const int cin_first = h->c_first, cin_second = h->c_second;
   if (h->layers["res0.conv1"].cin != cin_first || h->layers["res3.conv1"].cin != cin_second)

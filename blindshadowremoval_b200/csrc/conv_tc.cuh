@@ -51,6 +51,10 @@ constexpr int TC_THREADS = 576;
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MAX_STEPS = 64;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
+// row-exchange buffers: pixel stride in floats, padded so that 8 consecutive lanes' 16-byte accesses hit 8
+// different 4-bank groups (stride = 20 mod 32 words): 48 -> 52 (colour tail), 16 -> 20 (heads)
+constexpr int CLR_RS = 52, HEADS_RS = 20;
+constexpr int CLR_NB = 64;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns, padded to 64 (TMEM alignment)
 
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4 };
 enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
@@ -67,6 +71,16 @@ struct TcStep {
   int16_t b_row;           // first weight row (plus n-tile offset for plain convs)
   int16_t a_x0;            // extra GEMM-x offset of the A tile (heads: 0 / 128 for the two row halves)
   TcMma mma[8];
+};
+
+// Weights of the fused colour tail, passed BY VALUE as a kernel parameter: they live in the constant bank and are
+// consumed directly as FFMA operands (no loads, no shared-memory traffic competing with the UMMA operand reads).
+struct ClrWeights {
+  float wg[9 * 16];      // gs taps of clr_conv1 [tap][out]
+  float w2[16 * 16];     // clr_conv2 [in][out]
+  float b2[16];
+  float w3t[3 * 16];     // clr_conv3 transposed [out][in]
+  float b3[4];
 };
 
 struct TcWeights {
@@ -90,14 +104,14 @@ struct TcWeights {
   TcStep steps[TC_MAX_STEPS];
   TcStep* steps_dev = nullptr;
   bf16* dev = nullptr;
-  float* aux = nullptr;   // EPI_CLR: [9][16] gs weights, [16][16] conv2, [16] b2, [16][3] conv3, [3] b3
+  ClrWeights* clr = nullptr;   // EPI_CLR: host copy of the colour-tail weights (kernel parameter)
   CUtensorMap map;
   void release() {
     if (dev) cudaFree(dev);
-    if (aux) cudaFree(aux);
+    if (clr) delete clr;
     if (steps_dev) cudaFree(steps_dev);
     dev = nullptr;
-    aux = nullptr;
+    clr = nullptr;
     steps_dev = nullptr;
     ready = false;
   }
@@ -112,7 +126,6 @@ struct EpiExtra {
   float* gs_f32;           // fp32 [N,256,256] gs (input of the colour tail)
   float* rgb_out;
   float* dif_out;
-  const float* aux;        // EPI_CLR weights (see TcWeights::aux)
 };
 
 struct ConvTcParams {
@@ -184,7 +197,8 @@ template <int EPI, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ ConvTcParams p,
-                                                                const EpiParams e, const EpiExtra x) {
+                                                                const EpiParams e, const EpiExtra x,
+                                                                const __grid_constant__ ClrWeights cw) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TC_BM * 128;
@@ -382,8 +396,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float* bias_s = epi_smem;                   // [512] (the device bias buffer is zero-padded past cout)
     float* epi_work = epi_smem + 512;
     for (int i = ethread; i < 512; i += TC_EPI_WARPS * 32) bias_s[i] = __ldg(e.bias + i);
-    if (EPI == EPI_CLR)
-      for (int i = ethread; i < 144 + 256 + 16 + 48 + 3; i += TC_EPI_WARPS * 32) epi_work[i] = x.aux[i];
     epi_bar_all();
     pdl_wait();
     const int OH = p.OH, OW = p.OW, bn = p.bn, rows_per_tile = p.rows_per_tile;
@@ -513,11 +525,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int half = cg & 1, slot = cg >> 1;
         const int y0 = tr * rows_per_tile;
         const int xg = half * 128 + r;
-        float* rowbuf = epi_work + slot * (262 * 16);               // [256 + 6][16], 3 zero columns either side
+        float* rowbuf = epi_work + slot * (262 * HEADS_RS);         // [256 + 6][16 (+4 pad)], 3 zero columns either side
         const int st = ethread - slot * 256 - (ethread >= 256 && slot == 0 ? 0 : 0);
         if ((ethread & 255) < 96) {
           const int i = ethread & 255;                              // zero the two halos (3 x 16 each) of my slot's buffer
-          rowbuf[(i < 48 ? 0 : 256 * 16) + i] = 0.f;
+          const int px = i < 48 ? i / 16 : 259 + (i - 48) / 16;
+          rowbuf[px * HEADS_RS + (i & 15)] = 0.f;
         }
         (void)st;
         const float b2 = bias_s[0], b3 = bias_s[1];
@@ -542,12 +555,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(rowbuf + (xg + 3) * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            *reinterpret_cast<float4*>(rowbuf + (xg + 3) * HEADS_RS + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           epi_bar_slot(slot);
           float c2 = b2, c3 = b3;
 #pragma unroll
           for (int kw = 0; kw < 7; ++kw) {
-            const float2 t = *reinterpret_cast<const float2*>(rowbuf + (xg + kw) * 16 + kw * 2);
+            const float2 t = *reinterpret_cast<const float2*>(rowbuf + (xg + kw) * HEADS_RS + kw * 2);
             c2 += t.x;
             c3 += t.y;
           }
@@ -571,15 +584,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int half = cg & 1, slot = cg >> 1;
         const int y0 = tr * rows_per_tile;
         const int xg = half * 128 + r;
-        const float4* wg4 = reinterpret_cast<const float4*>(epi_work);            // [9][16]
-        const float4* w24 = reinterpret_cast<const float4*>(epi_work + 144);      // [16 in][16 out]
-        const float4* b24 = reinterpret_cast<const float4*>(epi_work + 400);
-        const float4* w3t4 = reinterpret_cast<const float4*>(epi_work + 416);     // [3 out][16 in]
-        const float* b3 = epi_work + 464;
-        float* rowbuf = epi_work + 512 + slot * (258 * 48);   // [256 + 2][48], one zero column either side
+        float* rowbuf = epi_work + slot * (258 * CLR_RS);   // [256 + 2][48 (+4 pad)], one zero column either side
         if ((ethread & 255) < 96) {
           const int i = ethread & 255;
-          rowbuf[(i < 48 ? 0 : 256 * 48) + i] = 0.f;
+          rowbuf[(i < 48 ? 0 : 257 * CLR_RS) + (i % 48)] = 0.f;
         }
         const float* gsn = x.gs_f32 + (size_t)n * OH * OW;
         // issue the 9 gs taps and the input pixel first: their latency overlaps the accumulator wait
@@ -596,11 +604,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (!ok) break;
         tc_fence_after();
         {
-          float* dst = rowbuf + (xg + 1) * 48;
+          float* dst = rowbuf + (xg + 1) * CLR_RS;
 #pragma unroll
           for (int c = 0; c < 48; c += 16) {
             float v[16];
-            tmem_ld16(acc + (uint32_t)((half * rows_per_tile + slot) * 48 + c), v);
+            tmem_ld16(acc + (uint32_t)((half * rows_per_tile + slot) * CLR_NB + c), v);
 #pragma unroll
             for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int i = 0; i < 16; ++i) v[i] = bias_s[i];
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float* src = rowbuf + (xg + kw) * 48 + kw * 16;
+          const float* src = rowbuf + (xg + kw) * CLR_RS + kw * 16;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 t = *reinterpret_cast<const float4*>(src + i);
@@ -625,28 +633,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 w = wg4[t * 4 + i];
-            v[4 * i] = fmaf(gv[t], w.x, v[4 * i]); v[4 * i + 1] = fmaf(gv[t], w.y, v[4 * i + 1]);
-            v[4 * i + 2] = fmaf(gv[t], w.z, v[4 * i + 2]); v[4 * i + 3] = fmaf(gv[t], w.w, v[4 * i + 3]);
-          }
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(gv[t], cw.wg[t * 16 + i], v[i]);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
         float hbuf[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b = b24[i];
-          hbuf[4 * i] = b.x; hbuf[4 * i + 1] = b.y; hbuf[4 * i + 2] = b.z; hbuf[4 * i + 3] = b.w;
-        }
+        for (int i = 0; i < 16; ++i) hbuf[i] = cw.b2[i];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 w = w24[c * 4 + i];
-            hbuf[4 * i] = fmaf(v[c], w.x, hbuf[4 * i]); hbuf[4 * i + 1] = fmaf(v[c], w.y, hbuf[4 * i + 1]);
-            hbuf[4 * i + 2] = fmaf(v[c], w.z, hbuf[4 * i + 2]); hbuf[4 * i + 3] = fmaf(v[c], w.w, hbuf[4 * i + 3]);
-          }
+          for (int i = 0; i < 16; ++i) hbuf[i] = fmaf(v[c], cw.w2[c * 16 + i], hbuf[i]);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) hbuf[i] = fmaxf(hbuf[i], kLeaky * hbuf[i]);
@@ -654,12 +651,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           // four independent partial sums keep the FMA chain short
-          float s0 = b3[o], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          float s0 = cw.b3[o], s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 w = w3t4[o * 4 + i];
-            s0 = fmaf(hbuf[4 * i], w.x, s0); s1 = fmaf(hbuf[4 * i + 1], w.y, s1);
-            s2 = fmaf(hbuf[4 * i + 2], w.z, s2); s3 = fmaf(hbuf[4 * i + 3], w.w, s3);
+            s0 = fmaf(hbuf[4 * i], cw.w3t[o * 16 + 4 * i], s0); s1 = fmaf(hbuf[4 * i + 1], cw.w3t[o * 16 + 4 * i + 1], s1);
+            s2 = fmaf(hbuf[4 * i + 2], cw.w3t[o * 16 + 4 * i + 2], s2); s3 = fmaf(hbuf[4 * i + 3], cw.w3t[o * 16 + 4 * i + 3], s3);
           }
           rgb[o] = (s0 + s1) + (s2 + s3);
         }
@@ -824,15 +820,15 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   if (name == "clr_conv1") {
     // canonical input order [f0..f63, gs]: f runs on tensor cores, gs (fp32) in the epilogue
     if (kh != 3 || kw != 3 || cin != 65 || cout != 16) { *why = "clr_conv1 must be 3x3 65->16"; return false; }
-    const int R = 2;
-    t.kind = TC_CLR; t.cin_pad = 64; t.bn = R * 2 * 48; t.n_tiles = 1; t.b_box_rows = 48; t.b_stage_rows = 0;
+    const int R = 2, nb = CLR_NB;
+    t.kind = TC_CLR; t.cin_pad = 64; t.bn = R * 2 * nb; t.n_tiles = 1; t.b_box_rows = nb; t.b_stage_rows = 0;
     t.b_resident = 1; t.rows_per_tile = R; t.halves = 2; t.tile_w = 128;
-    const size_t K = 64, rows = 3 * 48;
+    const size_t K = 64, rows = 3 * (size_t)nb;
     std::vector<uint16_t> host(rows * K, 0);
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 3; ++b)
         for (int c = 0; c < 64; ++c)
-          for (int o = 0; o < 16; ++o) host[((size_t)(2 - a) * 48 + b * 16 + o) * K + c] = f32_to_bf16_bits(W(a * 3 + b, c, o));
+          for (int o = 0; o < 16; ++o) host[((size_t)(2 - a) * nb + b * 16 + o) * K + c] = f32_to_bf16_bits(W(a * 3 + b, c, o));
     int ns = 0;
     const bool rpair = !getenv("BSR_NO_RPAIR");
     if (rpair) t.a_sub = 2;
@@ -840,7 +836,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       for (int j = 0; j < R + 2; j += rpair ? 2 : 1) {
         TcStep& sp = t.steps[ns++];
         sp.dy = (int8_t)(j - 1); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
-        tc_rows_step(sp, j, R, 3, 48, hh * R, rpair);
+        tc_rows_step(sp, j, R, 3, nb, hh * R, rpair);
       }
     t.n_steps = ns;
     (void)bias;
@@ -1025,7 +1021,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const bool resident = t.b_resident || (t.can_reside && p.total_tiles >= 6 * grid);
   p.b_resident = resident ? 1 : 0;
-  const int epi_bytes = 2048 + (p.epi_mode == EPI_HEADS ? 2 * 262 * 16 * 4 : (p.epi_mode == EPI_CLR ? 2048 + 2 * 258 * 48 * 4 : 0));
+  const int epi_bytes = 2048 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 258 * CLR_RS * 4 : 0));
   p.b_res_kblocks = t.b_res_kblocks;
   { const char* ab = getenv("BSR_ABLATE"); p.ablate = ab ? atoi(ab) : 0; }
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
@@ -1068,11 +1064,13 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
+  static const ClrWeights no_clr = {};
+  const ClrWeights& cw = (p.epi_mode == EPI_CLR && t.clr) ? *t.clr : no_clr;
   cudaError_t le;
-  if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x);
-  else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x);
-  else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x);
-  else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x);
+  if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x, cw);
+  else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x, cw);
+  else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x, cw);
+  else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x, cw);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }
   (*launches)++;
   return 0;
