@@ -24,7 +24,7 @@ namespace bsr {
 constexpr int AT_S = 1024, AT_D = 128, AT_BQ = 128, AT_BK = 128;
 constexpr int AT_NK = AT_S / AT_BK;                   // 8 key tiles
 constexpr uint32_t AT_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 bf16] as two 16 KB k-blocks
-constexpr size_t kAttnTcSmem = 1024 + 6 * (size_t)AT_TILE + 192 + 1024 + 64;   // Q, K x2, V x2, P, barriers, exchange
+constexpr size_t kAttnTcSmem = 1024 + 7 * (size_t)AT_TILE + 192 + 1024;   // Q, K x2, V x2, P x2, barriers, exchange
 
 constexpr int AT_THREADS = 320;      // warps 0-7 softmax / epilogue, warp 8 TMA, warp 9 TMEM alloc + MMA issue
 
@@ -34,10 +34,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = sQ + AT_TILE, sV = sK + 2 * AT_TILE, sP = sV + 2 * AT_TILE;
-  const uint32_t bars = sP + AT_TILE;
+  const uint32_t bars = sP + 2 * AT_TILE;       // P is double-buffered: softmax(j+1) overlaps the PV MMA of tile j
   const uint32_t b_q = bars, b_kfull = bars + 8, b_kempty = bars + 24, b_vfull = bars + 40, b_vempty = bars + 56,
-                 b_sfull = bars + 72, b_sempty = bars + 88, b_pfull = bars + 104, b_pempty = bars + 112,
-                 b_ofull = bars + 120, tmem_slot = bars + 128;
+                 b_sfull = bars + 72, b_sempty = bars + 88, b_pfull = bars + 104, b_pempty = bars + 120,
+                 b_ofull = bars + 136, tmem_slot = bars + 144;
   uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
   uint8_t* sP_gen = smem_al + (sP - base);
@@ -58,8 +58,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       mbar_init(b_sfull + 8 * s, 1);
       mbar_init(b_sempty + 8 * s, 8);
     }
-    mbar_init(b_pfull, 8);
-    mbar_init(b_pempty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_pfull + 8 * s, 8);
+      mbar_init(b_pempty + 8 * s, 1);
+    }
     mbar_init(b_ofull, 1);
     fence_barrier_init();
   }
@@ -111,18 +113,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     bool ok = mbar_wait(b_q, 0, errflag, 13, true);
     auto issue_pv = [&](int j) -> bool {
       const int vs = j & 1, vf = j >> 1;
-      if (!mbar_wait(b_pfull, (uint32_t)(j & 1), errflag, 14, true)) return false;
+      const int ps = j & 1, pf = j >> 1;
+      if (!mbar_wait(b_pfull + 8 * ps, (uint32_t)(pf & 1), errflag, 14, true)) return false;
       if (!mbar_wait(b_vfull + 8 * vs, (uint32_t)(vf & 1), errflag, 15, true)) return false;
       tc_fence_after();
       if (leader) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint32_t a_lo = umma_desc_lo(sP + kb * (AT_TILE / 2));
+          const uint32_t a_lo = umma_desc_lo(sP + ps * AT_TILE + kb * (AT_TILE / 2));
           const uint32_t b_lo = umma_desc_lo(sV + vs * AT_TILE + kb * (AT_TILE / 2));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_lo(tO, a_lo + 2 * k, b_lo + 2 * k, idesc, (j | kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(b_pempty);
+        umma_commit(b_pempty + 8 * ps);
         umma_commit(b_vempty + 8 * vs);
       }
       __syncwarp();
@@ -189,10 +192,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       const int it = AT_NK + j, s = it & 1, f = it >> 1;
       ok = mbar_wait(b_sfull + 8 * s, (uint32_t)(f & 1), errflag, 19);
       if (!ok) break;
-      ok = mbar_wait(b_pempty, (uint32_t)(j & 1) ^ 1u, errflag, 20);
+      const int ps = j & 1, pf = j >> 1;
+      ok = mbar_wait(b_pempty + 8 * ps, (uint32_t)(pf & 1) ^ 1u, errflag, 20);
       if (!ok) break;
       tc_fence_after();
-      uint8_t* blk = sP_gen + h * (AT_TILE / 2) + row * 128;        // keys h*64 .. +63 = k-block h
+      uint8_t* blk = sP_gen + ps * AT_TILE + h * (AT_TILE / 2) + row * 128;        // keys h*64 .. +63 = k-block h
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         float v[32];
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(b_sempty + 8 * s);
-        mbar_arrive(b_pfull);
+        mbar_arrive(b_pfull + 8 * ps);
       }
     }
     xch[h * 128 + row] = sum;
