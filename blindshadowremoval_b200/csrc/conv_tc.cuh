@@ -56,7 +56,7 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 constexpr int CLR_RS = 52, HEADS_RS = 20;
 constexpr int CLR_NB = 64;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns, padded to 64 (TMEM alignment)
 
-enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4 };
+enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4, TC_PAIRX = 5 };
 enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
 
 struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overwrite (first tap), bit 1 = A sub-tile
@@ -133,6 +133,7 @@ struct ConvTcParams {
   int tiles_x, tiles_y;       // tiles per image in GEMM space
   int bw, bh;                 // A-tile rectangle
   int in_stride;              // 1 or 2: input coordinate = gemm coordinate * in_stride + shift
+  int in_stride_x;            // x stride in units of the TMA x dimension (TC_PAIRX: pixel PAIRS -> 1)
   int out_scale;              // 1 (conv) or 2 (transposed)
   int OH, OW;
   int n_tiles;                // weight n-tiles (plain conv)
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t it = 0;
       bool ok = true;
       const bool leader = elect_one();
-      const int in_stride = p.in_stride, pad_l = p.pad_l, pad_t = p.pad_t, b_resident = p.b_resident;
+      const int in_stride = p.in_stride, in_stride_x = p.in_stride_x, pad_l = p.pad_l, pad_t = p.pad_t, b_resident = p.b_resident;
       const int b_box_rows = p.b_box_rows, bn = p.bn, ablate = p.ablate;
       const uint32_t a_sub = (uint32_t)p.a_sub, b_kb_stride = (uint32_t)(p.stage_bytes / 128 - p.a_sub * TC_BM) / (uint32_t)p.a_sub;
       const int tiles_x = p.tiles_x, tile_h = p.bh * p.rows_per_tile, tile_w = p.bw * p.halves;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int ntile = tile % n_tiles, mt = tile / n_tiles;
         const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
         const int gy0 = (tr / tiles_x) * tile_h, gx0 = (tr % tiles_x) * tile_w;
-        const int xbase = gx0 * in_stride - pad_l, ybase = gy0 * in_stride - pad_t, brow_base = ntile * bn;
+        const int xbase = gx0 * in_stride_x - pad_l, ybase = gy0 * in_stride - pad_t, brow_base = ntile * bn;
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
           const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               mbar_expect_tx(bar_full + 8 * s, bbytes);
             } else {
               mbar_expect_tx(bar_full + 8 * s, nsub * a_bytes + bbytes);
-              const int ax = xbase + sp.a_x0 * in_stride + sp.dx, ay = ybase + sp.dy;
+              const int ax = xbase + sp.a_x0 * in_stride_x + sp.dx, ay = ybase + sp.dy;
               tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, ax, ay, n);
               if (nsub == 2)
                 tma_load_4d(dstA + a_bytes, &tmA, bar_full + 8 * s, sp.a_c0 + (rowmode ? 0 : TC_BK), ax, ay + (int)rowmode, n);
@@ -893,6 +894,35 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     return tc_upload(tma, t, host, rows, K, why);
   }
 
+  if (!transposed && kh == 3 && kw == 3 && cin == 32 && name == "down1" && !getenv("BSR_NO_PAIRX")) {
+    // 3x3 / stride 2 over a 32-channel tensor (down1, model.py:207): two neighbouring pixels are 64 contiguous
+    // elements, so taps (kh,0),(kh,1) of output column ox are ONE full K block at pixel pair ox and tap (kh,2) is the
+    // first half of pair ox+1: 6 steps instead of 9 half-empty ones, and no x-stride in the TMA box.
+    t.kind = TC_PAIRX; t.cin_pad = 64; t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1;
+    t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
+    const size_t K = 6 * 64, rows = t.bn;
+    std::vector<uint16_t> host(rows * K, 0);
+    int ns = 0;
+    for (int a = 0; a < 3; ++a)
+      for (int half = 0; half < 2; ++half) {
+        TcStep& sp = t.steps[ns];
+        sp.dy = (int8_t)a; sp.dx = (int8_t)half; sp.a_c0 = 0; sp.b_rows = (int16_t)t.bn; sp.b_k = ns * 64; sp.b_row = 0; sp.n_a = 1;
+        sp.n_mma = 1; sp.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
+        for (int o = 0; o < cout; ++o)
+          for (int c = 0; c < 32; ++c) {
+            if (half == 0) {
+              host[(size_t)o * K + ns * 64 + c] = f32_to_bf16_bits(W(a * 3 + 0, c, o));
+              host[(size_t)o * K + ns * 64 + 32 + c] = f32_to_bf16_bits(W(a * 3 + 1, c, o));
+            } else {
+              host[(size_t)o * K + ns * 64 + c] = f32_to_bf16_bits(W(a * 3 + 2, c, o));
+            }
+          }
+        ++ns;
+      }
+    t.n_steps = ns;
+    return tc_upload(tma, t, host, rows, K, why);
+  }
+
   // ---- plain conv, or one launch per phase for wide transposed convs (handled by the caller via `phase`)
   if (transposed) return false;          // cout > 96 transposed convs: see pack_tc_weights_phase
   if (kh * kw * ncb > TC_MAX_STEPS) return false;
@@ -989,6 +1019,11 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     int tot_w = (p.OW - 1) * stride + t.kw - W; if (tot_w < 0) tot_w = 0;
     pad_t = tot_h / 2; pad_l = tot_w / 2;        // TF SAME: before = total // 2
   }
+  p.in_stride_x = p.in_stride;
+  if (t.kind == TC_PAIRX) {
+    if (stride != 2 || (W & 1) || (H & 1) || in_ld != 32) { tma.last_error = "pair-packed conv needs stride 2 and a dense 32-channel input"; return -7; }
+    p.in_stride_x = 1;           // TMA x dimension counts pixel pairs; SAME padding of a stride-2 conv on even sizes is 0 before
+  }
   p.n_steps = t.n_steps;
   p.steps = t.steps_dev;
   if (t.kind == TC_CONV && !t.transposed) { p.pad_t = pad_t; p.pad_l = pad_l; }
@@ -1048,6 +1083,12 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     }
     uint32_t box[4] = {TC_BK, (uint32_t)(p.bw * p.in_stride), (uint32_t)(p.bh * p.in_stride), 1};
     uint32_t es[4] = {1, (uint32_t)p.in_stride, (uint32_t)p.in_stride, 1};
+    if (t.kind == TC_PAIRX) {
+      // view [N][H][W/2][64]: dim 0 = one pixel pair (2 x 32 channels, 128 contiguous bytes)
+      dims[0] = 64; dims[1] = (uint64_t)(W / 2);
+      strides[0] = 128;
+      box[1] = (uint32_t)p.bw; es[1] = 1;
+    }
     if (!tma.encode_bf16(&m, (void*)((const bf16*)in + in_coff), 4, dims, strides, box, es)) return -3;
     if (cache.size() > 4096) cache.clear();
     it = cache.emplace(key, m).first;
