@@ -322,6 +322,10 @@ def main():
             calls = len(v) // 5
             key = name if name in work else ("res0.attention" if name == "attention" else None)
             fl, by = work.get(key, (0.0, 0.0))
+            if name == "attention+w":      # fused kernel: attention + output conv w + block tail; O never leaves the SM
+                fa, ba = work["res1.attention"]
+                fw, bw = work["res1.w"]
+                fl, by = fa + fw, ba + bw - 2 * 1024 * 128 * 2
             t_s = per_call * 1e-3
             tf = fl * mb / t_s / 1e12 if t_s > 0 else 0.0
             gb = by * mb / t_s / 1e9 if t_s > 0 else 0.0
@@ -334,6 +338,9 @@ def main():
         total_ms = sum(r["ms_per_forward"] for r in rows)
         top = rows[0]
         unit_work = work.get(top["layer"], work.get("res0.attention"))
+        if top["layer"] == "attention+w":
+            unit_work = (work["res1.attention"][0] + work["res1.w"][0],
+                         work["res1.attention"][1] + work["res1.w"][1] - 2 * 1024 * 128 * 2)
         traffic = None
         try:      # dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/)
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))

@@ -26,18 +26,35 @@ constexpr int AT_NK = AT_S / AT_BK;                   // 8 key tiles
 constexpr uint32_t AT_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 bf16] as two 16 KB k-blocks
 constexpr size_t kAttnTcSmem = 1024 + 7 * (size_t)AT_TILE + 192 + 1024;   // Q, K x2, V x2, P x2, barriers, exchange
 
+__device__ __forceinline__ void add_bf16x16_attn(const uint4& a, const uint4& b, float* v) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] += __low2float(t);
+    v[2 * i + 1] += __high2float(t);
+  }
+}
+
 constexpr int AT_THREADS = 320;      // warps 0-7 softmax / epilogue, warp 8 TMA, warp 9 TMEM alloc + MMA issue
 
+// fuse_w = 1: the NonLocalBlock output conv w (1x1, 128 -> 257, BN folded) and the ResBottleneck tail run here too:
+//   out = LeakyReLU(x_in + y + W_w . O + b)      (model.py:56-59, 105-113)
+// O (bf16) goes to shared memory as the A operand of one more GEMM (N = 144 + 128 accumulator columns reuse the S / O
+// TMEM columns, W_w lands in the Q/K buffers once the last S MMA has retired) and never reaches HBM.
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
                                                                      const __grid_constant__ CUtensorMap tmVT,
-                                                                     bf16* __restrict__ o, int* errflag) {
+                                                                     const __grid_constant__ CUtensorMap tmW,
+                                                                     bf16* __restrict__ o, const EpiParams e,
+                                                                     const int fuse_w, int* errflag) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = sQ + AT_TILE, sV = sK + 2 * AT_TILE, sP = sV + 2 * AT_TILE;
   const uint32_t bars = sP + 2 * AT_TILE;       // P is double-buffered: softmax(j+1) overlaps the PV MMA of tile j
   const uint32_t b_q = bars, b_kfull = bars + 8, b_kempty = bars + 24, b_vfull = bars + 40, b_vempty = bars + 56,
                  b_sfull = bars + 72, b_sempty = bars + 88, b_pfull = bars + 104, b_pempty = bars + 120,
-                 b_ofull = bars + 136, tmem_slot = bars + 144;
+                 b_ofull = bars + 136, b_wfull = bars + 144, b_a2full = bars + 152, b_d2full = bars + 160,
+                 tmem_slot = bars + 168;
   uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
   uint8_t* sP_gen = smem_al + (sP - base);
@@ -49,6 +66,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQK);
     prefetch_tmap(&tmVT);
+    if (fuse_w) prefetch_tmap(&tmW);
     mbar_init(b_q, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_kfull + 8 * s, 1);
@@ -63,6 +81,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       mbar_init(b_pempty + 8 * s, 1);
     }
     mbar_init(b_ofull, 1);
+    mbar_init(b_wfull, 1);
+    mbar_init(b_a2full, 8);
+    mbar_init(b_d2full, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -102,6 +123,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           mbar_expect_tx(b_vfull + 8 * vs, AT_TILE);
           tma_load_3d(sV + vs * AT_TILE, &tmVT, b_vfull + 8 * vs, j * AT_BK, 0, n);
           tma_load_3d(sV + vs * AT_TILE + AT_TILE / 2, &tmVT, b_vfull + 8 * vs, j * AT_BK + 64, 0, n);
+        }
+      }
+      __syncwarp();
+    }
+    if (fuse_w && ok) {
+      // W_w (288 rows x 128 K, bf16, 72 KB) replaces Q and the K stages once S_14 / S_15 have retired
+      ok = mbar_wait(b_kempty, (uint32_t)((AT_NK) & 1) ^ 1u, errflag, 22);
+      if (ok) ok = mbar_wait(b_kempty + 8, (uint32_t)((AT_NK) & 1) ^ 1u, errflag, 23);
+      if (ok && leader) {
+        mbar_expect_tx(b_wfull, 2 * 288 * 128);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(sQ + kb * (288 * 128), &tmW, b_wfull, kb * 64, 0);
+          tma_load_2d(sQ + kb * (288 * 128) + 144 * 128, &tmW, b_wfull, kb * 64, 144);
         }
       }
       __syncwarp();
@@ -156,6 +190,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     if (ok) ok = issue_pv(AT_NK - 1);
     if (leader) umma_commit(b_ofull);
     __syncwarp();
+    if (fuse_w && ok) {
+      ok = mbar_wait(b_wfull, 0, errflag, 24, true);
+      if (ok) ok = mbar_wait(b_a2full, 0, errflag, 25, true);      // O (bf16) is in sP[0]; S / O TMEM columns are drained
+      tc_fence_after();
+      if (ok && leader) {
+        const uint32_t id144 = umma_idesc_bf16(128, 144), id128 = umma_idesc_bf16(128, 128);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint32_t a_lo = umma_desc_lo(sP + kb * (AT_TILE / 2));
+          const uint32_t b_lo = umma_desc_lo(sQ + kb * (288 * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_lo(tmem, a_lo + 2 * k, b_lo + 2 * k, id144, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_lo(tmem + 144, a_lo + 2 * k, b_lo + (144 * 8) + 2 * k, id128, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(b_d2full);
+      }
+      __syncwarp();
+    }
   } else {
     // ================= softmax / epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int q = warp & 3, h = warp >> 2;
@@ -164,6 +218,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const float kLog2e = 1.4426950408889634f;
     float mx = -INFINITY;
     bool ok = true;
+    if (fuse_w) {
+      // the residual rows (x_in, y) of this thread are needed ~15 us from now: pull them from HBM into L2 already
+      const size_t pixp = (size_t)n * AT_S + q0 + row;
+      const char* r1p = (const char*)((const bf16*)e.res1 + pixp * e.res1_ld + h * 144);
+      const char* r2p = (const char*)((const bf16*)e.res2 + pixp * e.res2_ld + h * 144);
+#pragma unroll
+      for (int b = 0; b < 288; b += 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1p + b));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r2p + b));
+      }
+    }
     // ---- pass 1: exact row max (each warp over its 64 columns, combined through smem at the end)
     for (int it = 0; it < AT_NK && ok; ++it) {
       const int s = it & 1, f = it >> 1;
@@ -231,7 +296,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     // ---- epilogue: O / sum -> bf16 (each warp its 64 output channels)
     if (ok) ok = mbar_wait(b_ofull, 0, errflag, 21);
     tc_fence_after();
-    if (ok) {
+    if (ok && !fuse_w) {
       const float inv = 1.f / sum;
       bf16* dst = o + ((size_t)n * AT_S + q0 + row) * AT_D + h * 64;
 #pragma unroll
@@ -249,6 +314,97 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         }
       }
     }
+    if (ok && fuse_w) {
+      // O / sum -> bf16 A operand in sP[0] (same swizzled K-major layout as P: this warp's 64 channels = k-block h)
+      const float inv = 1.f / sum;
+      uint8_t* blk = sP_gen + h * (AT_TILE / 2) + row * 128;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld32(tO + lane_addr + (uint32_t)(h * 64 + c), v);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = (c >> 3) + g;
+          uint4 w;
+          w.x = pack_bf16x2(v[8 * g + 0] * inv, v[8 * g + 1] * inv);
+          w.y = pack_bf16x2(v[8 * g + 2] * inv, v[8 * g + 3] * inv);
+          w.z = pack_bf16x2(v[8 * g + 4] * inv, v[8 * g + 5] * inv);
+          w.w = pack_bf16x2(v[8 * g + 6] * inv, v[8 * g + 7] * inv);
+          *reinterpret_cast<uint4*>(blk + ((ch ^ (row & 7)) << 4)) = w;
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_a2full);
+      // second GEMM's epilogue: warp half h owns accumulator columns [h*144, h*144 + (h ? 128 : 144))
+      const size_t pix = (size_t)n * AT_S + q0 + row;
+      const int c_begin = h * 144, c_end = h ? 272 : 144;
+      const bf16* r1 = (const bf16*)e.res1 + pix * e.res1_ld;
+      const bf16* r2 = (const bf16*)e.res2 + pix * e.res2_ld;
+      bf16* dst = (bf16*)e.out + pix * e.out_ld + e.out_coff;
+      // first two chunks of the residuals are requested before the accumulator wait
+      uint4 pa[2][2], pb[2][2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint4* s1 = reinterpret_cast<const uint4*>(r1 + c_begin + 16 * k);
+        const uint4* s2 = reinterpret_cast<const uint4*>(r2 + c_begin + 16 * k);
+        pa[k][0] = s1[0]; pa[k][1] = s1[1];
+        pb[k][0] = s2[0]; pb[k][1] = s2[1];
+      }
+      ok = mbar_wait(b_d2full, 0, errflag, 26);
+      tc_fence_after();
+      if (ok) {
+        auto finish = [&](const int c, float* v) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          uint4* d = reinterpret_cast<uint4*>(dst + c);
+          d[0] = o0;
+          d[1] = o1;
+        };
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = c_begin + 16 * k;
+          float v[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)c, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);
+          add_bf16x16_attn(pa[k][0], pa[k][1], v);
+          add_bf16x16_attn(pb[k][0], pb[k][1], v);
+          finish(c, v);
+        }
+#pragma unroll 1
+        for (int c = c_begin + 32; c < c_end; c += 32) {
+          // two chunks per iteration: all four residual loads are in flight before the first use
+          const bool two = c + 16 < c_end;
+          const uint4* s1 = reinterpret_cast<const uint4*>(r1 + c);
+          const uint4* s2 = reinterpret_cast<const uint4*>(r2 + c);
+          const uint4 a0 = s1[0], a1 = s1[1], b0 = s2[0], b1 = s2[1];
+          uint4 a2 = a0, a3 = a1, b2 = b0, b3 = b1;
+          if (two) { a2 = s1[2]; a3 = s1[3]; b2 = s2[2]; b3 = s2[3]; }
+          float v[16];
+          tmem_ld16(tmem + lane_addr + (uint32_t)c, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);
+          add_bf16x16_attn(a0, a1, v);
+          add_bf16x16_attn(b0, b1, v);
+          finish(c, v);
+          if (two) {
+            tmem_ld16(tmem + lane_addr + (uint32_t)(c + 16), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + 16 + i);
+            add_bf16x16_attn(a2, a3, v);
+            add_bf16x16_attn(b2, b3, v);
+            finish(c + 16, v);
+          }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -259,8 +415,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   }
 }
 
+// w_map != nullptr: fused output conv (see kernel comment); `e` then carries bias / residuals / output of the block.
 inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, bf16* o, int n, int* errflag,
-                               cudaStream_t st) {
+                               cudaStream_t st, const CUtensorMap* w_map = nullptr, const EpiParams* e = nullptr) {
   static thread_local std::map<std::tuple<const void*, const void*, int>, std::pair<CUtensorMap, CUtensorMap>> cache;
   auto key = std::make_tuple((const void*)qk, (const void*)vt, n);
   auto it = cache.find(key);
@@ -286,7 +443,12 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, attention_tc_kernel, it->second.first, it->second.second, o, errflag);
+  EpiParams ep;
+  memset(&ep, 0, sizeof ep);
+  if (e) ep = *e;
+  const int fuse = (w_map != nullptr && e != nullptr) ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, attention_tc_kernel, it->second.first, it->second.second,
+                                      fuse ? *w_map : it->second.first, o, ep, fuse, errflag);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
   return 0;
 }

@@ -239,8 +239,8 @@ EpiParams epi(void* out, int out_ld, int out_coff, int out_c, int act, int mode 
   return e;
 }
 
-int run_attention(bsr_handle* h, cudaStream_t st, int n) {
-  Step step(h, st, "attention");
+int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullptr, const EpiParams* ew = nullptr) {
+  Step step(h, st, wl ? "attention+w" : "attention");
   if (h->precision == BSR_PRECISION_FP32CHECK) {
     attention_simple_kernel<float><<<dim3(AS_S / AS_Q, n), 256, kAttnSimpleSmem, st>>>(
         (const float*)h->QK, (const float*)h->VT, (float*)h->O, 128);
@@ -248,7 +248,10 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n) {
     return BSR_OK;
   }
   if (!h->force_direct) {
-    int rc = launch_attention_tc(h->tma, (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, n, h->errflag, st);
+    EpiParams e2;
+    if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
+    int rc = launch_attention_tc(h->tma, (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, n, h->errflag, st,
+                                 wl ? &wl->tc.map : nullptr, wl ? &e2 : nullptr);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
     h->launches++;
     return BSR_OK;
@@ -281,7 +284,6 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   eq.spatial = FEAT * FEAT;
   ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq, no_extra()};
   if ((rc = run_conv(h, st, c4, n))) return rc;
-  if ((rc = run_attention(h, st, n))) return rc;
   int oc = ld < ldy ? ld : ldy;
   EpiParams ew = epi(nxt, ld, 0, oc, 1);
   // residual widths are the PADDED widths: padding channels of Y / cur are kept at zero, so adding them is exact
@@ -289,8 +291,17 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   ew.res1 = h->Y; ew.res1_ld = ldy; ew.res1_c = ldy;
   ew.res2 = cur; ew.res2_ld = ld; ew.res2_c = ld;
   (void)c_cur;
-  ConvCall c5{nm[4], h->O, 128, 0, false, FEAT, FEAT, 1, ew, no_extra()};
-  if ((rc = run_conv(h, st, c5, n))) return rc;
+  // NonLocal output conv + block tail: fused into the attention kernel on the tensor-core path
+  const Layer& wl = h->layers[nm[4]];
+  const bool fuse_w = h->precision == BSR_PRECISION_BF16 && !h->force_direct && wl.tc.ready && wl.tc.kind == TC_CONV &&
+                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !getenv("BSR_NO_FUSE_W");
+  if (fuse_w) {
+    if ((rc = run_attention(h, st, n, &wl, &ew))) return rc;
+  } else {
+    if ((rc = run_attention(h, st, n))) return rc;
+    ConvCall c5{nm[4], h->O, 128, 0, false, FEAT, FEAT, 1, ew, no_extra()};
+    if ((rc = run_conv(h, st, c5, n))) return rc;
+  }
   if (ld > oc) {
     Step step(h, st, "res_tail");
     long long npix = (long long)n * FEAT * FEAT, tot = npix * (ld - oc);
