@@ -30,7 +30,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--micro-batch", type=int, default=128)
     ap.add_argument("--variant", default="gsc", choices=["gsc", "tsm"])
     ap.add_argument("--frame", type=int, default=2)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32check"])
@@ -186,6 +186,7 @@ def workload_config(args):
                         "random-init weights seed 1234" % (args.variant.upper(), args.batch, args.micro_batch),
             "variant": args.variant, "images_per_gpu_per_step": args.batch, "micro_batch": args.micro_batch,
             "frame": args.frame if args.variant == "tsm" else None,
+            "host_path_chunk": 64,
             "cache": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" %
                      (args.batch * 256 * 256 * 6 * 4 / 1e6)}
 

@@ -516,11 +516,16 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
   if (n <= 0) return fail(h, BSR_EINVAL, "n must be > 0");
   if (!h->loaded) return fail(h, BSR_ESTATE, "bsr_load_weights has not been called");
   CK(h, cudaSetDevice(h->device));
-  int step = h->mb;
+  // transfer/compute chunk of the pipelined host path: smaller than the device micro-batch so that PCIe copies and
+  // kernels of neighbouring chunks overlap well (measured optimum ~64 images; BSR_HOST_CHUNK overrides)
+  int host_chunk = 64;
+  if (const char* hc = getenv("BSR_HOST_CHUNK")) host_chunk = atoi(hc) > 0 ? atoi(hc) : host_chunk;
+  int step = h->mb < host_chunk ? h->mb : host_chunk;
   if (reg) {
     if (frame <= 0 || n % frame) return fail(h, BSR_EINVAL, "TSM needs n %% frame == 0");
     if (frame > h->mb) return fail(h, BSR_EINVAL, "frame %d exceeds micro_batch %d", frame, h->mb);
-    step = h->mb / frame * frame;
+    if (step < frame) step = frame;
+    step = step / frame * frame;
   }
   const size_t p1 = (size_t)IMG * IMG * sizeof(float);           // one single-channel image plane
   const size_t in_slot = (size_t)step * p1 * (3 + 3 + (reg ? 6 : 0));

@@ -76,7 +76,7 @@ class Generator:
     precision 'bf16' (tcgen05 product path) or 'fp32check' (CUDA-core check mode)
     """
 
-    def __init__(self, variant: str = "gsc", precision: str = "bf16", device: int = 0, micro_batch: int = 64,
+    def __init__(self, variant: str = "gsc", precision: str = "bf16", device: int = 0, micro_batch: int = 128,
                  weights: Optional[Dict[str, np.ndarray]] = None, seed: Optional[int] = None):
         if variant not in VARIANTS:
             raise ValueError("variant must be one of %r" % (VARIANTS,))
