@@ -36,6 +36,11 @@ __device__ __forceinline__ void add_bf16x16_attn(const uint4& a, const uint4& b,
   }
 }
 
+#ifdef BSR_ROLE_TIMERS
+#define AT_CLK() clock64()
+#else
+#define AT_CLK() 0ll
+#endif
 constexpr int AT_THREADS = 320;      // warps 0-7 softmax / epilogue, warp 8 TMA, warp 9 TMEM alloc + MMA issue
 
 // fuse_w = 1: the NonLocalBlock output conv w (1x1, 128 -> 257, BN folded) and the ResBottleneck tail run here too:
@@ -46,7 +51,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap tmVT,
                                                                      const __grid_constant__ CUtensorMap tmW,
                                                                      bf16* __restrict__ o, const EpiParams e,
-                                                                     const int fuse_w, int* errflag) {
+                                                                     const int fuse_w, int* errflag,
+                                                                     long long* timers) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = sQ + AT_TILE, sV = sK + 2 * AT_TILE, sP = sV + 2 * AT_TILE;
@@ -144,12 +150,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     // ================= MMA issuer (converged warp, elected lane issues) =================
     const bool leader = elect_one();
     const uint32_t idesc = umma_idesc_bf16(128, 128);
+    long long t_k = 0, t_se = 0, t_p = 0, t_v = 0, t_w = 0;
+    const long long t0m = AT_CLK();
     bool ok = mbar_wait(b_q, 0, errflag, 13, true);
     auto issue_pv = [&](int j) -> bool {
       const int vs = j & 1, vf = j >> 1;
       const int ps = j & 1, pf = j >> 1;
+      const long long c0 = AT_CLK();
       if (!mbar_wait(b_pfull + 8 * ps, (uint32_t)(pf & 1), errflag, 14, true)) return false;
+      const long long c1 = AT_CLK();
       if (!mbar_wait(b_vfull + 8 * vs, (uint32_t)(vf & 1), errflag, 15, true)) return false;
+      t_p += c1 - c0; t_v += AT_CLK() - c1;
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -167,10 +178,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     };
     for (int it = 0; it < 2 * AT_NK && ok; ++it) {
       const int s = it & 1, f = it >> 1;
+      const long long c0 = AT_CLK();
       ok = mbar_wait(b_kfull + 8 * s, (uint32_t)(f & 1), errflag, 16, true);
       if (!ok) break;
+      const long long c1 = AT_CLK();
       ok = mbar_wait(b_sempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 17, true);
       if (!ok) break;
+      t_k += c1 - c0; t_se += AT_CLK() - c1;
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -190,9 +204,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     if (ok) ok = issue_pv(AT_NK - 1);
     if (leader) umma_commit(b_ofull);
     __syncwarp();
+    const long long t1m = AT_CLK();
     if (fuse_w && ok) {
       ok = mbar_wait(b_wfull, 0, errflag, 24, true);
       if (ok) ok = mbar_wait(b_a2full, 0, errflag, 25, true);      // O (bf16) is in sP[0]; S / O TMEM columns are drained
+      t_w = AT_CLK() - t1m;
       tc_fence_after();
       if (ok && leader) {
         const uint32_t id144 = umma_idesc_bf16(128, 144), id128 = umma_idesc_bf16(128, 128);
@@ -210,6 +226,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       }
       __syncwarp();
     }
+#ifdef BSR_ROLE_TIMERS
+    if (leader && blockIdx.x == 0 && blockIdx.y == 0 && timers) {
+      timers[0] = AT_CLK() - t0m; timers[1] = t_k; timers[2] = t_se; timers[3] = t_p; timers[4] = t_v; timers[5] = t_w;
+      timers[6] = t1m - t0m;
+    }
+#endif
   } else {
     // ================= softmax / epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int q = warp & 3, h = warp >> 2;
@@ -218,6 +240,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const float kLog2e = 1.4426950408889634f;
     float mx = -INFINITY;
     bool ok = true;
+    long long u_s1 = 0, u_s2 = 0, u_pe = 0;
+    const long long t0s = AT_CLK();
     if (fuse_w) {
       // the residual rows (x_in, y) of this thread are needed ~15 us from now: pull them from HBM into L2 already
       const size_t pixp = (size_t)n * AT_S + q0 + row;
@@ -232,7 +256,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     // ---- pass 1: exact row max (each warp over its 64 columns, combined through smem at the end)
     for (int it = 0; it < AT_NK && ok; ++it) {
       const int s = it & 1, f = it >> 1;
+      const long long c0 = AT_CLK();
       ok = mbar_wait(b_sfull + 8 * s, (uint32_t)(f & 1), errflag, 18);
+      u_s1 += AT_CLK() - c0;
       if (!ok) break;
       tc_fence_after();
 #pragma unroll
@@ -255,11 +281,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     float sum = 0.f;
     for (int j = 0; j < AT_NK && ok; ++j) {
       const int it = AT_NK + j, s = it & 1, f = it >> 1;
+      const long long c0 = AT_CLK();
       ok = mbar_wait(b_sfull + 8 * s, (uint32_t)(f & 1), errflag, 19);
       if (!ok) break;
+      const long long c1 = AT_CLK();
       const int ps = j & 1, pf = j >> 1;
       ok = mbar_wait(b_pempty + 8 * ps, (uint32_t)(pf & 1) ^ 1u, errflag, 20);
       if (!ok) break;
+      u_s2 += c1 - c0; u_pe += AT_CLK() - c1;
       tc_fence_after();
       uint8_t* blk = sP_gen + ps * AT_TILE + h * (AT_TILE / 2) + row * 128;        // keys h*64 .. +63 = k-block h
 #pragma unroll
@@ -291,10 +320,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       }
     }
     xch[h * 128 + row] = sum;
+    // the K stage buffers are retired (S_15 was consumed above): stage the output conv's bias in shared memory
+    float* bias_s = reinterpret_cast<float*>(smem_al + (sK + AT_TILE + 16384 - base));
+    if (fuse_w)
+      for (int i = threadIdx.x; i < 288; i += 256) bias_s[i] = __ldg(e.bias + i);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     sum = xch[row] + xch[128 + row];
     // ---- epilogue: O / sum -> bf16 (each warp its 64 output channels)
+    const long long t1s = AT_CLK();
     if (ok) ok = mbar_wait(b_ofull, 0, errflag, 21);
+    const long long t2s = AT_CLK();
     tc_fence_after();
     if (ok && !fuse_w) {
       const float inv = 1.f / sum;
@@ -343,66 +378,64 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       const bf16* r1 = (const bf16*)e.res1 + pix * e.res1_ld;
       const bf16* r2 = (const bf16*)e.res2 + pix * e.res2_ld;
       bf16* dst = (bf16*)e.out + pix * e.out_ld + e.out_coff;
-      // first two chunks of the residuals are requested before the accumulator wait
-      uint4 pa[2][2], pb[2][2];
+      // residual operands are fetched in batches of four 16-channel chunks (16 independent 16-byte loads in flight per
+      // thread); the first batch is requested before the accumulator wait
+      uint4 pa[4][2], pb[4][2];
+      auto load_batch = [&](const int cb) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const uint4* s1 = reinterpret_cast<const uint4*>(r1 + c_begin + 16 * k);
-        const uint4* s2 = reinterpret_cast<const uint4*>(r2 + c_begin + 16 * k);
-        pa[k][0] = s1[0]; pa[k][1] = s1[1];
-        pb[k][0] = s2[0]; pb[k][1] = s2[1];
-      }
-      ok = mbar_wait(b_d2full, 0, errflag, 26);
-      tc_fence_after();
-      if (ok) {
-        auto finish = [&](const int c, float* v) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-          uint4* d = reinterpret_cast<uint4*>(dst + c);
-          d[0] = o0;
-          d[1] = o1;
-        };
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int c = c_begin + 16 * k;
-          float v[16];
-          tmem_ld16(tmem + lane_addr + (uint32_t)c, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);
-          add_bf16x16_attn(pa[k][0], pa[k][1], v);
-          add_bf16x16_attn(pb[k][0], pb[k][1], v);
-          finish(c, v);
-        }
-#pragma unroll 1
-        for (int c = c_begin + 32; c < c_end; c += 32) {
-          // two chunks per iteration: all four residual loads are in flight before the first use
-          const bool two = c + 16 < c_end;
-          const uint4* s1 = reinterpret_cast<const uint4*>(r1 + c);
-          const uint4* s2 = reinterpret_cast<const uint4*>(r2 + c);
-          const uint4 a0 = s1[0], a1 = s1[1], b0 = s2[0], b1 = s2[1];
-          uint4 a2 = a0, a3 = a1, b2 = b0, b3 = b1;
-          if (two) { a2 = s1[2]; a3 = s1[3]; b2 = s2[2]; b3 = s2[3]; }
-          float v[16];
-          tmem_ld16(tmem + lane_addr + (uint32_t)c, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + i);
-          add_bf16x16_attn(a0, a1, v);
-          add_bf16x16_attn(b0, b1, v);
-          finish(c, v);
-          if (two) {
-            tmem_ld16(tmem + lane_addr + (uint32_t)(c + 16), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + c + 16 + i);
-            add_bf16x16_attn(a2, a3, v);
-            add_bf16x16_attn(b2, b3, v);
-            finish(c + 16, v);
+        for (int k = 0; k < 4; ++k) {
+          if (cb + 16 * k < c_end) {
+            const uint4* s1 = reinterpret_cast<const uint4*>(r1 + cb + 16 * k);
+            const uint4* s2 = reinterpret_cast<const uint4*>(r2 + cb + 16 * k);
+            pa[k][0] = s1[0]; pa[k][1] = s1[1];
+            pb[k][0] = s2[0]; pb[k][1] = s2[1];
           }
         }
+      };
+      load_batch(c_begin);
+      const long long t3s = AT_CLK();
+      ok = mbar_wait(b_d2full, 0, errflag, 26);
+      const long long t4s = AT_CLK();
+#ifdef BSR_ROLE_TIMERS
+      if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && timers) {
+        timers[8] = t1s - t0s; timers[9] = u_s1; timers[10] = u_s2; timers[11] = u_pe; timers[12] = t2s - t1s;
+        timers[13] = t3s - t2s; timers[14] = t4s - t3s;
+      }
+#endif
+      tc_fence_after();
+      if (ok) {
+#pragma unroll 1
+        for (int cb = c_begin; cb < c_end; cb += 64) {
+          if (cb != c_begin) load_batch(cb);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = cb + 16 * k;
+            if (c < c_end) {
+              float v[16];
+              tmem_ld16(tmem + lane_addr + (uint32_t)c, v);
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+              add_bf16x16_attn(pa[k][0], pa[k][1], v);
+              add_bf16x16_attn(pb[k][0], pb[k][1], v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+              o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+              o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+              o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+              uint4* d = reinterpret_cast<uint4*>(dst + c);
+              d[0] = o0;
+              d[1] = o1;
+            }
+          }
+        }
+#ifdef BSR_ROLE_TIMERS
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && timers) timers[15] = AT_CLK() - t4s;
+#endif
       }
     }
   }
@@ -417,7 +450,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 
 // w_map != nullptr: fused output conv (see kernel comment); `e` then carries bias / residuals / output of the block.
 inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, bf16* o, int n, int* errflag,
-                               cudaStream_t st, const CUtensorMap* w_map = nullptr, const EpiParams* e = nullptr) {
+                               cudaStream_t st, const CUtensorMap* w_map = nullptr, const EpiParams* e = nullptr,
+                               int launch_index = 0) {
   static thread_local std::map<std::tuple<const void*, const void*, int>, std::pair<CUtensorMap, CUtensorMap>> cache;
   auto key = std::make_tuple((const void*)qk, (const void*)vt, n);
   auto it = cache.find(key);
@@ -448,7 +482,8 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
   if (e) ep = *e;
   const int fuse = (w_map != nullptr && e != nullptr) ? 1 : 0;
   cudaError_t le = cudaLaunchKernelEx(&cfg, attention_tc_kernel, it->second.first, it->second.second,
-                                      fuse ? *w_map : it->second.first, o, ep, fuse, errflag);
+                                      fuse ? *w_map : it->second.first, o, ep, fuse, errflag,
+                                      reinterpret_cast<long long*>(errflag) + 16 + 16 * (launch_index & 63));
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
   return 0;
 }

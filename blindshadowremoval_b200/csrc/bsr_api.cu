@@ -251,7 +251,7 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
     EpiParams e2;
     if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
     int rc = launch_attention_tc(h->tma, (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, n, h->errflag, st,
-                                 wl ? &wl->tc.map : nullptr, wl ? &e2 : nullptr);
+                                 wl ? &wl->tc.map : nullptr, wl ? &e2 : nullptr, h->launches);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
     h->launches++;
     return BSR_OK;

@@ -20,11 +20,16 @@ for _ in range(3):
     gen(img, uv, None, want=("con_rgb", "dif"))
 torch.cuda.synchronize()
 t = gen.debug_read("timers").reshape(64, 16)
-names = {1: "conv1", 2: "down1", 3: "down2", 4: "down3", 7: "r0.c1", 8: "r0.c2", 9: "r0.c3", 10: "r0.qkv", 12: "r0.w",
+ATT = {11, 16, 21, 31, 36, 41}
+names = {11: "attn+w", 1: "conv1", 2: "down1", 3: "down2", 4: "down3", 7: "r0.c1", 8: "r0.c2", 9: "r0.c3", 10: "r0.qkv", 12: "r0.w",
          25: "up1", 26: "up2", 27: "up3", 28: "heads", 52: "clr_up2", 53: "clr_up3", 54: "clr_conv1"}
 print("launch  name       | producer: total wait_empty dep_wait steps | mma: total wait_full wait_tempty wait_res tiles | epi: total wait_tfull tiles")
 for i in range(64):
     if t[i, 0] == 0 and t[i, 4] == 0:
+        continue
+    if i in ATT:
+        print("%3d attn+w | mma: total %d (main %d) wait k %d s_empty %d p_full %d v_full %d w+a2 %d | softmax: passes %d wait s(p1) %d s(p2) %d p_empty %d o_full %d | O->smem %d d2 wait %d epilogue2 %d" % (
+            i, t[i, 0], t[i, 6], t[i, 1], t[i, 2], t[i, 3], t[i, 4], t[i, 5], t[i, 8], t[i, 9], t[i, 10], t[i, 11], t[i, 12], t[i, 13], t[i, 14], t[i, 15]))
         continue
     print("%3d %-10s | %9d %9d %8d %5d | %9d %9d %9d %8d %4d | %9d %9d %4d" % (
         i, names.get(i, ""), t[i, 0], t[i, 1], t[i, 2], t[i, 3], t[i, 4], t[i, 5], t[i, 6], t[i, 7], t[i, 8], t[i, 9],
