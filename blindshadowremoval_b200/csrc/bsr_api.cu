@@ -71,6 +71,7 @@ struct bsr_handle {
   size_t ev_used = 0;
   std::vector<std::pair<const char*, float>> times;
   // host-path staging
+  bool in_small = false;   // compact host path: uv/reg arrive already resized to 32x32
   void* stage = nullptr;
   size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
@@ -363,11 +364,16 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
   {
     Step step(h, st, "uv_small");
     int tot = n * FEAT * FEAT * 3;
-    uv_small_kernel<<<(tot + 255) / 256, 256, 0, st>>>(uv, h->UVS, n);
-    h->launches++;
+    if (h->in_small) {
+      CK(h, cudaMemcpyAsync(h->UVS, uv, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      uv_small_kernel<<<(tot + 255) / 256, 256, 0, st>>>(uv, h->UVS, n);
+      h->launches++;
+    }
     if (tsm) {
       int tot4 = n * FEAT * FEAT * 4;
-      reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
+      if (h->in_small) reg32_off_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
+      else reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
       h->launches++;
     }
   }
@@ -494,13 +500,15 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
   for (int i0 = 0; i0 < n; i0 += step) {
     int m = n - i0 < step ? n - i0 : step;
     const size_t o3 = (size_t)i0 * IMG * IMG * 3, o1 = (size_t)i0 * IMG * IMG;
+    const size_t aux_px = h->in_small ? (size_t)i0 * FEAT * FEAT : o1;      // uv/reg pixels per image
     int rc;
-    const float* regp = reg ? reg + (size_t)i0 * IMG * IMG * 6 : nullptr;
+    const float* uvp = uv + aux_px * 3;
+    const float* regp = reg ? reg + aux_px * 6 : nullptr;
     if (h->precision == BSR_PRECISION_FP32CHECK)
-      rc = forward_mb<float>(h, st, img + o3, uv + o3, regp, m, frame, share, gs ? gs + o1 : nullptr,
+      rc = forward_mb<float>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
                              rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
     else
-      rc = forward_mb<bf16>(h, st, img + o3, uv + o3, regp, m, frame, share, gs ? gs + o1 : nullptr,
+      rc = forward_mb<bf16>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
                             rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
     if (rc) return rc;
   }
@@ -510,15 +518,36 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
 
 // Host-buffer path: micro-batches are pipelined over three streams (H2D | compute | D2H) with two staging
 // slots, so PCIe transfers in both directions overlap the kernels of the neighbouring micro-batches.
+//
+// Compact mode (img_u8 != NULL): the image arrives as uint8 and is expanded on the compute
+// stream, uv/reg arrive at 32x32, and rgb/dif can leave as uint8 / binary16 (converted on the compute stream).
+struct HostCompact {
+  const unsigned char* img_u8 = nullptr;
+  unsigned char* rgb_u8 = nullptr;
+  unsigned short* dif_f16 = nullptr;
+};
+struct SmallInputScope {      // forward_mb reads uv/reg as 32x32 maps only while a compact call is in flight
+  bsr_handle* h;
+  SmallInputScope(bsr_handle* hh, bool on) : h(hh) { h->in_small = on; }
+  ~SmallInputScope() { h->in_small = false; }
+};
+
 int forward_host(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
-                 float* gs, float* rgb, float* mask22, float* dif) {
+                 float* gs, float* rgb, float* mask22, float* dif, HostCompact cp = HostCompact()) {
   if (!h) return BSR_EINVAL;
   if (n <= 0) return fail(h, BSR_EINVAL, "n must be > 0");
   if (!h->loaded) return fail(h, BSR_ESTATE, "bsr_load_weights has not been called");
+  const bool compact = cp.img_u8 != nullptr;
+  if ((!compact && !img) || !uv) return fail(h, BSR_EINVAL, "img/uv must be non-NULL");
+  if (!compact && (cp.rgb_u8 || cp.dif_f16)) return fail(h, BSR_EINVAL, "compact outputs need the compact entry point");
+  if (h->variant == BSR_VARIANT_TSM && !reg) return fail(h, BSR_EINVAL, "TSM needs reg");
+  SmallInputScope small_scope(h, compact);
   CK(h, cudaSetDevice(h->device));
   // transfer/compute chunk of the pipelined host path: smaller than the device micro-batch so that PCIe copies and
   // kernels of neighbouring chunks overlap well (measured optimum ~64 images; BSR_HOST_CHUNK overrides)
-  int host_chunk = 64;
+  // measured: fp32 I/O, 256 images/call: 64 -> 17.2k img/s, 128 -> 13.8k; 1024 images/call: 64 -> 18.7k, 128 -> 19.4k;
+  // compact I/O (transfers 5x smaller, head/tail cheap): 256/call: 64 -> 17.9k, 128 -> 18.6k; 1024/call: 128 -> 19.9k
+  int host_chunk = (compact || n >= 512) ? 128 : 64;
   if (const char* hc = getenv("BSR_HOST_CHUNK")) host_chunk = atoi(hc) > 0 ? atoi(hc) : host_chunk;
   int step = h->mb < host_chunk ? h->mb : host_chunk;
   if (reg) {
@@ -530,7 +559,11 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
   const size_t p1 = (size_t)IMG * IMG * sizeof(float);           // one single-channel image plane
   const size_t in_slot = (size_t)step * p1 * (3 + 3 + (reg ? 6 : 0));
   const size_t out_slot = (size_t)step * p1 * (1 + 3 + 3 + 1);
-  const size_t need = 2 * (in_slot + out_slot);
+  const size_t px = (size_t)IMG * IMG, px32 = (size_t)FEAT * FEAT;
+  // compact slots: [img_u8 | uv32 | reg32] in, [rgb_u8 | dif_f16] out (the fp32 slots stay as device-side scratch)
+  const size_t cin_slot = compact ? (size_t)step * (px * 3 + px32 * 3 * sizeof(float) + px32 * 6 * sizeof(float)) : 0;
+  const size_t cout_slot = compact ? (size_t)step * (px * 3 + px * 2) : 0;
+  const size_t need = 2 * (in_slot + out_slot + cin_slot + cout_slot);
   if (need > h->stage_bytes) {
     if (h->stage) cudaFree(h->stage);
     h->stage = nullptr;
@@ -578,25 +611,58 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
     float* d_m22 = (float*)(sout + (size_t)step * p1 * 4);
     float* d_dif = (float*)(sout + (size_t)step * p1 * 7);
     const size_t o1 = (size_t)i0 * IMG * IMG, pm = (size_t)m * p1;
+    char* cbase = (char*)h->stage + 2 * (in_slot + out_slot);
+    unsigned char* c_img = (unsigned char*)(cbase + slot * cin_slot);
+    float* c_uv = (float*)(c_img + (size_t)step * px * 3);
+    float* c_reg = c_uv + (size_t)step * px32 * 3;
+    unsigned char* c_rgb = (unsigned char*)(cbase + 2 * cin_slot + slot * cout_slot);
+    unsigned short* c_dif = (unsigned short*)(c_rgb + (size_t)step * px * 3);
     // the input slot is free once the compute that read it (two micro-batches ago) has finished
     if (k >= 2) CK(h, cudaStreamWaitEvent(s_in, h->ev_comp[slot], 0));
-    CK(h, cudaMemcpyAsync(d_img, img + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
-    CK(h, cudaMemcpyAsync(d_uv, uv + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
-    if (reg) CK(h, cudaMemcpyAsync(d_reg, reg + o1 * 6, pm * 6, cudaMemcpyHostToDevice, s_in));
+    if (compact) {
+      const size_t q1 = (size_t)i0 * px32, qm = (size_t)m * px32 * sizeof(float);
+      CK(h, cudaMemcpyAsync(c_img, cp.img_u8 + o1 * 3, (size_t)m * px * 3, cudaMemcpyHostToDevice, s_in));
+      CK(h, cudaMemcpyAsync(c_uv, uv + q1 * 3, qm * 3, cudaMemcpyHostToDevice, s_in));
+      if (reg) CK(h, cudaMemcpyAsync(c_reg, reg + q1 * 6, qm * 6, cudaMemcpyHostToDevice, s_in));
+    } else {
+      CK(h, cudaMemcpyAsync(d_img, img + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
+      CK(h, cudaMemcpyAsync(d_uv, uv + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
+      if (reg) CK(h, cudaMemcpyAsync(d_reg, reg + o1 * 6, pm * 6, cudaMemcpyHostToDevice, s_in));
+    }
     CK(h, cudaEventRecord(h->ev_in[slot], s_in));
     CK(h, cudaStreamWaitEvent(s_c, h->ev_in[slot], 0));
     // the output slot is free once its previous D2H (two micro-batches ago) has finished
     if (k >= 2) CK(h, cudaStreamWaitEvent(s_c, h->ev_out[slot], 0));
-    int rc = forward_common(h, d_img, d_uv, d_reg, m, frame, share, gs ? d_gs : nullptr, rgb ? d_rgb : nullptr,
-                            mask22 ? d_m22 : nullptr, dif ? d_dif : nullptr, s_c);
+    int extra_launches = 0;
+    if (compact) {
+      const long long n16 = (long long)m * px * 3 / 16;
+      expand_u8_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, s_c>>>((const uint4*)c_img, (float4*)d_img, n16);
+      ++extra_launches;
+    }
+    const bool want_rgb = rgb || cp.rgb_u8, want_dif = dif || cp.dif_f16;
+    int rc = forward_common(h, d_img, compact ? c_uv : d_uv, reg ? (compact ? c_reg : d_reg) : nullptr, m, frame, share,
+                            gs ? d_gs : nullptr, want_rgb ? d_rgb : nullptr, mask22 ? d_m22 : nullptr,
+                            want_dif ? d_dif : nullptr, s_c);
     if (rc) return rc;
-    total_launches += h->launches;
+    if (cp.rgb_u8) {
+      const long long n16 = (long long)m * px * 3 / 16;
+      rgb_to_u8_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, s_c>>>((const float4*)d_rgb, (uint4*)c_rgb, n16);
+      ++extra_launches;
+    }
+    if (cp.dif_f16) {
+      const long long n8 = (long long)m * px / 8;
+      f32_to_f16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s_c>>>((const float4*)d_dif, (uint4*)c_dif, n8);
+      ++extra_launches;
+    }
+    total_launches += h->launches + extra_launches;
     CK(h, cudaEventRecord(h->ev_comp[slot], s_c));
     CK(h, cudaStreamWaitEvent(s_out, h->ev_comp[slot], 0));
     if (gs) CK(h, cudaMemcpyAsync(gs + o1, d_gs, pm, cudaMemcpyDeviceToHost, s_out));
     if (rgb) CK(h, cudaMemcpyAsync(rgb + o1 * 3, d_rgb, pm * 3, cudaMemcpyDeviceToHost, s_out));
     if (mask22) CK(h, cudaMemcpyAsync(mask22 + o1 * 3, d_m22, pm * 3, cudaMemcpyDeviceToHost, s_out));
     if (dif) CK(h, cudaMemcpyAsync(dif + o1, d_dif, pm, cudaMemcpyDeviceToHost, s_out));
+    if (cp.rgb_u8) CK(h, cudaMemcpyAsync(cp.rgb_u8 + o1 * 3, c_rgb, (size_t)m * px * 3, cudaMemcpyDeviceToHost, s_out));
+    if (cp.dif_f16) CK(h, cudaMemcpyAsync(cp.dif_f16 + o1, c_dif, (size_t)m * px * 2, cudaMemcpyDeviceToHost, s_out));
     CK(h, cudaEventRecord(h->ev_out[slot], s_out));
   }
   CK(h, cudaStreamSynchronize(s_out));
@@ -841,6 +907,29 @@ int bsr_forward_tsm_host(bsr_handle* h, const float* img, const float* uv, const
   if (h->variant != BSR_VARIANT_TSM) return fail(h, BSR_EINVAL, "handle is not a TSM generator");
   if (n_chunks <= 0 || frame <= 0 || !reg) return fail(h, BSR_EINVAL, "n_chunks, frame > 0 and reg required");
   return forward_host(h, img, uv, reg, n_chunks * frame, frame, share, gs, rgb, mask22, dif);
+}
+
+int bsr_forward_gsc_host_compact(bsr_handle* h, const unsigned char* img_u8, const float* uv32, int n, float* gs,
+                                 float* rgb, float* mask22, float* dif, unsigned char* rgb_u8,
+                                 unsigned short* dif_f16) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_GSC) return fail(h, BSR_EINVAL, "handle is not a GSC generator");
+  if (!img_u8) return fail(h, BSR_EINVAL, "img_u8 must be non-NULL");
+  HostCompact cp;
+  cp.img_u8 = img_u8; cp.rgb_u8 = rgb_u8; cp.dif_f16 = dif_f16;
+  return forward_host(h, nullptr, uv32, nullptr, n, 1, 0, gs, rgb, mask22, dif, cp);
+}
+
+int bsr_forward_tsm_host_compact(bsr_handle* h, const unsigned char* img_u8, const float* uv32, const float* reg32,
+                                 int n_chunks, int frame, int share, float* gs, float* rgb, float* mask22, float* dif,
+                                 unsigned char* rgb_u8, unsigned short* dif_f16) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_TSM) return fail(h, BSR_EINVAL, "handle is not a TSM generator");
+  if (!img_u8) return fail(h, BSR_EINVAL, "img_u8 must be non-NULL");
+  if (n_chunks <= 0 || frame <= 0) return fail(h, BSR_EINVAL, "n_chunks and frame must be > 0");
+  HostCompact cp;
+  cp.img_u8 = img_u8; cp.rgb_u8 = rgb_u8; cp.dif_f16 = dif_f16;
+  return forward_host(h, nullptr, uv32, reg32, n_chunks * frame, frame, share, gs, rgb, mask22, dif, cp);
 }
 
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n, float* rgb_clipped,

@@ -1,6 +1,7 @@
 // Shared device helpers: activation storage types, the fused conv epilogue, small math.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 

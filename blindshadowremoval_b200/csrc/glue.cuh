@@ -58,6 +58,59 @@ __global__ void reg_small_kernel(const float* __restrict__ reg, float* __restric
   off[idx] = (v == v) ? v : 0.f;
 }
 
+// ---- compact host I/O -------------------------------------------------------
+// img_u8 -> fp32 `/ 255.` (dataset.py:119,159).  16 bytes in, 64 bytes out per thread; n16 = bytes/16.
+__global__ void expand_u8_kernel(const uint4* __restrict__ in, float4* __restrict__ out, long long n16) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n16) return;
+  uint4 v = __ldg(in + idx);
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 o;
+    o.x = __fdiv_rn((float)(w[k] & 0xffu), 255.f);
+    o.y = __fdiv_rn((float)((w[k] >> 8) & 0xffu), 255.f);
+    o.z = __fdiv_rn((float)((w[k] >> 16) & 0xffu), 255.f);
+    o.w = __fdiv_rn((float)(w[k] >> 24), 255.f);
+    out[idx * 4 + k] = o;
+  }
+}
+
+// reg32[N,32,32,6] (already resized) -> off[N,32,32,4], same selection/scale/NaN rule as reg_small_kernel.
+__global__ void reg32_off_kernel(const float* __restrict__ reg32, float* __restrict__ off, int n_img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * FEAT * FEAT * 4) return;
+  int k = idx & 3, cell = idx >> 2;
+  int c = (k < 2) ? k : k + 1;
+  float v = reg32[(size_t)cell * 6 + c] * (float)FEAT;
+  off[idx] = (v == v) ? v : 0.f;
+}
+
+// rgb fp32 -> uint8 rint(clip(x,0,1)*255) (train_test_GSC.py:809; utils.py:221,180): 16 floats -> 16 bytes.
+__global__ void rgb_to_u8_kernel(const float4* __restrict__ in, uint4* __restrict__ out, long long n16) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n16) return;
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 v = __ldg(in + idx * 4 + k);
+    auto q = [](float x) { return (uint32_t)__float2int_rn(fminf(fmaxf(x, 0.f), 1.f) * 255.f); };
+    w[k] = q(v.x) | (q(v.y) << 8) | (q(v.z) << 16) | (q(v.w) << 24);
+  }
+  out[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// dif fp32 -> binary16 (round to nearest even): 8 floats -> 16 bytes.
+__global__ void f32_to_f16_kernel(const float4* __restrict__ in, uint4* __restrict__ out, long long n8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  float4 a = __ldg(in + idx * 2), b = __ldg(in + idx * 2 + 1);
+  __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+  __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+  out[idx] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                        *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+}
+
 // First-half res-stack input: write uv at channel uv_off and zero [z0, z1)   (model.py:238;
 // model_with_TSM.py:272).  One thread per (pixel, channel of the written range).
 template <typename T>

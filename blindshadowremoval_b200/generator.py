@@ -23,6 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsr.so")
 PRECISIONS = ("bf16", "fp32check")
 IMG = 256
+FEAT = 32
 
 _F = ctypes.POINTER(ctypes.c_float)
 _SYMBOLS = {
@@ -35,6 +36,8 @@ _SYMBOLS = {
     "bsr_forward_tsm": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5),
     "bsr_forward_gsc_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 4),
     "bsr_forward_tsm_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4),
+    "bsr_forward_gsc_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6),
+    "bsr_forward_tsm_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 6),
     "bsr_caller_glue": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3),
     "bsr_composite": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t] + [ctypes.c_void_p] * 2),
     "bsr_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -63,6 +66,19 @@ def load_library(path: str = LIB_PATH):
 
 class BsrError(RuntimeError):
     pass
+
+
+def downsample8(x: np.ndarray) -> np.ndarray:
+    """``tf.image.resize(x, [32, 32])`` of a [N,256,256,C] map (bilinear, half-pixel centres, no antialias):
+    the mean of the centre 2x2 of every 8x8 cell (model.py:237; warp.py:137).  Same operation order as the
+    device kernel, so ``forward_compact(u8, downsample8(uv))`` reproduces ``__call__(u8/255, uv)`` bit for bit."""
+    x = np.asarray(x, dtype=np.float32)
+    if x.ndim != 4 or x.shape[1:3] != (IMG, IMG):
+        raise ValueError("expected [N,256,256,C], got %r" % (x.shape,))
+    h = np.float32(0.5)
+    top = x[:, 3::8, 3::8] * h + x[:, 3::8, 4::8] * h
+    bot = x[:, 4::8, 3::8] * h + x[:, 4::8, 4::8] * h
+    return np.ascontiguousarray(top * h + bot * h)
 
 
 def _ptr(t):
@@ -187,6 +203,57 @@ class Generator:
         else:
             rc = self._lib.bsr_forward_tsm_host(self._h, v(img_ptr), v(uv_ptr), v(reg_ptr), n // frame, frame, int(share),
                                                 v(gs_ptr), v(rgb_ptr), v(m22_ptr), v(dif_ptr))
+        self._check(rc)
+
+    # -- compact host I/O -----------------------------------------------
+    def forward_compact(self, img_u8, uv32, reg32=None, frame: Optional[int] = None, share=True,
+                        want=("rgb_u8", "dif_f16")):
+        """Forward fed with the bytes the dataset really holds (dataset.py:119,159 read uint8 PNGs and
+        divide by 255.; model.py:237 / warp.py:137 consume uv / reg only after the resize to 32x32).
+
+        img_u8 [N,256,256,3] uint8; uv32 [N,32,32,3] fp32 (= ``downsample8(uv)``); reg32 [N,32,32,6] (TSM).
+        ``want`` picks outputs from gs, con_rgb, mask22, dif (fp32 as in ``__call__``), rgb_u8
+        (= rint(clip(con_rgb,0,1)*255)) and dif_f16.  Returns a dict of NumPy arrays.
+        """
+        img_u8 = np.ascontiguousarray(img_u8)
+        if img_u8.dtype != np.uint8 or img_u8.ndim != 4 or img_u8.shape[1:] != (IMG, IMG, 3):
+            raise ValueError("img_u8 must be uint8 [N,256,256,3], got %s %r" % (img_u8.dtype, img_u8.shape))
+        n = img_u8.shape[0]
+        if n <= 0:
+            raise ValueError("empty batch")
+        uv32 = np.ascontiguousarray(uv32, dtype=np.float32)
+        if uv32.shape != (n, FEAT, FEAT, 3):
+            raise ValueError("uv32 must be [N,32,32,3], got %r" % (uv32.shape,))
+        if self.variant == "tsm":
+            if frame is None or frame <= 0:
+                raise ValueError("TSM variant needs frame > 0")
+            if reg32 is None or tuple(np.shape(reg32)) != (n, FEAT, FEAT, 6):
+                raise ValueError("reg32 must be [N,32,32,6]")
+            if n % frame:
+                raise ValueError("batch %d is not a multiple of frame %d (model_with_TSM.py:218)" % (n, frame))
+            reg32 = np.ascontiguousarray(reg32, dtype=np.float32)
+        unknown = set(want) - {"gs", "con_rgb", "mask22", "dif", "rgb_u8", "dif_f16"}
+        if unknown:
+            raise ValueError("unknown outputs %r" % sorted(unknown))
+        spec = {"gs": ((n, IMG, IMG, 1), np.float32), "con_rgb": ((n, IMG, IMG, 3), np.float32),
+                "mask22": ((n, IMG, IMG, 3), np.float32), "dif": ((n, IMG, IMG, 1), np.float32),
+                "rgb_u8": ((n, IMG, IMG, 3), np.uint8), "dif_f16": ((n, IMG, IMG, 1), np.float16)}
+        out = {k: (np.empty(*spec[k]) if k in want else None) for k in spec}
+        p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        outs = (p(out["gs"]), p(out["con_rgb"]), p(out["mask22"]), p(out["dif"]), p(out["rgb_u8"]), p(out["dif_f16"]))
+        self.forward_compact_ptrs(p(img_u8), p(uv32), p(reg32), n, frame, share, *outs)
+        return {k: v for k, v in out.items() if v is not None}
+
+    def forward_compact_ptrs(self, img_u8, uv32, reg32, n, frame, share, gs, rgb, m22, dif, rgb_u8, dif_f16):
+        """Compact host path on raw (e.g. pinned) pointers (ints or c_void_p); used by bench.py."""
+        v = lambda x: x if isinstance(x, ctypes.c_void_p) or x is None else (ctypes.c_void_p(x) if x else None)
+        if self.variant == "gsc":
+            rc = self._lib.bsr_forward_gsc_host_compact(self._h, v(img_u8), v(uv32), n, v(gs), v(rgb), v(m22), v(dif),
+                                                        v(rgb_u8), v(dif_f16))
+        else:
+            share = bool(share.item() if hasattr(share, "item") else share)
+            rc = self._lib.bsr_forward_tsm_host_compact(self._h, v(img_u8), v(uv32), v(reg32), n // frame, frame,
+                                                        int(share), v(gs), v(rgb), v(m22), v(dif), v(rgb_u8), v(dif_f16))
         self._check(rc)
 
     # -- caller glue (train_test_GSC.py:808-809, 711-718) ------------------------------------

@@ -72,6 +72,24 @@ int bsr_forward_tsm_host(bsr_handle* h, const float* img, const float* uv, const
                          int n_chunks, int frame, int share,
                          float* gs, float* rgb, float* mask22, float* dif);
 
+/* Compact host I/O: the same forward fed with the bytes the dataset really holds
+ * instead of the [F,256,256,16] fp32 chunk of dataset.py:296-302.
+ *   img_u8 [n,256,256,3] uint8 RGB, expanded on the device as float(u8)/255 (dataset.py:119,159 `/ 255.`);
+ *   uv32   [n,32,32,3]  fp32 = tf.image.resize(uv,[32,32]) - the only form model.py:237 consumes;
+ *   reg32  [n,32,32,6]  fp32 = tf.image.resize(reg,[32,32]) - the only form warp.py:137 consumes (TSM).
+ * Outputs: the four fp32 tensors as above and/or two compact ones, any of them NULL:
+ *   rgb_u8  [n,256,256,3] uint8 = rint(clip(con_rgb,0,1)*255), i.e. clip_by_value (train_test_GSC.py:809)
+ *           followed by the *255 + cv2.imwrite saturate-cast the loggers apply (utils.py:221,239,180);
+ *   dif_f16 [n,256,256,1] IEEE binary16 of `dif` (round to nearest even).
+ * 0.21 MB/image H2D instead of 1.57 (3.15 TSM); 0.33 MB/image D2H instead of 1.05 with the compact outputs. */
+int bsr_forward_gsc_host_compact(bsr_handle* h, const unsigned char* img_u8, const float* uv32, int n,
+                                 float* gs, float* rgb, float* mask22, float* dif,
+                                 unsigned char* rgb_u8, unsigned short* dif_f16);
+int bsr_forward_tsm_host_compact(bsr_handle* h, const unsigned char* img_u8, const float* uv32, const float* reg32,
+                                 int n_chunks, int frame, int share,
+                                 float* gs, float* rgb, float* mask22, float* dif,
+                                 unsigned char* rgb_u8, unsigned short* dif_f16);
+
 /* Caller glue, train_test_GSC.py:808-809 / 872-873 / 902-903 (TSM: train_with_TSM.py:677-678):
  * mask_pred = dif*face ; rgb_clipped = clip(rgb, 0, 1).  Device pointers; in-place allowed. */
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n,

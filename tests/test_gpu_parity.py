@@ -294,3 +294,46 @@ def test_full_size_properties(G):
     assert torch.equal(rgb2, rgb[:2])
     gen.close()
     small.close()
+
+
+def test_compact_host_io_matches_fp32_path_bit_for_bit(G):
+    """uint8 image + 32x32 uv/reg in, uint8 rgb + binary16 dif out.  Feeding u8 and downsample8(uv)
+    must give exactly the bits of the fp32 call on (u8/255, uv); the compact outputs must be the stated roundings of
+    the fp32 outputs."""
+    w, d = case("gsc", 2, 1)
+    n = 11                                                                       # ramped schedule at micro-batch 3
+    img_u8 = np.clip(np.rint(np.concatenate([d["img"]] * 6)[:n] * 255.0), 0, 255).astype(np.uint8)
+    uv = np.concatenate([d["uv"]] * 6)[:n]
+    img_f = img_u8.astype(np.float32) / np.float32(255.0)
+    gen = G.Generator("gsc", "bf16", device=0, micro_batch=3, weights=w)
+    gs, rgb, m22, dif = gen(img_f, uv, None)
+    out = gen.forward_compact(img_u8, G.downsample8(uv), want=("gs", "con_rgb", "mask22", "dif", "rgb_u8", "dif_f16"))
+    assert gen.debug_read("errflag")[0] == 0
+    assert np.array_equal(out["con_rgb"], rgb) and np.array_equal(out["dif"], dif)
+    assert np.array_equal(out["gs"], gs) and np.array_equal(out["mask22"], m22)
+    assert np.array_equal(out["rgb_u8"], np.rint(np.clip(rgb, 0.0, 1.0) * np.float32(255.0)).astype(np.uint8))
+    assert np.array_equal(out["dif_f16"], dif.astype(np.float16))
+    only = gen.forward_compact(img_u8, G.downsample8(uv))                        # default: compact outputs only
+    assert sorted(only) == ["dif_f16", "rgb_u8"] and np.array_equal(only["rgb_u8"], out["rgb_u8"])
+    # the fp32 entry point is unaffected by a preceding compact call (uv is read at 256x256 again)
+    _, rgb2, _, _ = gen(img_f, uv, None, want=("con_rgb",))
+    assert np.array_equal(rgb2, rgb)
+    with pytest.raises(ValueError):
+        gen.forward_compact(img_f, G.downsample8(uv))                            # not uint8
+    with pytest.raises(ValueError):
+        gen.forward_compact(img_u8, uv)                                          # uv not 32x32
+    gen.close()
+    # TSM: reg at 32x32 as well; 3 chunks of frame=2 through a 4-image workspace
+    wt, dt = case("tsm", 4, 2)
+    six = {k: np.concatenate([v] * 2)[:6] for k, v in dt.items()}
+    u8 = np.clip(np.rint(six["img"] * 255.0), 0, 255).astype(np.uint8)
+    tsm = G.Generator("tsm", "bf16", device=0, micro_batch=4, weights=wt)
+    _, rgb_t, _, dif_t = tsm(u8.astype(np.float32) / np.float32(255.0), six["uv"], six["reg"], frame=2,
+                             want=("con_rgb", "dif"))
+    out_t = tsm.forward_compact(u8, G.downsample8(six["uv"]), G.downsample8(six["reg"]), frame=2,
+                                want=("con_rgb", "dif", "rgb_u8"))
+    assert np.array_equal(out_t["con_rgb"], rgb_t) and np.array_equal(out_t["dif"], dif_t)
+    assert np.array_equal(out_t["rgb_u8"], np.rint(np.clip(rgb_t, 0.0, 1.0) * np.float32(255.0)).astype(np.uint8))
+    with pytest.raises(ValueError):
+        tsm.forward_compact(u8[:5], G.downsample8(six["uv"])[:5], G.downsample8(six["reg"])[:5], frame=2)
+    tsm.close()

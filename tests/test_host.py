@@ -123,3 +123,18 @@ def test_variable_shapes_wide_layers():
     g, t = variable_shapes("gsc"), variable_shapes("tsm")
     assert g["up1/conv/kernel"] == (3, 3, 96, 257) and t["up1/conv/kernel"] == (3, 3, 96, 291)
     assert g["clr_up1/conv/kernel"] == (3, 3, 128, 261) and t["clr_up1/conv/kernel"] == (3, 3, 128, 877)
+
+
+def test_compact_input_helpers_match_reference_arithmetic():
+    """what the compact host path assumes about the fp32 chunk it replaces."""
+    # dataset.py:119 `cv2.imread(...) / 255.` is a float64 division later cast to fp32 by tf; the device kernel does the
+    # fp32 division float(u8)/255.f -- identical for every byte value
+    u = np.arange(256)
+    assert np.array_equal((u / 255.).astype(np.float32), u.astype(np.float32) / np.float32(255.))
+    # downsample8 == tf.image.resize(x,[32,32]) as restated by the oracle (model.py:237, warp.py:137)
+    x = np.random.default_rng(0).random((2, 256, 256, 6), dtype=np.float32)
+    ref = R.resize_bilinear(torch.from_numpy(x), 32, 32).numpy()
+    got = generator.downsample8(x)
+    assert got.shape == (2, 32, 32, 6) and np.abs(got - ref).max() < 1e-6
+    with pytest.raises(ValueError):
+        generator.downsample8(x[:, :128])
