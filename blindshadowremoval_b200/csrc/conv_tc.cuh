@@ -12,7 +12,7 @@
 //       transposed conv : (model.py:153, 3x3 / stride 2 / SAME)  out[2i+py, 2j+px] = sum over taps
 //                         kh = py, kw = px (mod 2) of in[i-(kh>>1), j-(kw>>1)] . W[kh,kw].  The 4
 //                         sub-pixel phases share their A tiles, so a step = (shift, channel block) and
-//                         its MMAs feed the accumulators [p00 | p10 | p01 | p11] of ALL phases:
+//                         its MMAs feed the accumulators [p10 | p00 | p01 | p11] of ALL phases:
 //                         shift(0,0) -> 4 taps (N = 4*cout), (0,-1) -> 2, (-1,0) -> 2, (-1,-1) -> 1;
 //       conv1 (7x7, 3ch): rows of the pre-packed image [N][H][W+8][8]: one step per filter ROW, whose
 //                         64-element K block is the overlapping 8-pixel x 8-channel window;
@@ -150,6 +150,10 @@ struct ConvTcParams {
   int a_sub;                  // A sub-tiles per stage (max n_a over the steps)
   int b_resident, b_total_rows;
   int b_res_kblocks;          // resident weights: number of 64-element K blocks kept ([kblock][row] layout)
+  int st_chunk;               // staged TMA-store epilogue: 0 = direct per-thread stores, 16 / 8 = columns per warp and
+                              // iteration (an iteration = 4 x st_chunk columns = 32-channel SWIZZLE_64B boxes in smem)
+  int st_bufs;                // staging buffers: 2 = double-buffered, 1 = single (one more barrier per iteration)
+  int steps_bytes, epi_bytes; // shared-memory bytes of the step program / epilogue scratch (multiples of 128)
   int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
   long long* timers;          // [16] per launch (CTA 0): role wait / total cycle counters when ablate & 8
   int* errflag;
@@ -199,7 +203,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ ConvTcParams p,
                                                                 const EpiParams e, const EpiExtra x,
-                                                                const __grid_constant__ ClrWeights cw) {
+                                                                const __grid_constant__ ClrWeights cw,
+                                                                const __grid_constant__ CUtensorMap tmO) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TC_BM * 128;
@@ -212,7 +217,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
   TcStep* steps = reinterpret_cast<TcStep*>(smem_al + (bars + 192 - smem_base));
-  float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 + TC_MAX_STEPS * sizeof(TcStep) - smem_base));
+  float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 + (uint32_t)p.steps_bytes - smem_base));
+  // output staging of the TMA-store epilogue: 2 buffers of 128 rows x (4 x st_chunk) bf16 columns
+  const uint32_t st_stage = (bars + 192 + (uint32_t)p.steps_bytes + (uint32_t)p.epi_bytes + 511u) & ~511u;   // 512 B = one 64B-swizzle atom
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.steps);
     uint32_t* dst = reinterpret_cast<uint32_t*>(steps);
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.st_chunk) prefetch_tmap(&tmO);
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -391,12 +399,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int ethread = threadIdx.x;
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, st_it = 0;
     bool ok = true;
     // static data first (bias, colour-tail weights): not produced by the previous kernel
     float* bias_s = epi_smem;                   // [512] (the device bias buffer is zero-padded past cout)
     float* epi_work = epi_smem + 512;
-    for (int i = ethread; i < 512; i += TC_EPI_WARPS * 32) bias_s[i] = __ldg(e.bias + i);
+    for (int i = ethread; i < 512 && i * 4 < p.epi_bytes; i += TC_EPI_WARPS * 32) bias_s[i] = __ldg(e.bias + i);
     epi_bar_all();
     pdl_wait();
     const int OH = p.OH, OW = p.OW, bn = p.bn, rows_per_tile = p.rows_per_tile;
@@ -408,7 +416,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
       const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
       const uint32_t acc = tmem_base + as * (uint32_t)bn + lane_addr;
-      if (EPI == EPI_GENERIC) {
+      if (EPI == EPI_GENERIC && !RES && p.st_chunk) {
+        // ---- staged epilogue: accumulators -> bf16 -> 64B-swizzled shared memory -> TMA store.  Per-thread-row global
+        // stores touch 32 cache lines per warp instruction and (measured) slow the UMMA operand
+        // reads that share the L1/shared-memory pipe; the bulk store reads the staged tile at full line width instead.
+        const int cw_ = p.st_chunk, group_cols = p.group_cols, total_cols = p.n_groups * group_cols;
+        const int iter_cols = 4 * cw_;
+        const uint32_t buf_bytes = (uint32_t)iter_cols * 256u;                 // 128 rows x iter_cols bf16
+        const int gx0 = (tr % p.tiles_x) * p.bw, gy0 = (tr / p.tiles_x) * p.bh * rows_per_tile;
+        ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        if (!ok) break;
+        tc_fence_after();
+        const bool single = p.st_bufs == 1;
+        for (int col0 = 0; col0 < total_cols; col0 += iter_cols, ++st_it) {
+          const uint32_t buf = st_stage + (single ? 0u : (st_it & 1u) * buf_bytes);
+          const int colw = cg * cw_, col = col0 + colw;                        // this warp's columns of the iteration
+          uint32_t o[8];
+          if (col < total_cols) {
+            float v[16];
+            if (cw_ == 16) tmem_ld16(acc + (uint32_t)col, v);
+            else tmem_ld8(acc + (uint32_t)col, v);
+            const int j = col % group_cols;                                    // channel inside the group
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (i < cw_) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j + i);
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            }
+            if (e.act) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          }
+          if (col0 + iter_cols >= total_cols) {          // accumulators drained: the MMA warp may start the next tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          }
+          if (single) {       // one buffer: the previous bulk store must have finished reading it before anyone writes
+            if (ethread == 0) bulk_wait_read0();
+            epi_bar_all();
+          }
+          if (col < total_cols) {
+            // box = 32 channels (64-byte rows); 16-byte piece `pc` of row r lands at r*64 + ((pc ^ (r>>1)) & 3)*16
+            const uint32_t box = buf + (uint32_t)(colw >> 5) * 8192u;
+            const uint32_t pc0 = (uint32_t)(colw & 31) >> 3;
+            const uint32_t rowb = box + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
+            {
+              const uint32_t a = rowb + ((pc0 ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+            if (cw_ == 16) {
+              const uint32_t a = rowb + (((pc0 + 1u) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
+          }
+          fence_async_smem();
+          // double-buffered: the bulk store issued one iteration ago has finished READING the other buffer before anyone
+          // passes the barrier below and starts overwriting it
+          if (!single && ethread == 0) bulk_wait_read0();
+          epi_bar_all();
+          if (ethread == 0 && !(p.ablate & 1)) {
+            for (int b = 0; b * 32 < iter_cols; ++b) {
+              const int bc = col0 + b * 32;
+              if (bc < total_cols) {
+                const int g = bc / group_cols, j = bc - g * group_cols;
+                const int phase = rows_per_tile > 1 ? 0 : p.group_phase[g];
+                const int gy = gy0 + (rows_per_tile > 1 ? g * p.bh : 0);
+                tma_store_5d(&tmO, buf + (uint32_t)b * 8192u, e.out_coff + j, phase & 1, gx0, phase >> 1,
+                             n * (OH / p.out_scale) + gy);
+              }
+            }
+            bulk_commit();
+          }
+        }
+      } else if (EPI == EPI_GENERIC) {
         const int bw = p.bw, bh = p.bh, out_scale = p.out_scale, group_cols = p.group_cols;
         const int gyb = (tr / p.tiles_x) * bh * rows_per_tile + r / bw, gx = (tr % p.tiles_x) * bw + r % bw;
         const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
@@ -673,6 +758,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
     if (tm) { p.timers[9] = BSR_CLK() - t_start; p.timers[10] = t_wtfull; p.timers[11] = tcount; }
+    if (p.st_chunk && ethread == 0) bulk_wait0();        // staged stores have landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -847,14 +933,16 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   t.cin_pad = (cin + 63) / 64 * 64;
   const int ncb = t.cin_pad / 64;
   if (transposed && cout % 16 == 0 && cout <= 96 && 4 * ncb <= TC_MAX_STEPS && !tc_disabled("convt_fused")) {
-    // fused 4-phase transposed conv; accumulator column groups [p00 | p10 | p01 | p11]
+    // fused 4-phase transposed conv
     if (kh != 3 || kw != 3) { *why = "transposed conv must be 3x3"; return false; }
     t.kind = TC_CONVT_FUSED; t.bn = 4 * cout; t.n_tiles = 1; t.b_box_rows = cout; t.b_stage_rows = 4 * cout;
     const size_t K = t.cin_pad, rows = 9 * (size_t)cout;
     std::vector<uint16_t> host(rows * K, 0);
-    // weight row blocks, in order: shift(0,0): taps (0,0),(1,0),(0,1),(1,1); shift(0,-1): (0,2),(1,2);
+    // Accumulator column groups are [p10 | p00 | p01 | p11] so that the two phases fed by each one-pixel shift are
+    // adjacent and take ONE MMA of N = 2*cout (an SS-mode MMA costs ~44 + 0.47 N cycles: fewer, wider is cheaper).
+    // weight row blocks, in column order: shift(0,0): taps (1,0),(0,0),(0,1),(1,1); shift(0,-1): (1,2),(0,2);
     // shift(-1,0): (2,0),(2,1); shift(-1,-1): (2,2)
-    const int order[9][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}, {0, 2}, {1, 2}, {2, 0}, {2, 1}, {2, 2}};
+    const int order[9][2] = {{1, 0}, {0, 0}, {0, 1}, {1, 1}, {1, 2}, {0, 2}, {2, 0}, {2, 1}, {2, 2}};
     for (int b = 0; b < 9; ++b) {
       const int tap = order[b][0] * 3 + order[b][1];
       for (int c = 0; c < cin; ++c)
@@ -876,17 +964,17 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       if (4 * cout <= 256) { s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)(4 * co), 0, f}; }
       else { s.n_mma = 2; s.mma[0] = TcMma{0, (int16_t)(2 * co), 0, f}; s.mma[1] = TcMma{(int16_t)(2 * co), (int16_t)(2 * co), (int16_t)(2 * co), f}; }
       t.steps[ns++] = s;
-      // shift (0,-1): kw = 2 -> phases p00, p10 (adjacent columns)
+      // shift (0,-1): kw = 2 -> phases p10, p00 (columns 0 .. 2*cout)
       s.dy = 0; s.dx = -1; s.b_row = (int16_t)(4 * co); s.b_rows = (int16_t)(2 * co);
       s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)(2 * co), 0, 0};
       t.steps[ns++] = s;
-      // shift (-1,0): kh = 2 -> phases p00 (cols 0) and p01 (cols 2*cout)
+      // shift (-1,0): kh = 2 -> phases p00, p01 (columns cout .. 3*cout)
       s.dy = -1; s.dx = 0; s.b_row = (int16_t)(6 * co); s.b_rows = (int16_t)(2 * co);
-      s.n_mma = 2; s.mma[0] = TcMma{0, co, 0, 0}; s.mma[1] = TcMma{(int16_t)(2 * co), co, co, 0};
+      s.n_mma = 1; s.mma[0] = TcMma{co, (int16_t)(2 * co), 0, 0};
       t.steps[ns++] = s;
-      // shift (-1,-1): tap (2,2) -> p00
+      // shift (-1,-1): tap (2,2) -> p00 (columns cout .. 2*cout)
       s.dy = -1; s.dx = -1; s.b_row = (int16_t)(8 * co); s.b_rows = co;
-      s.n_mma = 1; s.mma[0] = TcMma{0, co, 0, 0};
+      s.n_mma = 1; s.mma[0] = TcMma{co, co, 0, 0};
       t.steps[ns++] = s;
       cb += na;
     }
@@ -1045,7 +1133,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.n_img = n; p.bn = t.bn; p.n_tiles = t.n_tiles; p.b_box_rows = t.b_box_rows;
   if (t.kind == TC_CONVT_FUSED) {
     p.n_groups = 4; p.group_cols = t.cout;
-    p.group_phase[0] = 0; p.group_phase[1] = 2; p.group_phase[2] = 1; p.group_phase[3] = 3;   // p00 p10 p01 p11
+    p.group_phase[0] = 2; p.group_phase[1] = 0; p.group_phase[2] = 1; p.group_phase[3] = 3;   // p10 p00 p01 p11
   } else if (t.rows_per_tile > 1) {
     p.n_groups = t.rows_per_tile; p.group_cols = t.bn / t.rows_per_tile;      // TC_ROWPACK: one group per output row
   } else {
@@ -1056,15 +1144,41 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const bool resident = t.b_resident || (t.can_reside && p.total_tiles >= 6 * grid);
   p.b_resident = resident ? 1 : 0;
-  const int epi_bytes = 2048 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 258 * CLR_RS * 4 : 0));
+  // bias staging: 512 floats unless the layer provably reads fewer (frees shared memory for the store staging)
+  const int bias_floats = (p.epi_mode == EPI_GENERIC && p.n_groups > 1 && p.group_cols <= 128) ? 128 : 512;
+  const int epi_bytes = bias_floats * 4 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 258 * CLR_RS * 4 : 0));
+  p.epi_bytes = (epi_bytes + 127) / 128 * 128;
+  p.steps_bytes = (int)((t.n_steps * sizeof(TcStep) + 127) / 128 * 128);
   p.b_res_kblocks = t.b_res_kblocks;
   { const char* ab = getenv("BSR_ABLATE"); p.ablate = ab ? atoi(ab) : 0; }
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
-  const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * t.b_total_rows * 128 : 0) + 192 + (int)(TC_MAX_STEPS * sizeof(TcStep)) + epi_bytes + 64;
+  const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * t.b_total_rows * 128 : 0) + 192 + p.steps_bytes + p.epi_bytes + 512 + 64;
   p.a_sub = t.a_sub;
   p.stage_bytes = t.a_sub * (TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128));
-  p.n_stages = (TC_SMEM_BUDGET + 20 * 1024 - fixed_bytes) / p.stage_bytes;
-  if (p.n_stages > 8) p.n_stages = 8;
+  const int max_smem = 227 * 1024;
+  // Staged TMA-store epilogue (bf16 NHWC outputs whose column groups are multiples of 32 channels), used when the
+  // staging fits without shortening the TMA->MMA pipeline; otherwise the direct-store epilogue runs.
+  p.st_chunk = 0;
+  int staging = 0;
+  const int stages_direct = std::min(8, (max_smem - fixed_bytes) / p.stage_bytes);
+  const bool st_ok = p.epi_mode == EPI_GENERIC && e.res1 == nullptr && e.res2 == nullptr && e.out_mode == OUT_T &&
+                     t.n_tiles == 1 && p.group_cols % 32 == 0 && e.out_c == p.group_cols && e.out_ld % 8 == 0 &&
+                     e.out_coff % 8 == 0 && p.OH % p.out_scale == 0 && p.OW % p.out_scale == 0 && !getenv("BSR_NO_TMA_STORE");
+  if (st_ok) {
+    // 64 accumulator columns per iteration; double-buffered (2 x 16 KB) if the pipeline keeps its depth, else one buffer
+    for (int bufs = 2; bufs >= 1 && !p.st_chunk; --bufs) {
+      const int need = bufs * 128 * 64 * 2;
+      const int ns = std::min(8, (max_smem - fixed_bytes - need) / p.stage_bytes);
+      // one buffer costs a second barrier per iteration: only worth it where the pipeline has >= 3 stages of slack
+      // (measured: up2 -13 %, conv1 -10 %, but up3 / clr_up3 with 2 stages +14 %)
+      if (ns >= 2 && (ns >= stages_direct || ns >= 4) && (bufs == 2 || ns >= 3)) { p.st_chunk = 16; p.st_bufs = bufs; staging = need; }
+    }
+    if (const char* sb = getenv("BSR_ST_BUFS")) {      // experiment knob: force the buffer count where it fits
+      const int bufs = atoi(sb), need = bufs * 128 * 64 * 2;
+      if ((bufs == 1 || bufs == 2) && (max_smem - fixed_bytes - need) / p.stage_bytes >= 2) { p.st_chunk = 16; p.st_bufs = bufs; staging = need; }
+    }
+  }
+  p.n_stages = std::min(8, (max_smem - fixed_bytes - staging) / p.stage_bytes);
   if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }
   p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
   p.errflag = errflag;
@@ -1093,7 +1207,26 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     if (cache.size() > 4096) cache.clear();
     it = cache.emplace(key, m).first;
   }
-  const size_t smem = (size_t)fixed_bytes + (size_t)p.n_stages * p.stage_bytes;
+  // output map of the staged epilogue: [C, px, W/s, py, N*H/s] (s = out_scale; a 3x3/s2 transposed conv writes the
+  // four sub-pixel phases (py, px) of every input position), box = 32 channels x bw x bh positions
+  static const CUtensorMap no_map = {};
+  const CUtensorMap* omap = &no_map;
+  if (p.st_chunk) {
+    const int sc = p.out_scale;
+    TmapKey okey{e.out, e.out_ld, 0, 0, p.OH, p.OW, n, sc, p.bw, p.bh, 1000};
+    auto ot = cache.find(okey);
+    if (ot == cache.end()) {
+      CUtensorMap m;
+      const uint64_t ld2 = (uint64_t)e.out_ld * 2;
+      uint64_t dims[5] = {(uint64_t)e.out_ld, (uint64_t)sc, (uint64_t)(p.OW / sc), (uint64_t)sc, (uint64_t)n * (uint64_t)(p.OH / sc)};
+      uint64_t strides[4] = {ld2, (uint64_t)sc * ld2, (uint64_t)p.OW * ld2, (uint64_t)sc * p.OW * ld2};
+      uint32_t box[5] = {32, 1, (uint32_t)p.bw, 1, (uint32_t)p.bh};
+      if (!tma.encode_bf16_store(&m, e.out, 5, dims, strides, box)) return -3;
+      ot = cache.emplace(okey, m).first;       // std::map: `it` (the input map) stays valid
+    }
+    omap = &ot->second;
+  }
+  const size_t smem = (size_t)fixed_bytes + (size_t)staging + (size_t)p.n_stages * p.stage_bytes;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)grid);
@@ -1108,10 +1241,10 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   static const ClrWeights no_clr = {};
   const ClrWeights& cw = (p.epi_mode == EPI_CLR && t.clr) ? *t.clr : no_clr;
   cudaError_t le;
-  if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x, cw);
-  else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x, cw);
-  else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x, cw);
-  else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x, cw);
+  if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x, cw, *omap);
+  else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x, cw, *omap);
+  else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x, cw, *omap);
+  else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x, cw, *omap);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }
   (*launches)++;
   return 0;

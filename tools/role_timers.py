@@ -12,7 +12,8 @@ os.environ["BSR_DEBUG_KEEP"] = "1"
 from blindshadowremoval_b200.generator import Generator  # noqa: E402
 from blindshadowremoval_b200.synthetic import make_inputs  # noqa: E402
 
-mb = 32
+mb = int(os.environ.get("MB", "128"))
+LAUNCHES = open(os.path.join(ROOT, "profiles", "launch_names_gsc.txt")).read().strip().split(",")
 gen = Generator("gsc", "bf16", device=0, micro_batch=mb, seed=1234)
 d = make_inputs(mb, 0)
 img, uv = torch.from_numpy(d["img"]).cuda(), torch.from_numpy(d["uv"]).cuda()
@@ -20,9 +21,8 @@ for _ in range(3):
     gen(img, uv, None, want=("con_rgb", "dif"))
 torch.cuda.synchronize()
 t = gen.debug_read("timers").reshape(64, 16)
-ATT = {11, 16, 21, 31, 36, 41}
-names = {11: "attn+w", 1: "conv1", 2: "down1", 3: "down2", 4: "down3", 7: "r0.c1", 8: "r0.c2", 9: "r0.c3", 10: "r0.qkv", 12: "r0.w",
-         25: "up1", 26: "up2", 27: "up3", 28: "heads", 52: "clr_up2", 53: "clr_up3", 54: "clr_conv1"}
+names = dict(enumerate(LAUNCHES))           # launch index inside one forward (h->launches at launch time)
+ATT = {i for i, nm in names.items() if nm.endswith("attn+w")}
 print("launch  name       | producer: total wait_empty dep_wait steps | mma: total wait_full wait_tempty wait_res tiles | epi: total wait_tfull tiles")
 for i in range(64):
     if t[i, 0] == 0 and t[i, 4] == 0:
