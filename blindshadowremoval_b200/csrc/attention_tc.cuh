@@ -24,7 +24,7 @@ namespace bsr {
 constexpr int AT_S = 1024, AT_D = 128, AT_BQ = 128, AT_BK = 128;
 constexpr int AT_NK = AT_S / AT_BK;                   // 8 key tiles
 constexpr uint32_t AT_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 bf16] as two 16 KB k-blocks
-constexpr size_t kAttnTcSmem = 1024 + 7 * (size_t)AT_TILE + 192 + 1024;   // Q, K x2, V x2, P x2, barriers, exchange
+constexpr size_t kAttnTcSmem = 1024 + 7 * (size_t)AT_TILE + 192 + 1024 + 64;   // Q, K x2, V x2, P x2, barriers, exchange, residual-ring barriers
 
 __device__ __forceinline__ void add_bf16x16_attn(const uint4& a, const uint4& b, float* v) {
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -47,9 +47,16 @@ constexpr int AT_THREADS = 320;      // warps 0-7 softmax / epilogue, warp 8 TMA
 //   out = LeakyReLU(x_in + y + W_w . O + b)      (model.py:56-59, 105-113)
 // O (bf16) goes to shared memory as the A operand of one more GEMM (N = 144 + 128 accumulator columns reuse the S / O
 // TMEM columns, W_w lands in the Q/K buffers once the last S MMA has retired) and never reaches HBM.
+// fuse_w = 2: same, with the block-tail epilogue staged through shared memory: the residual tiles (y, x_in) arrive by
+//   TMA into the retired V stages (ring of two 64-channel batches) and the result leaves by TMA bulk stores from the
+//   retired P[1] buffer.  Per-thread-row global accesses cost 32 L1 wavefronts per warp instruction (54 of them per
+//   thread made the direct epilogue LSU-bound: 13.7 k of a CTA's 60 k cycles); the staged one touches shared memory only.
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK,
                                                                      const __grid_constant__ CUtensorMap tmVT,
                                                                      const __grid_constant__ CUtensorMap tmW,
+                                                                     const __grid_constant__ CUtensorMap tmR1,
+                                                                     const __grid_constant__ CUtensorMap tmR2,
+                                                                     const __grid_constant__ CUtensorMap tmOut,
                                                                      bf16* __restrict__ o, const EpiParams e,
                                                                      const int fuse_w, int* errflag,
                                                                      long long* timers) {
@@ -65,6 +72,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
   uint8_t* sP_gen = smem_al + (sP - base);
   float* xch = reinterpret_cast<float*>(smem_al + (bars + 192 - base));      // [2][128] row max / row sum exchange
+  const uint32_t b_rfull = bars + 192 + 1024, b_rempty = b_rfull + 16;       // residual ring of the staged epilogue
+  uint8_t* sV_gen = smem_al + (sV - base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, n = blockIdx.y;
@@ -90,6 +99,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     mbar_init(b_wfull, 1);
     mbar_init(b_a2full, 8);
     mbar_init(b_d2full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_rfull + 8 * s, 1);
+      mbar_init(b_rempty + 8 * s, 8);
+    }
+    if (fuse_w == 2) {
+      prefetch_tmap(&tmR1);
+      prefetch_tmap(&tmR2);
+      prefetch_tmap(&tmOut);
+    }
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -145,6 +163,23 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         }
       }
       __syncwarp();
+    }
+    if (fuse_w == 2 && ok) {
+      // residual ring: batch b = channels 64b .. 64b+63 of y (res1) and x_in (res2) for this CTA's 128 pixels, into V
+      // stage b & 1 (16 KB each); the stages are free once every PV MMA has retired
+      ok = mbar_wait(b_ofull, 0, errflag, 27);
+      const int pix0 = n * AT_S + q0;
+      for (int b = 0; b < 4 && ok; ++b) {
+        const int s = b & 1;
+        if (b >= 2) ok = mbar_wait(b_rempty + 8 * s, 0, errflag, 28);
+        if (!ok) break;
+        if (leader) {
+          mbar_expect_tx(b_rfull + 8 * s, AT_TILE);
+          tma_load_2d(sV + s * AT_TILE, &tmR1, b_rfull + 8 * s, 64 * b, pix0);
+          tma_load_2d(sV + s * AT_TILE + AT_TILE / 2, &tmR2, b_rfull + 8 * s, 64 * b, pix0);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp == 9) {
     // ================= MMA issuer (converged warp, elected lane issues) =================
@@ -372,6 +407,85 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_a2full);
+      if (fuse_w == 2) {
+        // ---- staged block-tail epilogue (see kernel comment): batches of 64 channels; warp (q, h) owns rows 32q..32q+31 and
+        // channels 32h..32h+31 of every batch; the last 16 (padding) channels 256..271 go the direct way (h == 0 warps)
+        const size_t pix = (size_t)n * AT_S + q0 + row;
+        uint4 ra[2], rb[2];
+        if (h == 0) {
+          const uint4* s1 = reinterpret_cast<const uint4*>((const bf16*)e.res1 + pix * e.res1_ld + 256);
+          const uint4* s2 = reinterpret_cast<const uint4*>((const bf16*)e.res2 + pix * e.res2_ld + 256);
+          ra[0] = s1[0]; ra[1] = s1[1]; rb[0] = s2[0]; rb[1] = s2[1];
+        }
+        ok = mbar_wait(b_d2full, 0, errflag, 26);
+        tc_fence_after();
+        const long long t4s = AT_CLK();
+        auto finish16 = [&](float* v, const int c, const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1,
+                            uint4& o0, uint4& o1) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+          add_bf16x16_attn(a0, a1, v);
+          add_bf16x16_attn(b0, b1, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
+          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+        };
+        const uint32_t rowo = (uint32_t)row * 128u, sw = (uint32_t)row & 7u;
+        for (int b = 0; b < 4 && ok; ++b) {
+          const int s = b & 1;
+          ok = mbar_wait(b_rfull + 8 * s, (uint32_t)(b >> 1), errflag, 29);
+          if (!ok) break;
+          const uint8_t* r1s = sV_gen + s * AT_TILE + rowo;
+          const uint8_t* r2s = r1s + AT_TILE / 2;
+          uint8_t* outs = sP_gen + AT_TILE + s * (AT_TILE / 2) + rowo;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = 64 * b + 32 * h + 16 * k;
+            const uint32_t p0 = (((uint32_t)(4 * h + 2 * k)) ^ sw) << 4, p1 = (((uint32_t)(4 * h + 2 * k + 1)) ^ sw) << 4;
+            float v[16];
+            tmem_ld16(tmem + lane_addr + (uint32_t)c, v);
+            const uint4 a0 = *reinterpret_cast<const uint4*>(r1s + p0), a1 = *reinterpret_cast<const uint4*>(r1s + p1);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(r2s + p0), b1 = *reinterpret_cast<const uint4*>(r2s + p1);
+            uint4 o0, o1;
+            finish16(v, c, a0, a1, b0, b1, o0, o1);
+            *reinterpret_cast<uint4*>(outs + p0) = o0;
+            *reinterpret_cast<uint4*>(outs + p1) = o1;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_rempty + 8 * s);          // this warp is done with residual stage s
+          // the bulk store issued one batch ago has finished reading the other staging half before anyone passes the
+          // barrier and overwrites it in the next batch
+          if (threadIdx.x == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (threadIdx.x == 0) {
+            tma_store_2d(&tmOut, sP + AT_TILE + s * (AT_TILE / 2), 64 * b, (int)((size_t)n * AT_S + q0));
+            bulk_commit();
+          }
+        }
+        if (ok && h == 0) {
+          float v[16];
+          tmem_ld16(tmem + lane_addr + 256u, v);
+          uint4 o0, o1;
+          finish16(v, 256, ra[0], ra[1], rb[0], rb[1], o0, o1);
+          uint4* d = reinterpret_cast<uint4*>((bf16*)e.out + pix * e.out_ld + e.out_coff + 256);
+          d[0] = o0;
+          d[1] = o1;
+        }
+        if (threadIdx.x == 0) bulk_wait0();
+#ifdef BSR_ROLE_TIMERS
+        if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && timers) {
+          timers[8] = t1s - t0s; timers[9] = u_s1; timers[10] = u_s2; timers[11] = u_pe; timers[12] = t2s - t1s;
+          timers[13] = 0; timers[14] = t4s - t2s; timers[15] = AT_CLK() - t4s;
+        }
+#endif
+      } else {
       // second GEMM's epilogue: warp half h owns accumulator columns [h*144, h*144 + (h ? 128 : 144))
       const size_t pix = (size_t)n * AT_S + q0 + row;
       const int c_begin = h * 144, c_end = h ? 272 : 144;
@@ -437,6 +551,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && timers) timers[15] = AT_CLK() - t4s;
 #endif
       }
+      }      // fuse_w == 1 (direct epilogue)
     }
   }
   tc_fence_before();
@@ -480,9 +595,33 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
   EpiParams ep;
   memset(&ep, 0, sizeof ep);
   if (e) ep = *e;
-  const int fuse = (w_map != nullptr && e != nullptr) ? 1 : 0;
+  int fuse = (w_map != nullptr && e != nullptr) ? 1 : 0;
+  // staged block-tail epilogue: [pixels x channels] maps of y (res1), x_in (res2) and the output, 64 x 128 boxes
+  static thread_local std::map<std::tuple<const void*, int, int>, CUtensorMap> rcache;
+  const CUtensorMap* rm[3] = {&it->second.first, &it->second.first, &it->second.first};
+  if (fuse && !getenv("BSR_NO_TMA_STORE") && e->res1 && e->res2 && e->res1_ld >= 272 && e->res2_ld >= 272 &&
+      e->out_ld >= e->out_coff + 272 && e->out_coff % 8 == 0 && e->out_ld % 8 == 0 && e->res1_ld % 8 == 0 && e->res2_ld % 8 == 0) {
+    const void* bases[3] = {e->res1, e->res2, (const void*)((const bf16*)e->out + e->out_coff)};
+    const int lds[3] = {e->res1_ld, e->res2_ld, e->out_ld};
+    bool okm = true;
+    if (rcache.size() > 1024) rcache.clear();      // before this launch's lookups: pointers taken below stay valid
+    for (int i = 0; i < 3 && okm; ++i) {
+      auto rk = std::make_tuple(bases[i], lds[i], n);
+      auto rt = rcache.find(rk);
+      if (rt == rcache.end()) {
+        CUtensorMap m;
+        uint64_t d2[2] = {(uint64_t)lds[i], (uint64_t)n * AT_S}, s2[1] = {(uint64_t)lds[i] * 2};
+        uint32_t b2[2] = {64, 128};
+        if (!tma.encode_bf16(&m, (void*)bases[i], 2, d2, s2, b2, nullptr)) { okm = false; break; }
+        rt = rcache.emplace(rk, m).first;
+      }
+      rm[i] = &rt->second;
+    }
+    if (!okm) return -4;
+    fuse = 2;
+  }
   cudaError_t le = cudaLaunchKernelEx(&cfg, attention_tc_kernel, it->second.first, it->second.second,
-                                      fuse ? *w_map : it->second.first, o, ep, fuse, errflag,
+                                      fuse ? *w_map : it->second.first, *rm[0], *rm[1], *rm[2], o, ep, fuse, errflag,
                                       reinterpret_cast<long long*>(errflag) + 16 + 16 * (launch_index & 63));
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
   return 0;
