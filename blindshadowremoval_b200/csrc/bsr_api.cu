@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/bsr.h"
@@ -384,9 +385,14 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
   {
     Step step(h, st, "assemble_uv");
     int uv_off = c_cur - 3;
-    long long tot = px32 * (3 + (ld1 - c_cur));
-    assemble_uv_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((T*)h->XA, ld1, h->UVS, uv_off, c_cur, ld1,
-                                                                         (int)px32);
+    if (std::is_same<T, bf16>::value && ld1 % 8 == 0) {
+      long long tot = px32 * ((ld1 >> 3) - (uv_off >> 3));
+      assemble_uv_vec_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((bf16*)h->XA, ld1, h->UVS, uv_off, (int)px32);
+    } else {
+      long long tot = px32 * (3 + (ld1 - c_cur));
+      assemble_uv_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((T*)h->XA, ld1, h->UVS, uv_off, c_cur, ld1,
+                                                                           (int)px32);
+    }
     h->launches++;
   }
   debug_capture(h, st, "x_in0", h->XA, ld1, 0, c_cur, px32);

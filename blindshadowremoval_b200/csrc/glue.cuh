@@ -125,6 +125,29 @@ __global__ void assemble_uv_kernel(T* __restrict__ x, int ld, const float* __res
   else stf<T>(x, pix * ld + z0 + (k - 3), 0.f);
 }
 
+// bf16 product-path version of assemble_uv_kernel: one thread per 16-byte (8-channel) chunk of the written range
+// [uv_off & ~7, ld): channels [uv_off, uv_off+3) = uv, everything above = 0, channels below uv_off are preserved.
+__global__ void assemble_uv_vec_kernel(bf16* __restrict__ x, int ld, const float* __restrict__ uvs, int uv_off, int n_pix) {
+  const int k0 = uv_off >> 3, nk = (ld >> 3) - k0;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_pix * nk) return;
+  const int k = k0 + (int)(idx % nk);
+  const size_t pix = (size_t)(idx / nk);
+  uint4* dst = reinterpret_cast<uint4*>(x + pix * ld + 8 * k);
+  uint4 w = make_uint4(0u, 0u, 0u, 0u);
+  if (8 * k < uv_off + 3) {                      // chunk holds preserved and / or uv channels
+    if (8 * k < uv_off) w = *dst;
+    bf16* e = reinterpret_cast<bf16*>(&w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = 8 * k + i;
+      if (c >= uv_off + 3) e[i] = __float2bfloat16_rn(0.f);
+      else if (c >= uv_off) e[i] = __float2bfloat16_rn(uvs[pix * 3 + (c - uv_off)]);
+    }
+  }
+  *dst = w;
+}
+
 // model.py:246-252: mask = tanh(conv2(y)); con = conv3(y); gs = grey*(1+mask)+con; dif = gs-grey;
 // mask22 = [relu(mask), 0, relu(-mask)].  raw[...,0] = conv2(y), raw[...,1] = conv3(y) (bias included).
 // Also writes gs as channel `gs_c` of the clr_conv1 input buffer and zeroes its pad channels.
