@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   uint8_t* sP_gen = smem_al + (sP - base);
   float* xch = reinterpret_cast<float*>(smem_al + (bars + 192 - base));      // [2][128] row max / row sum exchange
   const uint32_t b_rfull = bars + 192 + 1024, b_rempty = b_rfull + 16;       // residual ring of the staged epilogue
+  const uint32_t b_k2full = b_rfull + 32, b_k2empty = b_rfull + 48;          // pass 1: the V stages serve as K stages 2, 3
   uint8_t* sV_gen = smem_al + (sV - base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,6 +103,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_rfull + 8 * s, 1);
       mbar_init(b_rempty + 8 * s, 8);
+      mbar_init(b_k2full + 8 * s, 1);
+      mbar_init(b_k2empty + 8 * s, 1);
     }
     if (fuse_w == 2) {
       prefetch_tmap(&tmR1);
@@ -131,17 +134,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     }
     bool ok = true;
     for (int it = 0; it < 2 * AT_NK && ok; ++it) {
-      const int s = it & 1, f = it >> 1, j = it & (AT_NK - 1);
-      ok = mbar_wait(b_kempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 11);
+      const int j = it & (AT_NK - 1);
+      // Pass 1 (it < 8) has no V / P traffic, so the two V stages serve as K stages 2 and 3: four key tiles in flight
+      // instead of two (with two, every S MMA waited a full L2 round trip for its tile).  Each stage is used twice in
+      // pass 1, i.e. an even number of times, so the pass-2 parities of the K barriers are what they always were.
+      const bool p1 = it < AT_NK;
+      const int s = p1 ? (it & 3) : (it & 1), f = p1 ? (it >> 2) : (it >> 1);
+      const uint32_t kfull = s < 2 ? b_kfull + 8 * s : b_k2full + 8 * (s - 2);
+      const uint32_t kempty = s < 2 ? b_kempty + 8 * s : b_k2empty + 8 * (s - 2);
+      const uint32_t kdst = s < 2 ? sK + s * AT_TILE : sV + (s - 2) * AT_TILE;
+      ok = mbar_wait(kempty, (uint32_t)(f & 1) ^ 1u, errflag, 11);
       if (!ok) break;
       if (leader) {
-        mbar_expect_tx(b_kfull + 8 * s, AT_TILE);
-        tma_load_3d(sK + s * AT_TILE, &tmQK, b_kfull + 8 * s, 128, j * AT_BK, n);
-        tma_load_3d(sK + s * AT_TILE + AT_TILE / 2, &tmQK, b_kfull + 8 * s, 192, j * AT_BK, n);
+        mbar_expect_tx(kfull, AT_TILE);
+        tma_load_3d(kdst, &tmQK, kfull, 128, j * AT_BK, n);
+        tma_load_3d(kdst + AT_TILE / 2, &tmQK, kfull, 192, j * AT_BK, n);
       }
       if (it >= AT_NK) {
         const int vs = j & 1, vf = j >> 1;
-        ok = mbar_wait(b_vempty + 8 * vs, (uint32_t)(vf & 1) ^ 1u, errflag, 12);
+        // first V tile of a stage: the pass-1 S MMAs that read this stage as a K tile (second use) have retired
+        if (vf == 0) ok = mbar_wait(b_k2empty + 8 * vs, 1u, errflag, 30);
+        if (ok) ok = mbar_wait(b_vempty + 8 * vs, (uint32_t)(vf & 1) ^ 1u, errflag, 12);
         if (!ok) break;
         if (leader) {
           mbar_expect_tx(b_vfull + 8 * vs, AT_TILE);
@@ -212,9 +225,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       return true;
     };
     for (int it = 0; it < 2 * AT_NK && ok; ++it) {
-      const int s = it & 1, f = it >> 1;
+      const int s = it & 1, f = it >> 1;                     // S accumulator stage (TMEM double buffer)
+      const bool p1 = it < AT_NK;                            // pass 1: four K stages (see the producer)
+      const int ks = p1 ? (it & 3) : s, kf = p1 ? (it >> 2) : f;
+      const uint32_t kfull = ks < 2 ? b_kfull + 8 * ks : b_k2full + 8 * (ks - 2);
+      const uint32_t kempty = ks < 2 ? b_kempty + 8 * ks : b_k2empty + 8 * (ks - 2);
+      const uint32_t ksrc = ks < 2 ? sK + ks * AT_TILE : sV + (ks - 2) * AT_TILE;
       const long long c0 = AT_CLK();
-      ok = mbar_wait(b_kfull + 8 * s, (uint32_t)(f & 1), errflag, 16, true);
+      ok = mbar_wait(kfull, (uint32_t)(kf & 1), errflag, 16, true);
       if (!ok) break;
       const long long c1 = AT_CLK();
       ok = mbar_wait(b_sempty + 8 * s, (uint32_t)(f & 1) ^ 1u, errflag, 17, true);
@@ -225,12 +243,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint32_t a_lo = umma_desc_lo(sQ + kb * (AT_TILE / 2));
-          const uint32_t b_lo = umma_desc_lo(sK + s * AT_TILE + kb * (AT_TILE / 2));
+          const uint32_t b_lo = umma_desc_lo(ksrc + kb * (AT_TILE / 2));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_lo(tS0 + (uint32_t)s * 128, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(b_kempty + 8 * s);
+        umma_commit(kempty);
         umma_commit(b_sfull + 8 * s);
       }
       __syncwarp();
