@@ -101,6 +101,7 @@ struct TcWeights {
   int b_total_rows = 0;
   int b_res_kblocks = 1;
   int can_reside = 0;
+  int can_pin = 0;        // n_tiles > 1: ONE n-tile's rows fit in shared memory -> a CTA may keep "its" n-tile resident
   TcStep steps[TC_MAX_STEPS];
   TcStep* steps_dev = nullptr;
   bf16* dev = nullptr;
@@ -149,6 +150,9 @@ struct ConvTcParams {
   int pad_t, pad_l;           // SAME padding subtracted from the step shifts (plain convs)
   int a_sub;                  // A sub-tiles per stage (max n_a over the steps)
   int b_resident, b_total_rows;
+  int b_res_rows;             // weight rows resident per CTA: all of them, or one n-tile's (b_pinned)
+  int b_pinned;               // grid is a multiple of n_tiles, so CTA b only ever sees n-tile b % n_tiles and keeps just
+                              // that tile's rows resident (qkv: 3 x 80 KB would not fit, 80 KB does)
   int b_res_kblocks;          // resident weights: number of 64-element K blocks kept ([kblock][row] layout)
   int st_chunk;               // staged TMA-store epilogue: 0 = direct per-thread stores, 16 / 8 = columns per warp and
                               // iteration (an iteration = 4 x st_chunk columns = 32-channel SWIZZLE_64B boxes in smem)
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t a_bytes = TC_BM * 128;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
   const uint32_t sBres = smem_base + (uint32_t)p.n_stages * stage_bytes;            // resident weights (optional)
-  const uint32_t bars = sBres + (p.b_resident ? (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u : 0u);
+  const uint32_t bars = sBres + (p.b_resident ? (uint32_t)(p.b_res_kblocks * p.b_res_rows) * 128u : 0u);
   // full[8], empty[8], tmem_full[2], tmem_empty[2], bres, tmem slot
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_tfull = bars + 128, bar_tempty = bars + 144;
   const uint32_t bar_bres = bars + 160, tmem_slot = bars + 168;
@@ -266,10 +270,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t a_sub = (uint32_t)p.a_sub, b_kb_stride = (uint32_t)(p.stage_bytes / 128 - p.a_sub * TC_BM) / (uint32_t)p.a_sub;
       const int tiles_x = p.tiles_x, tile_h = p.bh * p.rows_per_tile, tile_w = p.bw * p.halves;
       if (b_resident && leader) {          // weights are static: fetched before the dependency wait
-        mbar_expect_tx(bar_bres, (uint32_t)(p.b_res_kblocks * p.b_total_rows) * 128u);
+        const int row0 = p.b_pinned ? (int)(blockIdx.x % (unsigned)p.n_tiles) * bn : 0;
+        mbar_expect_tx(bar_bres, (uint32_t)(p.b_res_kblocks * p.b_res_rows) * 128u);
         for (int kb = 0; kb < p.b_res_kblocks; ++kb)
-          for (int r = 0; r < p.b_total_rows; r += b_box_rows)
-            tma_load_2d(sBres + (uint32_t)(kb * p.b_total_rows + r) * 128u, &tmB, bar_bres, kb * TC_BK, r);
+          for (int r = 0; r < p.b_res_rows; r += b_box_rows)
+            tma_load_2d(sBres + (uint32_t)(kb * p.b_res_rows + r) * 128u, &tmB, bar_bres, kb * TC_BK, row0 + r);
       }
       const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
       long long t_wait = 0, t_dep = 0, t_tma = 0;
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t it = 0, tcount = 0;
       bool ok = true;
       const bool leader = elect_one();
-      const int b_resident = p.b_resident, b_total_rows = p.b_total_rows, bn = p.bn, ablate = p.ablate;
+      const int b_resident = p.b_resident, b_total_rows = p.b_res_rows, bn = p.bn, ablate = p.ablate;
       const uint32_t a_sub = (uint32_t)p.a_sub;
       // distance (in 16-byte units) between the weight rows of the two K blocks of a step
       const uint32_t b_kb_lo = b_resident ? (uint32_t)b_total_rows * 8u
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (!ok) break;
         tc_fence_after();
         const uint32_t acc = tmem_base + as * (uint32_t)bn;
-        const int brow_base = (tile % n_tiles) * bn;
+        const int brow_base = p.b_pinned ? 0 : (tile % n_tiles) * bn;
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
           const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
@@ -804,6 +809,10 @@ inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>
     // decided per launch: it only pays when a CTA processes many tiles
     t.can_reside = 1;
     t.b_res_kblocks = (int)(K / TC_BK);
+  } else if (!t.b_resident && t.kind == TC_CONV && t.n_tiles > 1 && (size_t)t.bn * K * 2 <= 150 * 1024 &&
+             !getenv("BSR_NO_RESIDENT") && !getenv("BSR_NO_PIN")) {
+    t.can_pin = 1;
+    t.b_res_kblocks = (int)(K / TC_BK);
   }
   t.ready = true;
   return true;
@@ -1141,9 +1150,13 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     p.group_phase[0] = phase < 0 ? 0 : phase;
   }
   p.total_tiles = n * p.tiles_x * p.tiles_y * t.n_tiles;
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  const bool resident = t.b_resident || (t.can_reside && p.total_tiles >= 6 * grid);
+  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const bool pinned = t.can_pin && p.total_tiles >= 6 * num_sms;
+  if (pinned) grid = num_sms / t.n_tiles * t.n_tiles;        // tile += grid keeps tile % n_tiles fixed per CTA
+  const bool resident = t.b_resident || pinned || (t.can_reside && p.total_tiles >= 6 * grid);
   p.b_resident = resident ? 1 : 0;
+  p.b_pinned = pinned ? 1 : 0;
+  p.b_res_rows = pinned ? t.bn : t.b_total_rows;
   // bias staging: 512 floats unless the layer provably reads fewer (frees shared memory for the store staging)
   const int bias_floats = (p.epi_mode == EPI_GENERIC && p.n_groups > 1 && p.group_cols <= 128) ? 128 : 512;
   const int epi_bytes = bias_floats * 4 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 258 * CLR_RS * 4 : 0));
@@ -1152,7 +1165,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.b_res_kblocks = t.b_res_kblocks;
   { const char* ab = getenv("BSR_ABLATE"); p.ablate = ab ? atoi(ab) : 0; }
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
-  const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * t.b_total_rows * 128 : 0) + 192 + p.steps_bytes + p.epi_bytes + 512 + 64;
+  const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * p.b_res_rows * 128 : 0) + 192 + p.steps_bytes + p.epi_bytes + 512 + 64;
   p.a_sub = t.a_sub;
   p.stage_bytes = t.a_sub * (TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128));
   const int max_smem = 227 * 1024;
