@@ -307,7 +307,10 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   if (ld > oc) {
     Step step(h, st, "res_tail");
     long long npix = (long long)n * FEAT * FEAT, tot = npix * (ld - oc);
-    res_tail_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const T*)cur, ld, (T*)nxt, ld, oc, ld, npix);
+    if (std::is_same<T, bf16>::value && ld % 8 == 0 && oc % 8 == 0)
+      res_tail_vec_kernel<<<(unsigned)((tot / 8 + 255) / 256), 256, 0, st>>>((const bf16*)cur, ld, (bf16*)nxt, ld, oc, ld, npix);
+    else
+      res_tail_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const T*)cur, ld, (T*)nxt, ld, oc, ld, npix);
     h->launches++;
   }
   return BSR_OK;

@@ -291,6 +291,24 @@ __global__ void res_tail_kernel(const T* __restrict__ x, int ldx, T* __restrict_
   stf<T>(out, pix * ldo + c, leaky(ldf<T>(x, pix * ldx + c)));
 }
 
+// bf16 product-path version: 8 channels (16 bytes) per thread; needs c0, c1, ldx, ldo multiples of 8.
+__global__ void res_tail_vec_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, int c0, int c1,
+                                    long long n_pix) {
+  const int span = (c1 - c0) >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * span) return;
+  const size_t pix = (size_t)(idx / span);
+  const int c = c0 + 8 * (int)(idx % span);
+  uint4 v = *reinterpret_cast<const uint4*>(x + pix * ldx + c);
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    h[i] = __floats2bfloat162_rn(leaky(f.x), leaky(f.y));
+  }
+  *reinterpret_cast<uint4*>(out + pix * ldo + c) = v;
+}
+
 // clr_conv2 (1x1 16->16 + BN + LeakyReLU), clr_conv3 (1x1 16->3) and the final
 // dif = grey(con_rgb) - grey(inputs)   (model.py:268-269, 288).  w2[16][16] (in,out), w3[16][3].
 template <typename T>
