@@ -154,8 +154,8 @@ struct ConvTcParams {
   int b_pinned;               // grid is a multiple of n_tiles, so CTA b only ever sees n-tile b % n_tiles and keeps just
                               // that tile's rows resident (qkv: 3 x 80 KB would not fit, 80 KB does)
   int b_res_kblocks;          // resident weights: number of 64-element K blocks kept ([kblock][row] layout)
-  int st_chunk;               // staged TMA-store epilogue: 0 = direct per-thread stores, 16 / 8 = columns per warp and
-                              // iteration (an iteration = 4 x st_chunk columns = 32-channel SWIZZLE_64B boxes in smem)
+  int st_chunk;               // staged TMA-store epilogue: 0 = direct per-thread stores, 16 = columns per warp and
+                              // iteration (an iteration = 64 columns = two 32-channel SWIZZLE_64B boxes in smem)
   int st_bufs;                // staging buffers: 2 = double-buffered, 1 = single (one more barrier per iteration)
   int steps_bytes, epi_bytes; // shared-memory bytes of the step program / epilogue scratch (multiples of 128)
   int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
   TcStep* steps = reinterpret_cast<TcStep*>(smem_al + (bars + 192 - smem_base));
   float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 + (uint32_t)p.steps_bytes - smem_base));
-  // output staging of the TMA-store epilogue: 2 buffers of 128 rows x (4 x st_chunk) bf16 columns
+  // output staging of the TMA-store epilogue: st_bufs buffers of 128 rows x 64 bf16 columns
   const uint32_t st_stage = (bars + 192 + (uint32_t)p.steps_bytes + (uint32_t)p.epi_bytes + 511u) & ~511u;   // 512 B = one 64B-swizzle atom
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.steps);
@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ---- staged epilogue: accumulators -> bf16 -> 64B-swizzled shared memory -> TMA store.  Per-thread-row global
         // stores touch 32 cache lines per warp instruction and (measured) slow the UMMA operand
         // reads that share the L1/shared-memory pipe; the bulk store reads the staged tile at full line width instead.
-        const int cw_ = p.st_chunk, group_cols = p.group_cols, total_cols = p.n_groups * group_cols;
-        const int iter_cols = 4 * cw_;
+        const int group_cols = p.group_cols, total_cols = p.n_groups * group_cols;
+        constexpr int cw_ = 16, iter_cols = 4 * cw_;
         const uint32_t buf_bytes = (uint32_t)iter_cols * 256u;                 // 128 rows x iter_cols bf16
         const int gx0 = (tr % p.tiles_x) * p.bw, gy0 = (tr / p.tiles_x) * p.bh * rows_per_tile;
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
@@ -439,15 +439,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           uint32_t o[8];
           if (col < total_cols) {
             float v[16];
-            if (cw_ == 16) tmem_ld16(acc + (uint32_t)col, v);
-            else tmem_ld8(acc + (uint32_t)col, v);
+            tmem_ld16(acc + (uint32_t)col, v);
             const int j = col % group_cols;                                    // channel inside the group
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              if (i < cw_) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j + i);
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-              }
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
             if (e.act) {
 #pragma unroll
@@ -474,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t a = rowb + ((pc0 ^ sw) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
             }
-            if (cw_ == 16) {
+            {
               const uint32_t a = rowb + (((pc0 + 1u) ^ sw) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
             }
