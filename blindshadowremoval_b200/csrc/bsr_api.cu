@@ -72,6 +72,8 @@ struct bsr_handle {
   size_t ev_used = 0;
   std::vector<std::pair<const char*, float>> times;
   // host-path staging
+  void* chunk_stage = nullptr;      // dense img | uv | reg | face planes of one micro-batch (bsr_forward_chunk)
+  size_t chunk_stage_bytes = 0;
   bool in_small = false;   // compact host path: uv/reg arrive already resized to 32x32
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -793,6 +795,7 @@ int bsr_destroy(bsr_handle* h) {
   for (auto& e : h->ev) cudaEventDestroy(e);
   if (h->arena) cudaFree(h->arena);
   if (h->stage) cudaFree(h->stage);
+  if (h->chunk_stage) cudaFree(h->chunk_stage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -939,6 +942,60 @@ int bsr_forward_tsm_host_compact(bsr_handle* h, const unsigned char* img_u8, con
   HostCompact cp;
   cp.img_u8 = img_u8; cp.rgb_u8 = rgb_u8; cp.dif_f16 = dif_f16;
   return forward_host(h, nullptr, uv32, reg32, n_chunks * frame, frame, share, gs, rgb, mask22, dif, cp);
+}
+
+int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int frame, int share, float* rgb_clipped,
+                      float* mask_pred, float* gs, float* mask22, void* cuda_stream) {
+  if (!h) return BSR_EINVAL;
+  if (!h->loaded) return fail(h, BSR_ESTATE, "bsr_load_weights has not been called");
+  if (!chunk || n <= 0 || !rgb_clipped || !mask_pred) return fail(h, BSR_EINVAL, "chunk, rgb_clipped, mask_pred must be non-NULL and n > 0");
+  int C, o_uv, o_reg, o_face;
+  switch (layout) {      // channel offsets of tf.split(img, [...], 3)
+    case BSR_CHUNK_GT: C = 16; o_uv = 6; o_reg = 9; o_face = 15; break;        // [3,3,3,6,1]
+    case BSR_CHUNK_SFW: C = 17; o_uv = 7; o_reg = 10; o_face = 16; break;      // [3,3,1,3,6,1]
+    case BSR_CHUNK_PLAIN: C = 13; o_uv = 3; o_reg = 6; o_face = 12; break;     // [3,3,6,1]
+    default: return fail(h, BSR_EINVAL, "bad chunk layout %d", layout);
+  }
+  const bool tsm = h->variant == BSR_VARIANT_TSM;
+  if (tsm && (frame <= 0 || n % frame)) return fail(h, BSR_EINVAL, "TSM needs n %% frame == 0");
+  if (tsm && frame > h->mb) return fail(h, BSR_EINVAL, "frame %d exceeds micro_batch %d", frame, h->mb);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int dev;
+  CK(h, cudaGetDevice(&dev));
+  if (dev != h->device) CK(h, cudaSetDevice(h->device));
+  int step = h->mb < n ? h->mb : n;
+  if (tsm) step = step / frame * frame;
+  const size_t px = (size_t)IMG * IMG, need = (size_t)step * px * 13 * sizeof(float);
+  if (need > h->chunk_stage_bytes) {
+    CK(h, cudaStreamSynchronize(st));                 // the old buffer may still be in use by an earlier call
+    if (h->chunk_stage) cudaFree(h->chunk_stage);
+    h->chunk_stage = nullptr;
+    h->chunk_stage_bytes = 0;
+    if (cudaMalloc(&h->chunk_stage, need) != cudaSuccess) return fail(h, BSR_ENOMEM, "chunk staging allocation of %zu bytes failed", need);
+    h->chunk_stage_bytes = need;
+  }
+  float* d_img = (float*)h->chunk_stage;
+  float* d_uv = d_img + (size_t)step * px * 3;
+  float* d_reg = d_uv + (size_t)step * px * 3;
+  float* d_face = d_reg + (size_t)step * px * 6;
+  int total = 0;
+  for (int i0 = 0; i0 < n; i0 += step) {
+    const int m = n - i0 < step ? n - i0 : step;
+    const long long mpx = (long long)m * px;
+    unpack_chunk_kernel<<<(unsigned)((mpx * 13 + 255) / 256), 256, 0, st>>>(chunk + (size_t)i0 * px * C, C, o_uv, o_reg, o_face,
+                                                                        d_img, d_uv, tsm ? d_reg : nullptr, d_face, mpx);
+    float* rgb_o = rgb_clipped + (size_t)i0 * px * 3;
+    float* mp_o = mask_pred + (size_t)i0 * px;
+    int rc = forward_common(h, d_img, d_uv, tsm ? d_reg : nullptr, m, frame, share, gs ? gs + (size_t)i0 * px : nullptr, rgb_o,
+                            mask22 ? mask22 + (size_t)i0 * px * 3 : nullptr, mp_o, st);
+    if (rc) return rc;
+    caller_glue_kernel<<<(unsigned)((mpx + 255) / 256), 256, 0, st>>>(rgb_o, mp_o, d_face, rgb_o, mp_o, mpx);   // in place
+    total += h->launches + 2;
+  }
+  CK(h, cudaGetLastError());
+  h->launches = total;
+  if (dev != h->device) cudaSetDevice(dev);
+  return BSR_OK;
 }
 
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n, float* rgb_clipped,

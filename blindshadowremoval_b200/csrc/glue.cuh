@@ -354,6 +354,22 @@ __global__ void clr_tail_kernel(const T* __restrict__ c16, int ld, const float* 
   }
 }
 
+// tf.split of the dataset chunk (train_test_GSC.py:419, 806, 870, 900): [n,256,256,C] interleaved -> dense img / uv /
+// reg / face planes.  One thread per (pixel, kept channel); o_* = first source channel of each piece, reg may be NULL.
+__global__ void unpack_chunk_kernel(const float* __restrict__ chunk, int C, int o_uv, int o_reg, int o_face,
+                                    float* __restrict__ img, float* __restrict__ uv, float* __restrict__ reg,
+                                    float* __restrict__ face, long long n_pix) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * 13) return;
+  const long long p = idx / 13;
+  const int k = (int)(idx - p * 13);
+  const float* src = chunk + p * C;
+  if (k < 3) img[p * 3 + k] = src[k];
+  else if (k < 6) uv[p * 3 + (k - 3)] = src[o_uv + (k - 3)];
+  else if (k < 12) { if (reg) reg[p * 6 + (k - 6)] = src[o_reg + (k - 6)]; }
+  else face[p] = src[o_face];
+}
+
 // train_test_GSC.py:808-809: mask_pred = dif*face ; rgb = clip(rgb, 0, 1)
 __global__ void caller_glue_kernel(const float* __restrict__ rgb, const float* __restrict__ dif,
                                    const float* __restrict__ face, float* __restrict__ rgb_c,

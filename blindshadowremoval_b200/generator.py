@@ -38,6 +38,7 @@ _SYMBOLS = {
     "bsr_forward_tsm_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4),
     "bsr_forward_gsc_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6),
     "bsr_forward_tsm_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 6),
+    "bsr_forward_chunk": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5),
     "bsr_caller_glue": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3),
     "bsr_composite": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t] + [ctypes.c_void_p] * 2),
     "bsr_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -66,6 +67,32 @@ def load_library(path: str = LIB_PATH):
 
 class BsrError(RuntimeError):
     pass
+
+
+# tf.split sizes of the dataset chunk by channel count (train_test_GSC.py:419, 806, 870, 900; train_with_TSM.py:675, 717)
+CHUNK_LAYOUTS = {
+    16: (0, ("img", 3), ("gt", 3), ("uv", 3), ("reg", 6), ("face", 1)),
+    17: (1, ("img", 3), ("cmap", 3), ("mask", 1), ("uv", 3), ("reg", 6), ("face", 1)),
+    13: (2, ("img", 3), ("uv", 3), ("reg", 6), ("face", 1)),
+}
+
+
+def unpack_chunk(chunk, frames: Optional[int] = None):
+    """``tf.reshape(img, [F, 256, 256, -1])`` + ``tf.split(img, [...], 3)`` of the reference's test steps: returns a
+    dict of channel-slice views (NumPy or torch) of a [F,256,256,C] chunk, C in {13, 16, 17}; any other shape is first
+    reshaped to ``[frames, 256, 256, -1]`` as the reference does (F = 10, or 2 for the SFW mirror pairs)."""
+    if chunk.ndim != 4 or tuple(chunk.shape[1:3]) != (IMG, IMG):
+        if not frames:
+            raise ValueError("a chunk that is not [F,256,256,C] needs `frames`")
+        chunk = chunk.reshape(frames, IMG, IMG, -1)
+    c = chunk.shape[-1]
+    if c not in CHUNK_LAYOUTS:
+        raise ValueError("chunk must have 13, 16 or 17 channels, got %d" % c)
+    out, o = {}, 0
+    for name, width in CHUNK_LAYOUTS[c][1:]:
+        out[name] = chunk[..., o:o + width]
+        o += width
+    return out
 
 
 def downsample8(x: np.ndarray) -> np.ndarray:
@@ -204,6 +231,44 @@ class Generator:
             rc = self._lib.bsr_forward_tsm_host(self._h, v(img_ptr), v(uv_ptr), v(reg_ptr), n // frame, frame, int(share),
                                                 v(gs_ptr), v(rgb_ptr), v(m22_ptr), v(dif_ptr))
         self._check(rc)
+
+    # -- chunk entry (SURVEY.md 8a row 0 + row 13) ---------------------------------------------
+    def forward_chunk(self, chunk, frame: Optional[int] = None, share=True, want_raw: bool = False):
+        """Body of the reference's test steps around the generator call (train_test_GSC.py:415-422, 802-809, 866-873,
+        896-903; train_with_TSM.py:671-678, 713-720): split the dataset chunk [F,256,256,C] (C = 13 / 16 / 17), run the
+        generator, ``mask_pred = dif * face``, ``rgb = clip(con_rgb, 0, 1)``.  ``chunk`` is a CUDA tensor (device path,
+        returns CUDA tensors) or a NumPy array (uploaded once, returns NumPy).  Returns ``(rgb, mask_pred)`` or, with
+        ``want_raw``, ``(rgb, mask_pred, gs, mask22)``."""
+        import torch
+        is_np = isinstance(chunk, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(chunk, dtype=np.float32)).cuda(self.device) if is_np else chunk
+        if t.dim() != 4 or tuple(t.shape[1:3]) != (IMG, IMG) or int(t.shape[3]) not in CHUNK_LAYOUTS:
+            raise ValueError("chunk must be [F,256,256,C] with C in {13, 16, 17}, got %r" % (tuple(t.shape),))
+        if not t.is_cuda:
+            raise BsrError("pass a CUDA tensor (device path) or a NumPy array")
+        n = int(t.shape[0])
+        if n <= 0:
+            raise ValueError("empty chunk")
+        if self.variant == "tsm":
+            if frame is None or frame <= 0:
+                raise ValueError("TSM variant needs frame > 0")
+            if n % frame:
+                raise ValueError("chunk of %d frames is not a multiple of frame %d (model_with_TSM.py:218)" % (n, frame))
+        share = bool(share.item() if hasattr(share, "item") else share)
+        t = t.contiguous().float()
+        dev = t.device
+        rgb = torch.empty((n, IMG, IMG, 3), device=dev)
+        mp = torch.empty((n, IMG, IMG, 1), device=dev)
+        gs = torch.empty((n, IMG, IMG, 1), device=dev) if want_raw else None
+        m22 = torch.empty((n, IMG, IMG, 3), device=dev) if want_raw else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        self._check(self._lib.bsr_forward_chunk(self._h, _ptr(t), n, CHUNK_LAYOUTS[int(t.shape[3])][0], int(frame or 1),
+                                                int(share), _ptr(rgb), _ptr(mp), _ptr(gs), _ptr(m22), stream))
+        outs = (rgb, mp, gs, m22) if want_raw else (rgb, mp)
+        if is_np:
+            torch.cuda.synchronize(dev)
+            return tuple(o.cpu().numpy() for o in outs)
+        return outs
 
     # -- compact host I/O (SURVEY.md 8f row 1) -----------------------------------------------
     def forward_compact(self, img_u8, uv32, reg32=None, frame: Optional[int] = None, share=True,

@@ -90,6 +90,19 @@ int bsr_forward_tsm_host_compact(bsr_handle* h, const unsigned char* img_u8, con
                                  float* gs, float* rgb, float* mask22, float* dif,
                                  unsigned char* rgb_u8, unsigned short* dif_f16);
 
+/* Chunk entry = the whole body of the reference's test steps around the generator call: the dataset hands them ONE
+ * tensor [n,256,256,C] (dataset.py:296-302) which they split along channels, feed to the generator and post-process:
+ *   BSR_CHUNK_GT    C=16  img3|gt3|uv3|reg6|face1         train_test_GSC.py:415-419, 866-870 (UCB / FFHQ with ground truth)
+ *   BSR_CHUNK_SFW   C=17  img3|cmap3|mask1|uv3|reg6|face1  train_test_GSC.py:802-806; train_with_TSM.py:671-675 (SFW labels)
+ *   BSR_CHUNK_PLAIN C=13  img3|uv3|reg6|face1              train_test_GSC.py:896-900; train_with_TSM.py:713-717
+ * then  _, rgb, _, mask_pred = gen(img, uv, reg, ...);  mask_pred *= face;  rgb = clip(rgb, 0, 1)  (:807-809, 871-873,
+ * 901-903).  Device pointers; `chunk` is read in place (one de-interleaving pass into a library-owned staging buffer
+ * that is allocated on the first chunk call); outputs rgb_clipped[n,256,256,3], mask_pred[n,256,256,1] and, optionally
+ * (may be NULL), the raw gs[n,256,256,1] / mask22[n,256,256,3].  frame / share are used by the TSM variant only. */
+enum { BSR_CHUNK_GT = 0, BSR_CHUNK_SFW = 1, BSR_CHUNK_PLAIN = 2 };
+int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int frame, int share,
+                      float* rgb_clipped, float* mask_pred, float* gs, float* mask22, void* cuda_stream);
+
 /* Caller glue, train_test_GSC.py:808-809 / 872-873 / 902-903 (TSM: train_with_TSM.py:677-678):
  * mask_pred = dif*face ; rgb_clipped = clip(rgb, 0, 1).  Device pointers; in-place allowed. */
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n,

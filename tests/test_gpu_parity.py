@@ -337,3 +337,45 @@ def test_compact_host_io_matches_fp32_path_bit_for_bit(G):
     with pytest.raises(ValueError):
         tsm.forward_compact(u8[:5], G.downsample8(six["uv"])[:5], G.downsample8(six["reg"])[:5], frame=2)
     tsm.close()
+
+
+def test_forward_chunk_equals_split_forward_and_caller_glue(G):
+    """SURVEY 8a rows 0 + 13: one dataset chunk [F,256,256,C] in, (clip(con_rgb), dif * face) out, for the three channel
+    layouts of the reference's test steps; must equal the explicit split -> generator -> caller glue sequence bit for bit
+    (the generator itself is checked against the oracle by the tests above)."""
+    from oracle.generator_ref import caller_glue as oracle_glue
+    w, d = case("gsc", 2, 1)
+    rng = np.random.default_rng(5)
+    n = 5
+    img, uv, reg = (np.concatenate([d[k]] * 3)[:n] for k in ("img", "uv", "reg"))
+    face = (rng.random((n, 256, 256, 1)) > 0.3).astype(np.float32)
+    gt, cmap, mask = rng.random((n, 256, 256, 3), dtype=np.float32), rng.random((n, 256, 256, 3), dtype=np.float32), face
+    gen = G.Generator("gsc", "bf16", device=0, micro_batch=2, weights=w)          # 5 images through a 2-image workspace
+    t = lambda a: torch.from_numpy(a).cuda()
+    _, rgb, _, dif = gen(t(img), t(uv), None, want=("con_rgb", "dif"))
+    rgb_c, mp = gen.caller_glue(rgb, dif, t(face))
+    for parts in ([img, gt, uv, reg, face], [img, cmap, mask, uv, reg, face], [img, uv, reg, face]):
+        chunk = np.concatenate(parts, axis=3)
+        r2, m2 = gen.forward_chunk(t(chunk))
+        assert torch.equal(r2, rgb_c) and torch.equal(m2, mp), chunk.shape
+    r3, m3, gs3, m22 = gen.forward_chunk(np.concatenate([img, uv, reg, face], axis=3), want_raw=True)   # NumPy in -> NumPy out
+    assert np.array_equal(r3, rgb_c.cpu().numpy()) and gs3.shape == (n, 256, 256, 1) and m22.shape == (n, 256, 256, 3)
+    assert gen.debug_read("errflag")[0] == 0
+    # the oracle's restatement of the caller glue (row 13) applied to the device's raw outputs gives the same bits
+    o_rgb, o_mp = oracle_glue(rgb.cpu().numpy(), dif.cpu().numpy(), face)
+    assert np.array_equal(o_rgb, r3) and np.array_equal(o_mp, mp.cpu().numpy())
+    with pytest.raises(ValueError):
+        gen.forward_chunk(t(np.zeros((1, 256, 256, 12), np.float32)))
+    gen.close()
+    # TSM: reg is consumed; chunk of 2 mirror frames (train_with_TSM.py:671-678)
+    wt, dt = case("tsm", 4, 2)
+    tsm = G.Generator("tsm", "bf16", device=0, micro_batch=4, weights=wt)
+    f4 = (rng.random((4, 256, 256, 1)) > 0.3).astype(np.float32)
+    _, rgb_t, _, dif_t = tsm(t(dt["img"]), t(dt["uv"]), t(dt["reg"]), frame=2, want=("con_rgb", "dif"))
+    rc_t, mp_t = tsm.caller_glue(rgb_t, dif_t, t(f4))
+    chunk = np.concatenate([dt["img"], cmap[:4], f4, dt["uv"], dt["reg"], f4], axis=3)                    # C = 17
+    r4, m4 = tsm.forward_chunk(t(chunk), frame=2, share=True)
+    assert torch.equal(r4, rc_t) and torch.equal(m4, mp_t)
+    with pytest.raises(ValueError):
+        tsm.forward_chunk(t(chunk[:3]), frame=2)
+    tsm.close()

@@ -138,3 +138,23 @@ def test_compact_input_helpers_match_reference_arithmetic():
     assert got.shape == (2, 32, 32, 6) and np.abs(got - ref).max() < 1e-6
     with pytest.raises(ValueError):
         generator.downsample8(x[:, :128])
+
+
+def test_unpack_chunk_matches_reference_split_sizes():
+    """tf.split(img, [3,3,3,6,1] / [3,3,1,3,6,1] / [3,3,6,1], 3) after the reshape to [F,256,256,-1]."""
+    rng = np.random.default_rng(1)
+    for c, names in ((16, ["img", "gt", "uv", "reg", "face"]), (17, ["img", "cmap", "mask", "uv", "reg", "face"]),
+                     (13, ["img", "uv", "reg", "face"])):
+        chunk = rng.random((2, 256, 256, c), dtype=np.float32)
+        parts = generator.unpack_chunk(chunk)
+        assert list(parts) == names
+        assert np.array_equal(np.concatenate([parts[k] for k in names], axis=3), chunk)
+        assert parts["img"].shape[3] == 3 and parts["uv"].shape[3] == 3 and parts["reg"].shape[3] == 6 and parts["face"].shape[3] == 1
+        flat = generator.unpack_chunk(chunk.reshape(-1), frames=2)                # the reference reshapes a flat record
+        assert np.array_equal(flat["uv"], parts["uv"])
+        t = generator.unpack_chunk(torch.from_numpy(chunk))                       # torch tensors slice the same way
+        assert torch.equal(t["reg"], torch.from_numpy(parts["reg"]))
+    with pytest.raises(ValueError):
+        generator.unpack_chunk(np.zeros((1, 256, 256, 12), np.float32))
+    with pytest.raises(ValueError):
+        generator.unpack_chunk(np.zeros(5, np.float32))
