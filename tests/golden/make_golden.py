@@ -15,7 +15,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from blindshadowremoval_b200.synthetic import make_inputs  # noqa: E402
 from blindshadowremoval_b200.tf_checkpoint import generator_variables  # noqa: E402
