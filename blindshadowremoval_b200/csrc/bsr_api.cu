@@ -692,6 +692,36 @@ extern "C" {
 
 const char* bsr_version(void) { return "bsr-b200 0.1 (sm_100a)"; }
 
+// CRC-32C, reflected polynomial 0x82F63B78, slicing-by-8 (host only)
+unsigned int bsr_crc32c(unsigned int crc, const void* data, size_t n) {
+  static uint32_t tab[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+      tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xffu];
+    init = true;
+  }
+  const unsigned char* p = (const unsigned char*)data;
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tab[7][lo & 0xffu] ^ tab[6][(lo >> 8) & 0xffu] ^ tab[5][(lo >> 16) & 0xffu] ^ tab[4][lo >> 24] ^
+        tab[3][hi & 0xffu] ^ tab[2][(hi >> 8) & 0xffu] ^ tab[1][(hi >> 16) & 0xffu] ^ tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ tab[0][(c ^ *p++) & 0xffu];
+  return ~c;
+}
+
 const char* bsr_last_error(const bsr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int bsr_create(int variant, int precision, int device, int micro_batch, bsr_handle** out) {

@@ -28,6 +28,7 @@ FEAT = 32
 _F = ctypes.POINTER(ctypes.c_float)
 _SYMBOLS = {
     "bsr_version": (ctypes.c_char_p, []),
+    "bsr_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t]),
     "bsr_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "bsr_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "bsr_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),

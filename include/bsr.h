@@ -37,6 +37,11 @@ enum {
 #define BSR_FEAT 32   /* bottleneck resolution after three stride-2 convs, model.py:231-234 */
 
 const char* bsr_version(void);
+/* Host utility for the checkpoint converter (no device work): CRC-32C (Castagnoli) of `n` bytes, the checksum
+ * TensorFlow stores (masked) per leveldb block of `ckpt-N.index` and per tensor in BundleEntryProto.crc32c - what
+ * `checkpoint.restore` verifies (train_test_GSC.py:362-365).  crc = 0 starts a new checksum; pass the previous result
+ * to continue one. */
+unsigned int bsr_crc32c(unsigned int crc, const void* data, size_t n);
 
 /* Replaces `self.gen = Generator()` (train_test_GSC.py:120).  micro_batch = images resident in the
  * workspace at once (forward loops over larger batches); for TSM it must be >= frame. */
