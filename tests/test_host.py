@@ -158,3 +158,16 @@ def test_unpack_chunk_matches_reference_split_sizes():
         generator.unpack_chunk(np.zeros((1, 256, 256, 12), np.float32))
     with pytest.raises(ValueError):
         generator.unpack_chunk(np.zeros(5, np.float32))
+
+
+def test_ssim_matches_definition_on_simple_cases():
+    from blindshadowremoval_b200.metrics import ssim
+    rng = np.random.default_rng(2)
+    a = rng.random((64, 64, 1))
+    assert abs(ssim(a, a) - 1.0) < 1e-12                                          # identical images
+    assert ssim(a, 1.0 - a) < 0.0                                                 # anti-correlated structure
+    c = np.full((32, 32, 1), 0.25)
+    d = np.full((32, 32, 1), 0.75)                                                # constants: luminance term only
+    lum = (2 * 0.25 * 0.75 + 1e-4) / (0.25 ** 2 + 0.75 ** 2 + 1e-4)
+    assert abs(ssim(c, d) - lum) < 1e-9
+    assert abs(ssim(a[..., 0], a[..., 0] * 0.5 + 0.1) - ssim(a, a * 0.5 + 0.1)) < 1e-12   # [H,W] accepted

@@ -50,3 +50,54 @@ def test_two_rank_sharding_and_metric_reduce():
 def test_reduce_metrics_single_process():
     out = sharding.reduce_metrics({"ssim": 3.0}, 4)
     assert out == {"ssim": 0.75, "count": 4.0}
+
+
+class _FakeGen:
+    """Stands in for the CUDA generator in the CPU test of the evaluation loop: a deterministic function of the chunk."""
+
+    def forward_chunk(self, chunk, frame=None, share=True):
+        import numpy as np
+        img, mask, face = chunk[..., 0:3], chunk[..., 6:7], chunk[..., 16:17]
+        pred = (0.8 * (mask == 2) + 0.1 * img[..., 0:1]) * face
+        return np.clip(img, 0, 1), pred.astype(np.float32)
+
+
+def _chunk(i):
+    import numpy as np
+    rng = np.random.default_rng(100 + i)
+    c = rng.random((2, 256, 256, 17), dtype=np.float32)
+    c[..., 6] = rng.integers(0, 3, (2, 256, 256))                  # SFW label map {0,1,2}
+    c[..., 16] = (rng.random((2, 256, 256)) > 0.2)
+    return c
+
+
+def _eval_worker(rank, world, port, n_chunks, q):
+    from blindshadowremoval_b200.evaluate import evaluate_sfw
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q.put((rank, evaluate_sfw(_FakeGen(), _chunk, n_chunks, frame=2, rank=rank, world=world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_sfw_evaluation_equals_single_process():
+    """Config 3 host logic: chunks of 2 frames dealt to 2 ranks, one all-reduce -> every rank holds the means a single
+    process computes over all chunks (train_with_TSM.py:633-637 + utils.py:136-171)."""
+    from blindshadowremoval_b200.evaluate import evaluate_sfw
+    n_chunks = 5
+    ref = evaluate_sfw(_FakeGen(), _chunk, n_chunks, frame=2)
+    assert ref["count"] == n_chunks and 0.5 < ref["auc"] <= 1.0 and ref["psnr"] > 0 and -1 <= ref["ssim"] <= 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, n_chunks, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        assert out["count"] == n_chunks
+        for k in ("auc", "psnr", "ssim"):
+            assert abs(out[k] - ref[k]) < 1e-9, (k, out[k], ref[k])
