@@ -379,3 +379,27 @@ def test_forward_chunk_equals_split_forward_and_caller_glue(G):
     with pytest.raises(ValueError):
         tsm.forward_chunk(t(chunk[:3]), frame=2)
     tsm.close()
+
+
+def test_evaluate_sfw_runs_on_device_and_matches_manual_metrics(G):
+    """Config 3 on one GPU: two SFW-style chunks (frame = 2, 17 channels) through evaluate_sfw with the real TSM
+    generator; the means equal metrics computed by hand from gen.forward_chunk outputs."""
+    from blindshadowremoval_b200.evaluate import evaluate_sfw
+    from blindshadowremoval_b200.metrics import ssim
+    wt, dt = case("tsm", 4, 2)
+    rng = np.random.default_rng(11)
+    chunks = []
+    for k in range(2):
+        sl = slice(2 * k, 2 * k + 2)
+        label = rng.integers(0, 3, (2, 256, 256, 1)).astype(np.float32)
+        face = (rng.random((2, 256, 256, 1)) > 0.2).astype(np.float32)
+        chunks.append(np.concatenate([dt["img"][sl], rng.random((2, 256, 256, 3), dtype=np.float32), label, dt["uv"][sl],
+                                      dt["reg"][sl], face], axis=3))
+    gen = G.Generator("tsm", "bf16", device=0, micro_batch=2, weights=wt)
+    seen = []
+    out = evaluate_sfw(gen, lambda i: chunks[i], 2, frame=2, on_result=lambda i, rgb, mp: seen.append((i, mp[0])))
+    assert out["count"] == 2 and [i for i, _ in seen] == [0, 1]
+    auc = np.mean([sfw_auc((chunks[i][0, ..., 6:7] == 2), mp) for i, mp in seen])
+    ss = np.mean([ssim(chunks[i][0, ..., 6:7], mp) for i, mp in seen])
+    assert abs(out["auc"] - auc) < 1e-12 and abs(out["ssim"] - ss) < 1e-12 and np.isfinite(out["psnr"])
+    gen.close()
