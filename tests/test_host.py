@@ -171,3 +171,30 @@ def test_ssim_matches_definition_on_simple_cases():
     lum = (2 * 0.25 * 0.75 + 1e-4) / (0.25 ** 2 + 0.75 ** 2 + 1e-4)
     assert abs(ssim(c, d) - lum) < 1e-9
     assert abs(ssim(a[..., 0], a[..., 0] * 0.5 + 0.1) - ssim(a, a * 0.5 + 0.1)) < 1e-12   # [H,W] accepted
+
+
+def test_bench_layer_work_matches_survey_mac_table():
+    """The roofline numerators bench.py reports are SURVEY.md Appendix B / section 8d: per-layer MACs and the network
+    totals 9052.1 (GSC) / 10085.1 (TSM) MMAC per image."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for variant, total in (("gsc", 9052.1), ("tsm", 10085.1)):
+        L = bench.layer_work(variant)
+        mmac = {k: v[0] / 2e6 for k, v in L.items()}
+        convs = sum(v for k, v in mmac.items() if k not in ("compose", "clr_tail"))
+        tail = mmac["clr_tail"]                                   # clr_conv2 + clr_conv3 = 16.8 + 3.1
+        assert abs(tail - 19.9) < 0.1
+        assert abs(convs + tail - total) < 0.6, (variant, convs + tail)
+    g = {k: v[0] / 2e6 for k, v in bench.layer_work("gsc").items()}
+    for name, want in (("conv1", 308.3), ("down1", 302.0), ("down2", 151.0), ("down3", 56.6), ("res0.conv1", 13.0),
+                       ("res1.conv1", 33.7), ("res3.conv1", 34.2), ("res2.conv2", 151.0), ("res4.conv3", 33.7),
+                       ("res0.qkv", 3 * 33.7), ("res5.attention", 2 * 134.2), ("res1.w", 33.7), ("up1", 227.4),
+                       ("up2", 377.5), ("up3", 1208.0), ("heads", 2 * 205.5), ("clr_up1", 307.9), ("clr_up2", 453.0),
+                       ("clr_up3", 906.0), ("clr_conv1", 613.4)):
+        assert abs(g[name] - want) < 0.06 * max(1.0, want / 100), (name, g[name], want)
+    t = {k: v[0] / 2e6 for k, v in bench.layer_work("tsm").items()}
+    assert abs(t["res0.conv1"] - 38.1) < 0.1 and abs(t["res4.conv1"] - 115.0) < 0.1 and abs(t["clr_up1"] - 1034.6) < 0.1
+    # bytes: every fused unit moves at least its unique input + output once
+    assert all(v[1] > 0 for v in bench.layer_work("gsc").values())
