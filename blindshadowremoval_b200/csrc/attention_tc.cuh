@@ -1,13 +1,13 @@
-// Fused non-local attention on tcgen05 (bf16 in, fp32 logits / softmax / accumulate):
+// Fused non-local attention on tcgen05 (h16 in, fp32 logits / softmax / accumulate):
 //   y = softmax(theta . phi^T) . g      S = 1024 tokens, d = 128, one head, logits NOT scaled
 // (/root/reference/model.py:51-53).  The 1024x1024 logit matrix never leaves the SM.
 //
 // One CTA per (image, 128-query tile).  Two passes over the 8 key tiles of 128:
 //   pass 1: S_j = Q.K_j^T in TMEM (double buffered) -> running row max in registers;
-//   pass 2: S_j again -> p = exp(s - max) -> bf16 P tile in swizzled smem -> O += P.V_j in TMEM.
+//   pass 2: S_j again -> p = exp(s - max) -> h16 P tile in swizzled smem -> O += P.V_j in TMEM.
 // Recomputing QK^T costs 1.5x the attention MMAs but needs no accumulator rescaling; the unscaled
 // logits of this network make an exact (not running) max the safest choice as well.
-// Layouts: QK[n][1024][256] = theta | phi (bf16);  VT[n][128][1024] = g transposed (so every UMMA
+// Layouts: QK[n][1024][256] = theta | phi (h16);  VT[n][128][1024] = g transposed (so every UMMA
 // operand is K-major);  O[n][1024][128].
 // Warp roles (320 threads): warps 0-7 softmax / epilogue (4 TMEM lane quarters x 2 column halves), warp 8 TMA,
 // warp 9 TMEM alloc + MMA issue (single-thread roles get the highest warp ids: the arbiter favours high ids).
@@ -23,16 +23,16 @@ namespace bsr {
 
 constexpr int AT_S = 1024, AT_D = 128, AT_BQ = 128, AT_BK = 128;
 constexpr int AT_NK = AT_S / AT_BK;                   // 8 key tiles
-constexpr uint32_t AT_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 bf16] as two 16 KB k-blocks
+constexpr uint32_t AT_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 h16] as two 16 KB k-blocks
 constexpr size_t kAttnTcSmem = 1024 + 7 * (size_t)AT_TILE + 192 + 1024 + 64;   // Q, K x2, V x2, P x2, barriers, exchange, residual-ring barriers
 
-__device__ __forceinline__ void add_bf16x16_attn(const uint4& a, const uint4& b, float* v) {
+__device__ __forceinline__ void add_h16x16_attn(const uint4& a, const uint4& b, float* v) {
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-    v[2 * i] += __low2float(t);
-    v[2 * i + 1] += __high2float(t);
+    const float2 t = unpack_h16x2(w[i]);
+    v[2 * i] += t.x;
+    v[2 * i + 1] += t.y;
   }
 }
 
@@ -45,7 +45,7 @@ constexpr int AT_THREADS = 320;      // warps 0-7 softmax / epilogue, warp 8 TMA
 
 // fuse_w = 1: the NonLocalBlock output conv w (1x1, 128 -> 257, BN folded) and the ResBottleneck tail run here too:
 //   out = LeakyReLU(x_in + y + W_w . O + b)      (model.py:56-59, 105-113)
-// O (bf16) goes to shared memory as the A operand of one more GEMM (N = 144 + 128 accumulator columns reuse the S / O
+// O (h16) goes to shared memory as the A operand of one more GEMM (N = 144 + 128 accumulator columns reuse the S / O
 // TMEM columns, W_w lands in the Q/K buffers once the last S MMA has retired) and never reaches HBM.
 // fuse_w = 2: same, with the block-tail epilogue staged through shared memory: the residual tiles (y, x_in) arrive by
 //   TMA into the retired V stages (ring of two 64-channel batches) and the result leaves by TMA bulk stores from the
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap tmR1,
                                                                      const __grid_constant__ CUtensorMap tmR2,
                                                                      const __grid_constant__ CUtensorMap tmOut,
-                                                                     bf16* __restrict__ o, const EpiParams e,
+                                                                     h16* __restrict__ o, const EpiParams e,
                                                                      const int fuse_w, int* errflag,
                                                                      long long* timers) {
   extern __shared__ uint8_t smem_raw[];
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       __syncwarp();
     }
     if (fuse_w && ok) {
-      // W_w (288 rows x 128 K, bf16, 72 KB) replaces Q and the K stages once S_14 / S_15 have retired
+      // W_w (288 rows x 128 K, h16, 72 KB) replaces Q and the K stages once S_14 / S_15 have retired
       ok = mbar_wait(b_kempty, (uint32_t)((AT_NK) & 1) ^ 1u, errflag, 22);
       if (ok) ok = mbar_wait(b_kempty + 8, (uint32_t)((AT_NK) & 1) ^ 1u, errflag, 23);
       if (ok && leader) {
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   } else if (warp == 9) {
     // ================= MMA issuer (converged warp, elected lane issues) =================
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint32_t idesc = umma_idesc_h16(128, 128);
     long long t_k = 0, t_se = 0, t_p = 0, t_v = 0, t_w = 0;
     const long long t0m = AT_CLK();
     bool ok = mbar_wait(b_q, 0, errflag, 13, true);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           const uint32_t a_lo = umma_desc_lo(sP + ps * AT_TILE + kb * (AT_TILE / 2));
           const uint32_t b_lo = umma_desc_lo(sV + vs * AT_TILE + kb * (AT_TILE / 2));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_lo(tO, a_lo + 2 * k, b_lo + 2 * k, idesc, (j | kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_h16_lo(tO, a_lo + 2 * k, b_lo + 2 * k, idesc, (j | kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(b_pempty + 8 * ps);
         umma_commit(b_vempty + 8 * vs);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           const uint32_t b_lo = umma_desc_lo(ksrc + kb * (AT_TILE / 2));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_lo(tS0 + (uint32_t)s * 128, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_h16_lo(tS0 + (uint32_t)s * 128, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(kempty);
         umma_commit(b_sfull + 8 * s);
@@ -260,19 +260,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const long long t1m = AT_CLK();
     if (fuse_w && ok) {
       ok = mbar_wait(b_wfull, 0, errflag, 24, true);
-      if (ok) ok = mbar_wait(b_a2full, 0, errflag, 25, true);      // O (bf16) is in sP[0]; S / O TMEM columns are drained
+      if (ok) ok = mbar_wait(b_a2full, 0, errflag, 25, true);      // O (h16) is in sP[0]; S / O TMEM columns are drained
       t_w = AT_CLK() - t1m;
       tc_fence_after();
       if (ok && leader) {
-        const uint32_t id144 = umma_idesc_bf16(128, 144), id128 = umma_idesc_bf16(128, 128);
+        const uint32_t id144 = umma_idesc_h16(128, 144), id128 = umma_idesc_h16(128, 128);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint32_t a_lo = umma_desc_lo(sP + kb * (AT_TILE / 2));
           const uint32_t b_lo = umma_desc_lo(sQ + kb * (288 * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16_lo(tmem, a_lo + 2 * k, b_lo + 2 * k, id144, (kb | k) != 0 ? 1u : 0u);
-            umma_bf16_lo(tmem + 144, a_lo + 2 * k, b_lo + (144 * 8) + 2 * k, id128, (kb | k) != 0 ? 1u : 0u);
+            umma_h16_lo(tmem, a_lo + 2 * k, b_lo + 2 * k, id144, (kb | k) != 0 ? 1u : 0u);
+            umma_h16_lo(tmem + 144, a_lo + 2 * k, b_lo + (144 * 8) + 2 * k, id128, (kb | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(b_d2full);
@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     if (fuse_w) {
       // the residual rows (x_in, y) of this thread are needed ~15 us from now: pull them from HBM into L2 already
       const size_t pixp = (size_t)n * AT_S + q0 + row;
-      const char* r1p = (const char*)((const bf16*)e.res1 + pixp * e.res1_ld + h * 144);
-      const char* r2p = (const char*)((const bf16*)e.res2 + pixp * e.res2_ld + h * 144);
+      const char* r1p = (const char*)((const h16*)e.res1 + pixp * e.res1_ld + h * 144);
+      const char* r2p = (const char*)((const h16*)e.res2 + pixp * e.res2_ld + h * 144);
 #pragma unroll
       for (int b = 0; b < 288; b += 128) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(r1p + b));
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     asm volatile("bar.sync 1, 256;" ::: "memory");
     mx = fmaxf(xch[row], xch[128 + row]);
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    // ---- pass 2: p = exp(s - max), P -> smem (bf16, 128B-swizzled K-major), row sum
+    // ---- pass 2: p = exp(s - max), P -> smem (h16, 128B-swizzled K-major), row sum
     const float mneg = -mx * kLog2e;
     float sum = 0.f;
     for (int j = 0; j < AT_NK && ok; ++j) {
@@ -357,10 +357,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         for (int g = 0; g < 4; ++g) {
           const int ch = (c >> 3) + g;                                // 16-byte chunk inside the 128-byte row
           uint4 w;
-          w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-          w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-          w.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-          w.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+          w.x = pack_h16x2(v[8 * g + 0], v[8 * g + 1]);
+          w.y = pack_h16x2(v[8 * g + 2], v[8 * g + 3]);
+          w.z = pack_h16x2(v[8 * g + 4], v[8 * g + 5]);
+          w.w = pack_h16x2(v[8 * g + 6], v[8 * g + 7]);
           *reinterpret_cast<uint4*>(blk + ((ch ^ (row & 7)) << 4)) = w;
         }
       }
@@ -379,14 +379,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       for (int i = threadIdx.x; i < 288; i += 256) bias_s[i] = __ldg(e.bias + i);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     sum = xch[row] + xch[128 + row];
-    // ---- epilogue: O / sum -> bf16 (each warp its 64 output channels)
+    // ---- epilogue: O / sum -> h16 (each warp its 64 output channels)
     const long long t1s = AT_CLK();
     if (ok) ok = mbar_wait(b_ofull, 0, errflag, 21);
     const long long t2s = AT_CLK();
     tc_fence_after();
     if (ok && !fuse_w) {
       const float inv = 1.f / sum;
-      bf16* dst = o + ((size_t)n * AT_S + q0 + row) * AT_D + h * 64;
+      h16* dst = o + ((size_t)n * AT_S + q0 + row) * AT_D + h * 64;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         float v[32];
@@ -394,16 +394,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 w;
-          w.x = pack_bf16x2(v[8 * g + 0] * inv, v[8 * g + 1] * inv);
-          w.y = pack_bf16x2(v[8 * g + 2] * inv, v[8 * g + 3] * inv);
-          w.z = pack_bf16x2(v[8 * g + 4] * inv, v[8 * g + 5] * inv);
-          w.w = pack_bf16x2(v[8 * g + 6] * inv, v[8 * g + 7] * inv);
+          w.x = pack_h16x2(v[8 * g + 0] * inv, v[8 * g + 1] * inv);
+          w.y = pack_h16x2(v[8 * g + 2] * inv, v[8 * g + 3] * inv);
+          w.z = pack_h16x2(v[8 * g + 4] * inv, v[8 * g + 5] * inv);
+          w.w = pack_h16x2(v[8 * g + 6] * inv, v[8 * g + 7] * inv);
           *reinterpret_cast<uint4*>(dst + c + 8 * g) = w;
         }
       }
     }
     if (ok && fuse_w) {
-      // O / sum -> bf16 A operand in sP[0] (same swizzled K-major layout as P: this warp's 64 channels = k-block h)
+      // O / sum -> h16 A operand in sP[0] (same swizzled K-major layout as P: this warp's 64 channels = k-block h)
       const float inv = 1.f / sum;
       uint8_t* blk = sP_gen + h * (AT_TILE / 2) + row * 128;
 #pragma unroll
@@ -414,10 +414,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         for (int g = 0; g < 4; ++g) {
           const int ch = (c >> 3) + g;
           uint4 w;
-          w.x = pack_bf16x2(v[8 * g + 0] * inv, v[8 * g + 1] * inv);
-          w.y = pack_bf16x2(v[8 * g + 2] * inv, v[8 * g + 3] * inv);
-          w.z = pack_bf16x2(v[8 * g + 4] * inv, v[8 * g + 5] * inv);
-          w.w = pack_bf16x2(v[8 * g + 6] * inv, v[8 * g + 7] * inv);
+          w.x = pack_h16x2(v[8 * g + 0] * inv, v[8 * g + 1] * inv);
+          w.y = pack_h16x2(v[8 * g + 2] * inv, v[8 * g + 3] * inv);
+          w.z = pack_h16x2(v[8 * g + 4] * inv, v[8 * g + 5] * inv);
+          w.w = pack_h16x2(v[8 * g + 6] * inv, v[8 * g + 7] * inv);
           *reinterpret_cast<uint4*>(blk + ((ch ^ (row & 7)) << 4)) = w;
         }
       }
@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         const size_t pix = (size_t)n * AT_S + q0 + row;
         uint4 ra[2], rb[2];
         if (h == 0) {
-          const uint4* s1 = reinterpret_cast<const uint4*>((const bf16*)e.res1 + pix * e.res1_ld + 256);
-          const uint4* s2 = reinterpret_cast<const uint4*>((const bf16*)e.res2 + pix * e.res2_ld + 256);
+          const uint4* s1 = reinterpret_cast<const uint4*>((const h16*)e.res1 + pix * e.res1_ld + 256);
+          const uint4* s2 = reinterpret_cast<const uint4*>((const h16*)e.res2 + pix * e.res2_ld + 256);
           ra[0] = s1[0]; ra[1] = s1[1]; rb[0] = s2[0]; rb[1] = s2[1];
         }
         ok = mbar_wait(b_d2full, 0, errflag, 26);
@@ -445,14 +445,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
-          add_bf16x16_attn(a0, a1, v);
-          add_bf16x16_attn(b0, b1, v);
+          add_h16x16_attn(a0, a1, v);
+          add_h16x16_attn(b0, b1, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
-          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          o0.x = pack_h16x2(v[0], v[1]); o0.y = pack_h16x2(v[2], v[3]);
+          o0.z = pack_h16x2(v[4], v[5]); o0.w = pack_h16x2(v[6], v[7]);
+          o1.x = pack_h16x2(v[8], v[9]); o1.y = pack_h16x2(v[10], v[11]);
+          o1.z = pack_h16x2(v[12], v[13]); o1.w = pack_h16x2(v[14], v[15]);
         };
         const uint32_t rowo = (uint32_t)row * 128u, sw = (uint32_t)row & 7u;
         for (int b = 0; b < 4 && ok; ++b) {
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           tmem_ld16(tmem + lane_addr + 256u, v);
           uint4 o0, o1;
           finish16(v, 256, ra[0], ra[1], rb[0], rb[1], o0, o1);
-          uint4* d = reinterpret_cast<uint4*>((bf16*)e.out + pix * e.out_ld + e.out_coff + 256);
+          uint4* d = reinterpret_cast<uint4*>((h16*)e.out + pix * e.out_ld + e.out_coff + 256);
           d[0] = o0;
           d[1] = o1;
         }
@@ -507,9 +507,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       // second GEMM's epilogue: warp half h owns accumulator columns [h*144, h*144 + (h ? 128 : 144))
       const size_t pix = (size_t)n * AT_S + q0 + row;
       const int c_begin = h * 144, c_end = h ? 272 : 144;
-      const bf16* r1 = (const bf16*)e.res1 + pix * e.res1_ld;
-      const bf16* r2 = (const bf16*)e.res2 + pix * e.res2_ld;
-      bf16* dst = (bf16*)e.out + pix * e.out_ld + e.out_coff;
+      const h16* r1 = (const h16*)e.res1 + pix * e.res1_ld;
+      const h16* r2 = (const h16*)e.res2 + pix * e.res2_ld;
+      h16* dst = (h16*)e.out + pix * e.out_ld + e.out_coff;
       // residual operands are fetched in batches of four 16-channel chunks (16 independent 16-byte loads in flight per
       // thread); the first batch is requested before the accumulator wait
       uint4 pa[4][2], pb[4][2];
@@ -550,15 +550,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
-              add_bf16x16_attn(pa[k][0], pa[k][1], v);
-              add_bf16x16_attn(pb[k][0], pb[k][1], v);
+              add_h16x16_attn(pa[k][0], pa[k][1], v);
+              add_h16x16_attn(pb[k][0], pb[k][1], v);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
               uint4 o0, o1;
-              o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-              o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-              o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-              o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+              o0.x = pack_h16x2(v[0], v[1]); o0.y = pack_h16x2(v[2], v[3]);
+              o0.z = pack_h16x2(v[4], v[5]); o0.w = pack_h16x2(v[6], v[7]);
+              o1.x = pack_h16x2(v[8], v[9]); o1.y = pack_h16x2(v[10], v[11]);
+              o1.z = pack_h16x2(v[12], v[13]); o1.w = pack_h16x2(v[14], v[15]);
               uint4* d = reinterpret_cast<uint4*>(dst + c);
               d[0] = o0;
               d[1] = o1;
@@ -582,9 +582,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 }
 
 // w_map != nullptr: fused output conv (see kernel comment); `e` then carries bias / residuals / output of the block.
-inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, bf16* o, int n, int* errflag,
-                               cudaStream_t st, const CUtensorMap* w_map = nullptr, const EpiParams* e = nullptr,
-                               int launch_index = 0) {
+inline int launch_attention_tc(TmaEncoder& tma, const h16* qk, const h16* vt, h16* o, int n, int* errflag,
+                               cudaStream_t st, const Knobs& kn, const CUtensorMap* w_map = nullptr,
+                               const EpiParams* e = nullptr, int launch_index = 0) {
   static thread_local std::map<std::tuple<const void*, const void*, int>, std::pair<CUtensorMap, CUtensorMap>> cache;
   auto key = std::make_tuple((const void*)qk, (const void*)vt, n);
   auto it = cache.find(key);
@@ -592,10 +592,10 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
     CUtensorMap mq, mv;
     uint64_t dq[3] = {256, AT_S, (uint64_t)n}, sq[2] = {256 * 2, (uint64_t)AT_S * 256 * 2};
     uint32_t bq[3] = {64, 128, 1};
-    if (!tma.encode_bf16(&mq, (void*)qk, 3, dq, sq, bq, nullptr)) return -1;
+    if (!tma.encode_h16(&mq, (void*)qk, 3, dq, sq, bq, nullptr)) return -1;
     uint64_t dv[3] = {AT_S, AT_D, (uint64_t)n}, sv[2] = {(uint64_t)AT_S * 2, (uint64_t)AT_D * AT_S * 2};
     uint32_t bv[3] = {64, 128, 1};
-    if (!tma.encode_bf16(&mv, (void*)vt, 3, dv, sv, bv, nullptr)) return -2;
+    if (!tma.encode_h16(&mv, (void*)vt, 3, dv, sv, bv, nullptr)) return -2;
     if (cache.size() > 256) cache.clear();
     it = cache.emplace(key, std::make_pair(mq, mv)).first;
   }
@@ -609,7 +609,7 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
+  cfg.numAttrs = kn.no_pdl ? 0 : 1;
   EpiParams ep;
   memset(&ep, 0, sizeof ep);
   if (e) ep = *e;
@@ -617,9 +617,9 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
   // staged block-tail epilogue: [pixels x channels] maps of y (res1), x_in (res2) and the output, 64 x 128 boxes
   static thread_local std::map<std::tuple<const void*, int, int>, CUtensorMap> rcache;
   const CUtensorMap* rm[3] = {&it->second.first, &it->second.first, &it->second.first};
-  if (fuse && !getenv("BSR_NO_TMA_STORE") && e->res1 && e->res2 && e->res1_ld >= 272 && e->res2_ld >= 272 &&
+  if (fuse && !kn.no_tma_store && e->res1 && e->res2 && e->res1_ld >= 272 && e->res2_ld >= 272 &&
       e->out_ld >= e->out_coff + 272 && e->out_coff % 8 == 0 && e->out_ld % 8 == 0 && e->res1_ld % 8 == 0 && e->res2_ld % 8 == 0) {
-    const void* bases[3] = {e->res1, e->res2, (const void*)((const bf16*)e->out + e->out_coff)};
+    const void* bases[3] = {e->res1, e->res2, (const void*)((const h16*)e->out + e->out_coff)};
     const int lds[3] = {e->res1_ld, e->res2_ld, e->out_ld};
     bool okm = true;
     if (rcache.size() > 1024) rcache.clear();      // before this launch's lookups: pointers taken below stay valid
@@ -630,7 +630,7 @@ inline int launch_attention_tc(TmaEncoder& tma, const bf16* qk, const bf16* vt, 
         CUtensorMap m;
         uint64_t d2[2] = {(uint64_t)lds[i], (uint64_t)n * AT_S}, s2[1] = {(uint64_t)lds[i] * 2};
         uint32_t b2[2] = {64, 128};
-        if (!tma.encode_bf16(&m, (void*)bases[i], 2, d2, s2, b2, nullptr)) { okm = false; break; }
+        if (!tma.encode_h16(&m, (void*)bases[i], 2, d2, s2, b2, nullptr)) { okm = false; break; }
         rt = rcache.emplace(rk, m).first;
       }
       rm[i] = &rt->second;

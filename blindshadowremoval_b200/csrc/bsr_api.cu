@@ -34,7 +34,7 @@ struct Layer {
   std::vector<float> w_host, b_host;   // canonical fp32 [tap][cin][cout], [cout]
   float* w_dev = nullptr;              // same, on device (CUDA-core kernels)
   float* b_dev = nullptr;              // bias padded with zeros to a multiple of 16 (+256 slack)
-  TcWeights tc;                        // bf16 K-major packing + step program + tensor map (conv_tc.cuh)
+  TcWeights tc;                        // h16 K-major packing + step program + tensor map (conv_tc.cuh)
   TcWeights tc_phase[4];               // wide transposed convs: one plain gather conv per sub-pixel phase
   bool phases_ready = false;
 };
@@ -47,7 +47,7 @@ struct bsr_handle {
   int variant = 0, precision = 0, device = 0, mb = 0;
   bool loaded = false;
   bool debug_keep = false, profile = false;
-  int force_direct = 0;      // BSR_FORCE_DIRECT=1: bf16 storage but CUDA-core convs/attention (bring-up aid)
+  int force_direct = 0;      // BSR_FORCE_DIRECT=1: h16 storage but CUDA-core convs/attention (bring-up aid)
   std::string err;
   std::map<std::string, Layer> layers;
   // channel geometry
@@ -64,6 +64,12 @@ struct bsr_handle {
   float *RAW = nullptr, *DIFGS = nullptr, *UVS = nullptr, *OFF = nullptr, *BMASK = nullptr, *DIFSMALL = nullptr,
         *SH = nullptr;
   int* errflag = nullptr;    // device flag set by kernels whose mbarrier wait timed out
+  int* errflag_host = nullptr;   // pinned mirror, refreshed by an async copy at the end of every forward
+  cudaEvent_t ev_done = nullptr; // recorded at the end of every forward: the next forward (any stream) waits for it
+  cudaStream_t last_stream = nullptr;
+  bool have_done = false;
+  Knobs kn;
+  PlanCounters pc;
   int launches = 0;
   std::map<std::string, DebugBuf> dbg;
   // profiling
@@ -72,11 +78,13 @@ struct bsr_handle {
   size_t ev_used = 0;
   std::vector<std::pair<const char*, float>> times;
   // host-path staging
-  void* chunk_stage = nullptr;      // dense img | uv | reg | face planes of one micro-batch (bsr_forward_chunk)
+  // staging of the chunk / host entry points: part of the arena, sized at bsr_create
+  char* chunk_stage = nullptr;      // dense img | uv | reg | face planes of one micro-batch (bsr_forward_chunk)
   size_t chunk_stage_bytes = 0;
   bool in_small = false;   // compact host path: uv/reg arrive already resized to 32x32
-  void* stage = nullptr;
+  char* stage = nullptr;
   size_t stage_bytes = 0;
+  int host_step_cap = 0;   // images per host-path chunk the staging was sized for
   cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   TmaEncoder tma;
@@ -159,7 +167,7 @@ void debug_capture(bsr_handle* h, cudaStream_t st, const char* name, const void*
   if (is_f32 || h->precision == BSR_PRECISION_FP32CHECK)
     debug_capture_t<float>(h, st, name, buf, ld, coff, C, npix);
   else
-    debug_capture_t<bf16>(h, st, name, buf, ld, coff, C, npix);
+    debug_capture_t<h16>(h, st, name, buf, ld, coff, C, npix);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,7 +219,7 @@ int run_conv(bsr_handle* h, cudaStream_t st, ConvCall c, int n) {
   const bool special = L.tc.ready && (L.tc.kind == TC_HEADS || L.tc.kind == TC_CLR);
   if (!h->force_direct && L.tc.ready && !c.in_f32 && (!special || c.x.gs_f32 != nullptr)) {
     int rc = launch_conv_tc(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, c.x, -1, h->num_sms,
-                            h->errflag, st, &h->launches);
+                            h->errflag, st, &h->launches, h->kn, &h->pc);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core conv %s: launch failed (%d): %s", c.layer, rc,
                              h->tma.last_error.c_str());
     return BSR_OK;
@@ -219,14 +227,19 @@ int run_conv(bsr_handle* h, cudaStream_t st, ConvCall c, int n) {
   if (!h->force_direct && L.phases_ready && !c.in_f32) {
     for (int ph = 0; ph < 4; ++ph) {
       int rc = launch_conv_tc(h->tma, L.tc_phase[ph], c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, c.x, ph,
-                              h->num_sms, h->errflag, st, &h->launches);
+                              h->num_sms, h->errflag, st, &h->launches, h->kn, &h->pc);
       if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core conv %s phase %d: launch failed (%d): %s", c.layer, ph, rc,
                                h->tma.last_error.c_str());
     }
     return BSR_OK;
   }
-  if (c.in_f32) launch_direct<float, bf16>(h, st, L, c, n);
-  else launch_direct<bf16, bf16>(h, st, L, c, n);
+  // CUDA-core convolutions inside the 16-bit path exist for bring-up only (BSR_FORCE_DIRECT=1, BSR_TC_DISABLE=<layer>);
+  // the product path never falls back to them silently
+  if (!h->force_direct && !tc_disabled(L.name))
+    return fail(h, BSR_EUNSUPPORTED, "layer %s has no tensor-core packing (cin %d cout %d k %dx%d%s); set BSR_FORCE_DIRECT=1 "
+                "for the CUDA-core bring-up path", c.layer, L.cin, L.cout, L.kh, L.kw, L.transposed ? " transposed" : "");
+  if (c.in_f32) launch_direct<float, h16>(h, st, L, c, n);
+  else launch_direct<h16, h16>(h, st, L, c, n);
   return BSR_OK;
 }
 
@@ -254,14 +267,15 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
   if (!h->force_direct) {
     EpiParams e2;
     if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
-    int rc = launch_attention_tc(h->tma, (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, n, h->errflag, st,
+    int rc = launch_attention_tc(h->tma, (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, n, h->errflag, st, h->kn,
                                  wl ? &wl->tc.map : nullptr, wl ? &e2 : nullptr, h->launches);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
     h->launches++;
+    h->pc.attn_fused += wl != nullptr;
     return BSR_OK;
   }
-  attention_simple_kernel<bf16><<<dim3(AS_S / AS_Q, n), 256, kAttnSimpleSmem, st>>>(
-      (const bf16*)h->QK, (const bf16*)h->VT, (bf16*)h->O, 128);
+  attention_simple_kernel<h16><<<dim3(AS_S / AS_Q, n), 256, kAttnSimpleSmem, st>>>(
+      (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, 128);
   h->launches++;
   return BSR_OK;
 }
@@ -288,6 +302,20 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   eq.spatial = FEAT * FEAT;
   ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq, no_extra()};
   if ((rc = run_conv(h, st, c4, n))) return rc;
+  if (h->debug_keep && (idx == 0 || idx == 5)) {
+    // direct view of the attention core for tests: the projections it reads and its un-fused output O = softmax(QK^T).V
+    // (model.py:51-53); these extra launches are not counted
+    const int launches0 = h->launches;
+    const PlanCounters pc0 = h->pc;
+    char nb[3][16];
+    snprintf(nb[0], 16, "qk%d", idx); snprintf(nb[1], 16, "vt%d", idx); snprintf(nb[2], 16, "attn_o%d", idx);
+    debug_capture(h, st, nb[0], h->QK, 256, 0, 256, (long long)n * 1024);
+    debug_capture(h, st, nb[1], h->VT, 1024, 0, 1024, (long long)n * 128);
+    if ((rc = run_attention(h, st, n))) return rc;
+    debug_capture(h, st, nb[2], h->O, 128, 0, 128, (long long)n * 1024);
+    h->launches = launches0;
+    h->pc = pc0;
+  }
   int oc = ld < ldy ? ld : ldy;
   EpiParams ew = epi(nxt, ld, 0, oc, 1);
   // residual widths are the PADDED widths: padding channels of Y / cur are kept at zero, so adding them is exact
@@ -298,7 +326,7 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   // NonLocal output conv + block tail: fused into the attention kernel on the tensor-core path
   const Layer& wl = h->layers[nm[4]];
   const bool fuse_w = h->precision == BSR_PRECISION_BF16 && !h->force_direct && wl.tc.ready && wl.tc.kind == TC_CONV &&
-                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !getenv("BSR_NO_FUSE_W");
+                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !h->kn.no_fuse_w;
   if (fuse_w) {
     if ((rc = run_attention(h, st, n, &wl, &ew))) return rc;
   } else {
@@ -309,8 +337,8 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   if (ld > oc) {
     Step step(h, st, "res_tail");
     long long npix = (long long)n * FEAT * FEAT, tot = npix * (ld - oc);
-    if (std::is_same<T, bf16>::value && ld % 8 == 0 && oc % 8 == 0)
-      res_tail_vec_kernel<<<(unsigned)((tot / 8 + 255) / 256), 256, 0, st>>>((const bf16*)cur, ld, (bf16*)nxt, ld, oc, ld, npix);
+    if (std::is_same<T, h16>::value && ld % 8 == 0 && oc % 8 == 0)
+      res_tail_vec_kernel<<<(unsigned)((tot / 8 + 255) / 256), 256, 0, st>>>((const h16*)cur, ld, (h16*)nxt, ld, oc, ld, npix);
     else
       res_tail_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const T*)cur, ld, (T*)nxt, ld, oc, ld, npix);
     h->launches++;
@@ -347,7 +375,7 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     {
       Step step(h, st, "pack_img");
       long long rows = (long long)n * IMG, tot = rows * (IMG + 8);
-      pack_img_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(img, (bf16*)h->PIMG, rows);
+      pack_img_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(img, (h16*)h->PIMG, rows);
       h->launches++;
     }
     ConvCall cv1{"conv1", h->PIMG, 8, 0, false, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1), no_extra()};
@@ -390,9 +418,9 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
   {
     Step step(h, st, "assemble_uv");
     int uv_off = c_cur - 3;
-    if (std::is_same<T, bf16>::value && ld1 % 8 == 0) {
+    if (std::is_same<T, h16>::value && ld1 % 8 == 0) {
       long long tot = px32 * ((ld1 >> 3) - (uv_off >> 3));
-      assemble_uv_vec_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((bf16*)h->XA, ld1, h->UVS, uv_off, (int)px32);
+      assemble_uv_vec_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((h16*)h->XA, ld1, h->UVS, uv_off, (int)px32);
     } else {
       long long tot = px32 * (3 + (ld1 - c_cur));
       assemble_uv_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((T*)h->XA, ld1, h->UVS, uv_off, c_cur, ld1,
@@ -492,6 +520,36 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
   return BSR_OK;
 }
 
+// RAII: make the handle's device current, restore the caller's device on every exit path.
+struct DeviceScope {
+  int prev = -1, want;
+  bool ok = true;
+  explicit DeviceScope(int dev) : want(dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; return; }
+    if (prev != want && cudaSetDevice(want) != cudaSuccess) ok = false;
+  }
+  ~DeviceScope() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+
+// A watchdog that fired in an EARLIER forward of this handle (its flag copy has landed in pinned memory): report it
+// once, before launching anything else on top of garbage.
+int pending_device_error(bsr_handle* h) {
+  const int flag = *(volatile int*)h->errflag_host;
+  if (!flag) return BSR_OK;
+  *(volatile int*)h->errflag_host = 0;
+  cudaMemsetAsync(h->errflag, 0, sizeof(int), h->last_stream);
+  return fail(h, BSR_EDEVICE, "device watchdog: an mbarrier wait timed out in an earlier forward (code %d); its outputs are invalid", flag);
+}
+
+// End of every forward: mirror the device error flag into pinned host memory and mark the workspace busy until here.
+int finish_forward(bsr_handle* h, cudaStream_t st) {
+  CK(h, cudaMemcpyAsync(h->errflag_host, h->errflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaEventRecord(h->ev_done, st));
+  h->last_stream = st;
+  h->have_done = true;
+  return BSR_OK;
+}
+
 int forward_common(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
                    float* gs, float* rgb, float* mask22, float* dif, cudaStream_t st) {
   if (!h) return BSR_EINVAL;
@@ -500,10 +558,13 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
   const bool tsm = h->variant == BSR_VARIANT_TSM;
   if (tsm && (!reg || frame <= 0 || n % frame)) return fail(h, BSR_EINVAL, "TSM needs reg and n %% frame == 0");
   if (tsm && frame > h->mb) return fail(h, BSR_EINVAL, "frame %d exceeds micro_batch %d", frame, h->mb);
-  int dev;
-  CK(h, cudaGetDevice(&dev));
-  if (dev != h->device) CK(h, cudaSetDevice(h->device));
+  if (int rc = pending_device_error(h)) return rc;
+  DeviceScope dev_scope(h->device);
+  if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
+  // forwards of one handle share the workspace: wait (device side) for the previous one, whatever stream it ran on
+  if (h->have_done && h->last_stream != st) CK(h, cudaStreamWaitEvent(st, h->ev_done, 0));
   h->launches = 0;
+  h->pc = PlanCounters();
   h->ev_used = 0;
   h->ev_names.clear();
   int step = h->mb;
@@ -519,12 +580,11 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
       rc = forward_mb<float>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
                              rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
     else
-      rc = forward_mb<bf16>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
+      rc = forward_mb<h16>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
                             rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
     if (rc) return rc;
   }
-  if (dev != h->device) cudaSetDevice(dev);
-  return BSR_OK;
+  return finish_forward(h, st);
 }
 
 // Host-buffer path: micro-batches are pipelined over three streams (H2D | compute | D2H) with two staging
@@ -537,6 +597,21 @@ struct HostCompact {
   unsigned char* rgb_u8 = nullptr;
   unsigned short* dif_f16 = nullptr;
 };
+// Staging slots of the pipelined host path for chunks of `step` images: fp32 [img | uv | reg] in, [gs | rgb | mask22 |
+// dif] out, and the compact forms [img_u8 | uv32 | reg32] in, [rgb_u8 | dif_f16] out; two slots of each.
+struct HostSlots {
+  size_t in_slot, out_slot, cin_slot, cout_slot;
+  size_t total() const { return 2 * (in_slot + out_slot + cin_slot + cout_slot); }
+};
+HostSlots host_slots(int step, bool with_reg) {
+  const size_t p1 = (size_t)IMG * IMG * sizeof(float), px = (size_t)IMG * IMG, px32 = (size_t)FEAT * FEAT;
+  HostSlots s;
+  s.in_slot = (size_t)step * p1 * (3 + 3 + (with_reg ? 6 : 0));
+  s.out_slot = (size_t)step * p1 * (1 + 3 + 3 + 1);
+  s.cin_slot = (size_t)step * (px * 3 + px32 * 3 * sizeof(float) + px32 * 6 * sizeof(float));
+  s.cout_slot = (size_t)step * (px * 3 + px * 2);
+  return s;
+}
 struct SmallInputScope {      // forward_mb reads uv/reg as 32x32 maps only while a compact call is in flight
   bsr_handle* h;
   SmallInputScope(bsr_handle* hh, bool on) : h(hh) { h->in_small = on; }
@@ -552,14 +627,17 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
   if ((!compact && !img) || !uv) return fail(h, BSR_EINVAL, "img/uv must be non-NULL");
   if (!compact && (cp.rgb_u8 || cp.dif_f16)) return fail(h, BSR_EINVAL, "compact outputs need the compact entry point");
   if (h->variant == BSR_VARIANT_TSM && !reg) return fail(h, BSR_EINVAL, "TSM needs reg");
+  if (int rc = pending_device_error(h)) return rc;
   SmallInputScope small_scope(h, compact);
-  CK(h, cudaSetDevice(h->device));
+  DeviceScope dev_scope(h->device);
+  if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
   // transfer/compute chunk of the pipelined host path: smaller than the device micro-batch so that PCIe copies and
   // kernels of neighbouring chunks overlap well (measured optimum ~64 images; BSR_HOST_CHUNK overrides)
   // measured: fp32 I/O, 256 images/call: 64 -> 17.2k img/s, 128 -> 13.8k; 1024 images/call: 64 -> 18.7k, 128 -> 19.4k;
   // compact I/O (transfers 5x smaller, head/tail cheap): 256/call: 64 -> 17.9k, 128 -> 18.6k; 1024/call: 128 -> 19.9k
   int host_chunk = (compact || n >= 512) ? 128 : 64;
-  if (const char* hc = getenv("BSR_HOST_CHUNK")) host_chunk = atoi(hc) > 0 ? atoi(hc) : host_chunk;
+  if (h->kn.host_chunk > 0) host_chunk = h->kn.host_chunk;
+  if (host_chunk > h->host_step_cap) host_chunk = h->host_step_cap;
   int step = h->mb < host_chunk ? h->mb : host_chunk;
   if (reg) {
     if (frame <= 0 || n % frame) return fail(h, BSR_EINVAL, "TSM needs n %% frame == 0");
@@ -568,30 +646,15 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
     step = step / frame * frame;
   }
   const size_t p1 = (size_t)IMG * IMG * sizeof(float);           // one single-channel image plane
-  const size_t in_slot = (size_t)step * p1 * (3 + 3 + (reg ? 6 : 0));
-  const size_t out_slot = (size_t)step * p1 * (1 + 3 + 3 + 1);
   const size_t px = (size_t)IMG * IMG, px32 = (size_t)FEAT * FEAT;
-  // compact slots: [img_u8 | uv32 | reg32] in, [rgb_u8 | dif_f16] out (the fp32 slots stay as device-side scratch)
-  const size_t cin_slot = compact ? (size_t)step * (px * 3 + px32 * 3 * sizeof(float) + px32 * 6 * sizeof(float)) : 0;
-  const size_t cout_slot = compact ? (size_t)step * (px * 3 + px * 2) : 0;
-  const size_t need = 2 * (in_slot + out_slot + cin_slot + cout_slot);
-  if (need > h->stage_bytes) {
-    if (h->stage) cudaFree(h->stage);
-    h->stage = nullptr;
-    h->stage_bytes = 0;
-    if (cudaMalloc(&h->stage, need) != cudaSuccess) return fail(h, BSR_ENOMEM, "staging allocation of %zu bytes failed", need);
-    h->stage_bytes = need;
-  }
-  if (!h->s_in) {
-    CK(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-    CK(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CK(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-      CK(h, cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
-      CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
-    }
-  }
+  const HostSlots hs = host_slots(step, reg != nullptr);
+  const size_t in_slot = hs.in_slot, out_slot = hs.out_slot, cin_slot = hs.cin_slot, cout_slot = hs.cout_slot;
+  if (hs.total() > h->stage_bytes)
+    return fail(h, BSR_EINVAL, "host path: a chunk of %d images needs %zu bytes of staging, the handle was created with %zu "
+                "(chunks are capped at %d images; frame must not exceed that)", step, hs.total(), h->stage_bytes, h->host_step_cap);
   cudaStream_t s_in = h->s_in, s_c = h->own_stream, s_out = h->s_out;
+  // the input staging slots are read by the previous forward of this handle until it has finished
+  if (h->have_done) CK(h, cudaStreamWaitEvent(s_in, h->ev_done, 0));
   // Chunk schedule: ramp up and down (step/4, step/2, step ... step, step/2, step/4) so that the H2D of the
   // first chunk and the D2H of the last one - the only transfers that cannot overlap compute - are short.
   const int unit = reg ? frame : 1;
@@ -609,6 +672,7 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
     for (int v : tail) { sched.push_back(v); left -= v; }
   }
   int total_launches = 0, k = 0, i0 = 0;
+  PlanCounters pc_total;
   for (size_t ci = 0; ci < sched.size(); i0 += sched[ci], ++ci, ++k) {
     const int m = sched[ci];
     const int slot = k & 1;
@@ -666,6 +730,8 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
       ++extra_launches;
     }
     total_launches += h->launches + extra_launches;
+    pc_total.resident += h->pc.resident; pc_total.pinned += h->pc.pinned; pc_total.staged += h->pc.staged;
+    pc_total.attn_fused += h->pc.attn_fused; pc_total.graph_replays += h->pc.graph_replays;
     CK(h, cudaEventRecord(h->ev_comp[slot], s_c));
     CK(h, cudaStreamWaitEvent(s_out, h->ev_comp[slot], 0));
     if (gs) CK(h, cudaMemcpyAsync(gs + o1, d_gs, pm, cudaMemcpyDeviceToHost, s_out));
@@ -679,10 +745,8 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
   CK(h, cudaStreamSynchronize(s_out));
   CK(h, cudaStreamSynchronize(s_c));
   h->launches = total_launches;
-  int flag = 0;
-  CK(h, cudaMemcpy(&flag, h->errflag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) return fail(h, BSR_ECUDA, "device watchdog: an mbarrier wait timed out (code %d)", flag);
-  return BSR_OK;
+  h->pc = pc_total;
+  return pending_device_error(h);       // the flag copy of the last chunk has landed (stream synchronised above)
 }
 
 }  // namespace
@@ -690,7 +754,11 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
 // =============================================================================================
 extern "C" {
 
-const char* bsr_version(void) { return "bsr-b200 0.1 (sm_100a)"; }
+const char* bsr_version(void) { return "bsr-b200 0.2 (sm_100a, " BSR_ACT_DTYPE_NAME " storage)"; }
+const char* bsr_act_dtype(void) { return BSR_ACT_DTYPE_NAME; }
+void bsr_convert_h16(const float* in, unsigned short* out, size_t n) {
+  for (size_t i = 0; i < n; ++i) out[i] = f32_to_h16_bits(in[i]);
+}
 
 // CRC-32C, reflected polynomial 0x82F63B78, slicing-by-8 (host only)
 unsigned int bsr_crc32c(unsigned int crc, const void* data, size_t n) {
@@ -753,6 +821,15 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->profile = ev && atoi(ev) != 0;
   ev = getenv("BSR_FORCE_DIRECT");
   h->force_direct = ev ? atoi(ev) : 0;
+  auto env_int = [](const char* k) { const char* v = getenv(k); return v ? atoi(v) : 0; };
+  auto env_set = [](const char* k) { return getenv(k) != nullptr ? 1 : 0; };
+  h->kn.ablate = env_int("BSR_ABLATE");
+  h->kn.no_pdl = env_set("BSR_NO_PDL");
+  h->kn.no_tma_store = env_set("BSR_NO_TMA_STORE");
+  h->kn.st_bufs = env_int("BSR_ST_BUFS");
+  h->kn.no_fuse_w = env_set("BSR_NO_FUSE_W");
+  h->kn.host_chunk = env_int("BSR_HOST_CHUNK");
+  h->kn.no_graph = env_set("BSR_NO_GRAPH");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
   h->ld1 = pad16(h->c_first > 257 ? h->c_first : 257);
@@ -775,6 +852,13 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {(char**)&h->DIFSMALL, mb * 1024 * 4},
       {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 2 * 291 * 4 : 256},
       {(char**)&h->errflag, 16384}};
+  // staging of the host / chunk entry points (include/bsr.h: no allocation inside forward_*): host-path chunks are
+  // capped at 128 images (the measured optimum is 64-128), chunk entry at one micro-batch
+  h->host_step_cap = micro_batch < 128 ? micro_batch : 128;
+  h->stage_bytes = host_slots(h->host_step_cap, variant == BSR_VARIANT_TSM).total();
+  h->chunk_stage_bytes = mb * IMG * IMG * 13 * sizeof(float);
+  reqs.push_back({&h->stage, h->stage_bytes});
+  reqs.push_back({&h->chunk_stage, h->chunk_stage_bytes});
   size_t total = 0;
   for (auto& r : reqs) total += align256(r.bytes);
   if (cudaMalloc(&h->arena, total) != cudaSuccess) {
@@ -787,6 +871,20 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   size_t off = 0;
   for (auto& r : reqs) { *r.p = (char*)h->arena + off; off += align256(r.bytes); }
   cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+  }
+  if (cudaHostAlloc((void**)&h->errflag_host, 64, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    bsr_destroy(h);
+    return fail(nullptr, BSR_ENOMEM, "pinned allocation of the error-flag mirror failed");
+  }
+  *h->errflag_host = 0;
   if (h->profile) {
     h->ev.resize(512);
     for (auto& e : h->ev) cudaEventCreate(&e);
@@ -801,7 +899,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
     return fail(nullptr, BSR_ECUDA, "cudaFuncSetAttribute failed for tensor-core kernels (%d)", rc);
   }
   cudaFuncSetAttribute(attention_simple_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSimpleSmem);
-  cudaFuncSetAttribute(attention_simple_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSimpleSmem);
+  cudaFuncSetAttribute(attention_simple_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSimpleSmem);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     bsr_destroy(h);
@@ -824,8 +922,8 @@ int bsr_destroy(bsr_handle* h) {
   for (auto& kv : h->dbg) if (kv.second.dev) cudaFree(kv.second.dev);
   for (auto& e : h->ev) cudaEventDestroy(e);
   if (h->arena) cudaFree(h->arena);
-  if (h->stage) cudaFree(h->stage);
-  if (h->chunk_stage) cudaFree(h->chunk_stage);
+  if (h->errflag_host) cudaFreeHost(h->errflag_host);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -990,25 +1088,20 @@ int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int 
   if (tsm && (frame <= 0 || n % frame)) return fail(h, BSR_EINVAL, "TSM needs n %% frame == 0");
   if (tsm && frame > h->mb) return fail(h, BSR_EINVAL, "frame %d exceeds micro_batch %d", frame, h->mb);
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int dev;
-  CK(h, cudaGetDevice(&dev));
-  if (dev != h->device) CK(h, cudaSetDevice(h->device));
+  if (int rc = pending_device_error(h)) return rc;
+  DeviceScope dev_scope(h->device);
+  if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
   int step = h->mb < n ? h->mb : n;
   if (tsm) step = step / frame * frame;
-  const size_t px = (size_t)IMG * IMG, need = (size_t)step * px * 13 * sizeof(float);
-  if (need > h->chunk_stage_bytes) {
-    CK(h, cudaStreamSynchronize(st));                 // the old buffer may still be in use by an earlier call
-    if (h->chunk_stage) cudaFree(h->chunk_stage);
-    h->chunk_stage = nullptr;
-    h->chunk_stage_bytes = 0;
-    if (cudaMalloc(&h->chunk_stage, need) != cudaSuccess) return fail(h, BSR_ENOMEM, "chunk staging allocation of %zu bytes failed", need);
-    h->chunk_stage_bytes = need;
-  }
+  const size_t px = (size_t)IMG * IMG;      // staging: one micro-batch of 13 dense planes, carved from the arena at create
+  // the staging planes are read by the previous forward of this handle until it has finished
+  if (h->have_done && h->last_stream != st) CK(h, cudaStreamWaitEvent(st, h->ev_done, 0));
   float* d_img = (float*)h->chunk_stage;
   float* d_uv = d_img + (size_t)step * px * 3;
   float* d_reg = d_uv + (size_t)step * px * 3;
   float* d_face = d_reg + (size_t)step * px * 6;
   int total = 0;
+  PlanCounters pc_total;
   for (int i0 = 0; i0 < n; i0 += step) {
     const int m = n - i0 < step ? n - i0 : step;
     const long long mpx = (long long)m * px;
@@ -1021,11 +1114,13 @@ int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int 
     if (rc) return rc;
     caller_glue_kernel<<<(unsigned)((mpx + 255) / 256), 256, 0, st>>>(rgb_o, mp_o, d_face, rgb_o, mp_o, mpx);   // in place
     total += h->launches + 2;
+    pc_total.resident += h->pc.resident; pc_total.pinned += h->pc.pinned; pc_total.staged += h->pc.staged;
+    pc_total.attn_fused += h->pc.attn_fused; pc_total.graph_replays += h->pc.graph_replays;
   }
   CK(h, cudaGetLastError());
   h->launches = total;
-  if (dev != h->device) cudaSetDevice(dev);
-  return BSR_OK;
+  h->pc = pc_total;
+  return finish_forward(h, st);        // the in-place caller glue above is part of this forward
 }
 
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n, float* rgb_clipped,
@@ -1051,19 +1146,38 @@ int bsr_composite(bsr_handle* h, const float* pred, const float* inp, const floa
   return BSR_OK;
 }
 
+int bsr_check(bsr_handle* h) {
+  if (!h) return BSR_EINVAL;
+  DeviceScope dev_scope(h->device);
+  if (h->have_done) CK(h, cudaEventSynchronize(h->ev_done));
+  return pending_device_error(h);
+}
+
+int bsr_plan_counter(const bsr_handle* h, int which) {
+  if (!h) return 0;
+  switch (which) {
+    case 0: return h->pc.resident;
+    case 1: return h->pc.pinned;
+    case 2: return h->pc.staged;
+    case 3: return h->pc.attn_fused;
+    case 4: return h->pc.graph_replays;
+    default: return 0;
+  }
+}
+
 int bsr_launch_count(const bsr_handle* h) { return h ? h->launches : 0; }
 size_t bsr_workspace_bytes(const bsr_handle* h) { return h ? h->arena_bytes : 0; }
 
 int bsr_debug_read(bsr_handle* h, const char* name, float* host_out, size_t capacity, size_t* n_elems) {
   if (!h || !name) return BSR_EINVAL;
-  if (!h->debug_keep) return fail(h, BSR_ESTATE, "create the handle with BSR_DEBUG_KEEP=1 to keep intermediates");
-  if (!strcmp(name, "errflag")) {
+  if (!strcmp(name, "errflag")) {      // the raw device flag (sticky until bsr_check / the next forward reports it)
     int flag = 0;
     CK(h, cudaMemcpy(&flag, h->errflag, sizeof(int), cudaMemcpyDeviceToHost));
     if (n_elems) *n_elems = 1;
     if (host_out && capacity >= 1) host_out[0] = (float)flag;
     return BSR_OK;
   }
+  if (!h->debug_keep) return fail(h, BSR_ESTATE, "create the handle with BSR_DEBUG_KEEP=1 to keep intermediates");
   if (!strcmp(name, "timers")) {       // BSR_ABLATE=8: 64 launches x 16 cycle counters (see conv_tc.cuh)
     if (n_elems) *n_elems = 1024;
     if (!host_out) return BSR_OK;

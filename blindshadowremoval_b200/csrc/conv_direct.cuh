@@ -1,5 +1,5 @@
 // CUDA-core implicit-GEMM convolution (fp32 accumulate).  This is the FP32CHECK arithmetic of every
-// conv / transposed conv (north_star's "<=1e-4 check mode"); the bf16 product path uses
+// conv / transposed conv (north_star's "<=1e-4 check mode"); the h16 product path uses
 // conv_tc.cuh instead.
 //
 // Semantics follow Keras Conv2D / Conv2DTranspose with padding='same' as used by

@@ -1,4 +1,4 @@
-// Implicit-GEMM convolution on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM) — persistent,
+// Implicit-GEMM convolution on tcgen05 tensor cores (h16 in, fp32 accumulate in TMEM) — persistent,
 // warp-specialised, driven by a per-layer "step program".
 //
 // GEMM view:  D[128 pixels, N couts] = sum over steps  A_step[128, 64] . W_step[N, 64]^T
@@ -19,7 +19,7 @@
 //       heads (7x7, 64->2, model.py:204-205): "kw expansion": N = 7(kw) x 2 outputs, K = 7(kh) x 64, one
 //                         image row (2 x 128 pixels) per tile; the horizontal taps are summed in the
 //                         epilogue through shared memory, fused with the grey composition (model.py:246-252).
-//   * W is packed once at load time (bf16, K-major) and fetched by 2-D TMA; 128-byte swizzle on both
+//   * W is packed once at load time (h16, K-major) and fetched by 2-D TMA; 128-byte swizzle on both
 //     operands; UMMA M = 128, K = 16 per instruction.
 // Persistent CTAs (one per SM) loop over tiles; accumulators are double-buffered in TMEM whenever
 // 2 x columns <= 512, so the epilogue of tile t overlaps the TMA/MMA main loop of tile t+1.
@@ -46,7 +46,7 @@
 namespace bsr {
 
 constexpr int TC_BM = 128;          // pixels per A tile (UMMA M)
-constexpr int TC_BK = 64;           // K elements per step (128 B of bf16 = one swizzle row)
+constexpr int TC_BK = 64;           // K elements per step (128 B of h16 = one swizzle row)
 constexpr int TC_THREADS = 576;
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MAX_STEPS = 64;
@@ -104,7 +104,7 @@ struct TcWeights {
   int can_pin = 0;        // n_tiles > 1: ONE n-tile's rows fit in shared memory -> a CTA may keep "its" n-tile resident
   TcStep steps[TC_MAX_STEPS];
   TcStep* steps_dev = nullptr;
-  bf16* dev = nullptr;
+  h16* dev = nullptr;
   ClrWeights* clr = nullptr;   // EPI_CLR: host copy of the colour-tail weights (kernel parameter)
   CUtensorMap map;
   void release() {
@@ -166,21 +166,21 @@ struct ConvTcParams {
 
 // vectorised helpers for the epilogue ------------------------------------------------------
 __device__ __forceinline__ void add_res16(const void* base, size_t pix, int ld, int c, int climit, float* v) {
-  const bf16* p = (const bf16*)base + pix * ld + c;
+  const h16* p = (const h16*)base + pix * ld + c;
   if (c + 16 <= climit) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
     uint4 a = q[0], b = q[1];
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-      v[2 * i] += __low2float(t);
-      v[2 * i + 1] += __high2float(t);
+      const float2 t = unpack_h16x2(w[i]);
+      v[2 * i] += t.x;
+      v[2 * i + 1] += t.y;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      if (c + i < climit) v[i] += __bfloat162float(p[i]);
+      if (c + i < climit) v[i] += h16_to_f32(p[i]);
   }
 }
 
@@ -192,13 +192,13 @@ __device__ __forceinline__ void epi_bar_slot(int slot) { asm volatile("bar.sync 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ void add_bf16x16(const uint4& a, const uint4& b, float* v) {
+__device__ __forceinline__ void add_h16x16(const uint4& a, const uint4& b, float* v) {
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-    v[2 * i] += __low2float(t);
-    v[2 * i + 1] += __high2float(t);
+    const float2 t = unpack_h16x2(w[i]);
+    v[2 * i] += t.x;
+    v[2 * i + 1] += t.y;
   }
 }
 
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
   TcStep* steps = reinterpret_cast<TcStep*>(smem_al + (bars + 192 - smem_base));
   float* epi_smem = reinterpret_cast<float*>(smem_al + (bars + 192 + (uint32_t)p.steps_bytes - smem_base));
-  // output staging of the TMA-store epilogue: st_bufs buffers of 128 rows x 64 bf16 columns
+  // output staging of the TMA-store epilogue: st_bufs buffers of 128 rows x 64 h16 columns
   const uint32_t st_stage = (bars + 192 + (uint32_t)p.steps_bytes + (uint32_t)p.epi_bytes + 511u) & ~511u;   // 512 B = one 64B-swizzle atom
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.steps);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const long long t_start = BSR_CLK();
       if (b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
       const long long t_res = BSR_CLK() - t_start;
-      const uint32_t idesc_m = umma_idesc_bf16(TC_BM, 0);
+      const uint32_t idesc_m = umma_idesc_h16(TC_BM, 0);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
         const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
         const long long tw0 = BSR_CLK();
@@ -371,16 +371,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t idesc = idesc_m | ((uint32_t)(mm.n >> 3) << 17);
               const uint32_t d = acc + (uint32_t)mm.col;
               const uint32_t a0 = a_lo + ((mm.first & 2) ? (a_bytes >> 4) : 0u);     // row mode: second input row
-              umma_bf16_lo(d, a0, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
-              umma_bf16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
-              umma_bf16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
-              umma_bf16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
+              umma_h16_lo(d, a0, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
+              umma_h16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
+              umma_h16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
+              umma_h16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
               if (na == 2) {       // second 64-wide K block of the step
                 const uint32_t a1 = a_lo + (a_bytes >> 4), b1 = b_lo + b_kb_lo;
-                umma_bf16_lo(d, a1, b1, idesc, 1u);
-                umma_bf16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
-                umma_bf16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
-                umma_bf16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
+                umma_h16_lo(d, a1, b1, idesc, 1u);
+                umma_h16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
+                umma_h16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
+                umma_h16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
               }
             }
           }
@@ -422,12 +422,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
       const uint32_t acc = tmem_base + as * (uint32_t)bn + lane_addr;
       if (EPI == EPI_GENERIC && !RES && p.st_chunk) {
-        // ---- staged epilogue: accumulators -> bf16 -> 64B-swizzled shared memory -> TMA store.  Per-thread-row global
+        // ---- staged epilogue: accumulators -> h16 -> 64B-swizzled shared memory -> TMA store.  Per-thread-row global
         // stores touch 32 cache lines per warp instruction and (measured) slow the UMMA operand
         // reads that share the L1/shared-memory pipe; the bulk store reads the staged tile at full line width instead.
         const int group_cols = p.group_cols, total_cols = p.n_groups * group_cols;
         constexpr int cw_ = 16, iter_cols = 4 * cw_;
-        const uint32_t buf_bytes = (uint32_t)iter_cols * 256u;                 // 128 rows x iter_cols bf16
+        const uint32_t buf_bytes = (uint32_t)iter_cols * 256u;                 // 128 rows x iter_cols h16
         const int gx0 = (tr % p.tiles_x) * p.bw, gy0 = (tr / p.tiles_x) * p.bh * rows_per_tile;
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
         if (!ok) break;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) o[i] = pack_h16x2(v[2 * i], v[2 * i + 1]);
           }
           if (col0 + iter_cols >= total_cols) {          // accumulators drained: the MMA warp may start the next tile
             tc_fence_before();
@@ -512,11 +512,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int col = (4 * k + cg) * 16, c = cbase + col;
             if (col < bn && c + 16 <= e.out_c) {
               if (e.res1 != nullptr && c + 16 <= e.res1_c) {
-                const uint4* src = reinterpret_cast<const uint4*>((const bf16*)e.res1 + pix0 * e.res1_ld + c);
+                const uint4* src = reinterpret_cast<const uint4*>((const h16*)e.res1 + pix0 * e.res1_ld + c);
                 rb1[k][0] = src[0]; rb1[k][1] = src[1]; m1 |= 1u << k;
               }
               if (e.res2 != nullptr && c + 16 <= e.res2_c) {
-                const uint4* src = reinterpret_cast<const uint4*>((const bf16*)e.res2 + pix0 * e.res2_ld + c);
+                const uint4* src = reinterpret_cast<const uint4*>((const h16*)e.res2 + pix0 * e.res2_ld + c);
                 rb2[k][0] = src[0]; rb2[k][1] = src[1]; m2 |= 1u << k;
               }
             }
@@ -553,9 +553,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
               if (RES) {
-                if (pf1) add_bf16x16(r1a, r1b, v);
+                if (pf1) add_h16x16(r1a, r1b, v);
                 else if (e.res1 != nullptr && c < e.res1_c) add_res16(e.res1, pix, e.res1_ld, c, e.res1_c, v);
-                if (pf2) add_bf16x16(r2a, r2b, v);
+                if (pf2) add_h16x16(r2a, r2b, v);
                 else if (e.res2 != nullptr && c < e.res2_c) add_res16(e.res2, pix, e.res2_ld, c, e.res2_c, v);
               }
               if (e.act) {
@@ -568,17 +568,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int i = 0; i < 16; ++i) dst[i] = v[i];
               } else if (e.out_mode == OUT_QKV && c >= 256) {
                 // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
-                bf16* dst = (bf16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * OW + gx);
+                h16* dst = (h16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * OW + gx);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = __float2bfloat16_rn(v[i]);
+                for (int i = 0; i < 16; ++i) dst[(size_t)i * e.spatial] = f32_to_h16(v[i]);
               } else {
                 uint4 o0, o1;
-                o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-                o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-                o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                o0.x = pack_h16x2(v[0], v[1]); o0.y = pack_h16x2(v[2], v[3]);
+                o0.z = pack_h16x2(v[4], v[5]); o0.w = pack_h16x2(v[6], v[7]);
+                o1.x = pack_h16x2(v[8], v[9]); o1.y = pack_h16x2(v[10], v[11]);
+                o1.z = pack_h16x2(v[12], v[13]); o1.w = pack_h16x2(v[14], v[15]);
                 const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
-                uint4* dst = reinterpret_cast<uint4*>((bf16*)e.out + off);
+                uint4* dst = reinterpret_cast<uint4*>((h16*)e.out + off);
                 if (!(p.ablate & 1)) {
                   dst[0] = o0;
                   dst[1] = o1;
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) epi_store<bf16>(e, pix, c + i, v[i]);
+              for (int i = 0; i < 16; ++i) epi_store<h16>(e, pix, c + i, v[i]);
             }
           }
           j += 64;
@@ -781,12 +781,29 @@ inline int configure_tc_kernels_conv() {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-inline uint16_t f32_to_bf16_bits(float f) {
+// host-side float -> 16-bit storage bits (round to nearest even; binary16 saturates to +-65504 like the device path)
+inline uint16_t f32_to_h16_bits(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
+#ifdef BSR_ACT_BF16
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
+#else
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                  // NaN
+  if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);                 // >= 65520 (rounds past max) or inf: saturate
+  if (a < 0x33000001u) return sign;                                        // <= 2^-25: rounds to zero
+  const int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;                                // 24-bit significand
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);                              // subnormal: shift further
+  const uint32_t half = 1u << (shift - 1), rem = m & ((1u << shift) - 1u);
+  uint32_t q = m >> shift;
+  if (rem > half || (rem == half && (q & 1u))) ++q;
+  const uint32_t bits = e >= -14 ? ((uint32_t)(e + 14) << 10) + q : q;     // carry out of q bumps the exponent correctly
+  return (uint16_t)(sign | bits);
+#endif
 }
 
 inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>& host, size_t rows, size_t K,
@@ -795,7 +812,7 @@ inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>
   if (cudaMemcpy(t.dev, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
   uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
   uint32_t box[2] = {TC_BK, (uint32_t)t.b_box_rows};
-  if (!tma.encode_bf16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
+  if (!tma.encode_h16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
   for (int i = 0; i < TC_MAX_STEPS; ++i) if (t.steps[i].n_a == 0) t.steps[i].n_a = 1;
   if (cudaMalloc(&t.steps_dev, sizeof t.steps) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   if (cudaMemcpy(t.steps_dev, t.steps, sizeof t.steps, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
@@ -844,7 +861,7 @@ inline void tc_rows_step(TcStep& sp, int j, int R, int KH, int nb, int base, boo
   }
 }
 
-// Build the step program and the packed bf16 weight matrix of one layer from canonical fp32
+// Build the step program and the packed h16 weight matrix of one layer from canonical fp32
 // [tap][cin][cout].  Returns false with empty *why when the layer stays on the CUDA-core kernel.
 inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, int kw, int cin, int cout, int transposed,
                             const std::vector<float>& w, const std::vector<float>& bias, TcWeights* out,
@@ -872,7 +889,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     for (int a = 0; a < 7; ++a)
       for (int b = 0; b < 7; ++b)
         for (int c = 0; c < cin; ++c)
-          for (int o = 0; o < cout; ++o) host[((size_t)(6 - a) * nb + o) * K + b * 8 + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+          for (int o = 0; o < cout; ++o) host[((size_t)(6 - a) * nb + o) * K + b * 8 + c] = f32_to_h16_bits(W(a * 7 + b, c, o));
     int ns = 0;
     const bool rpair = !getenv("BSR_NO_RPAIR");
     if (rpair) t.a_sub = 2;
@@ -896,7 +913,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     for (int a = 0; a < 7; ++a)
       for (int b = 0; b < 7; ++b)
         for (int c = 0; c < 64; ++c)
-          for (int o = 0; o < 2; ++o) host[((size_t)(6 - a) * 16 + b * 2 + o) * K + c] = f32_to_bf16_bits(W(a * 7 + b, c, o));
+          for (int o = 0; o < 2; ++o) host[((size_t)(6 - a) * 16 + b * 2 + o) * K + c] = f32_to_h16_bits(W(a * 7 + b, c, o));
     int ns = 0;
     const bool rpair = !getenv("BSR_NO_RPAIR");
     if (rpair) t.a_sub = 2;
@@ -921,7 +938,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 3; ++b)
         for (int c = 0; c < 64; ++c)
-          for (int o = 0; o < 16; ++o) host[((size_t)(2 - a) * nb + b * 16 + o) * K + c] = f32_to_bf16_bits(W(a * 3 + b, c, o));
+          for (int o = 0; o < 16; ++o) host[((size_t)(2 - a) * nb + b * 16 + o) * K + c] = f32_to_h16_bits(W(a * 3 + b, c, o));
     int ns = 0;
     const bool rpair = !getenv("BSR_NO_RPAIR");
     if (rpair) t.a_sub = 2;
@@ -952,7 +969,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     for (int b = 0; b < 9; ++b) {
       const int tap = order[b][0] * 3 + order[b][1];
       for (int c = 0; c < cin; ++c)
-        for (int o = 0; o < cout; ++o) host[((size_t)b * cout + o) * K + c] = f32_to_bf16_bits(W(tap, c, o));
+        for (int o = 0; o < cout; ++o) host[((size_t)b * cout + o) * K + c] = f32_to_h16_bits(W(tap, c, o));
     }
     int ns = 0;
     const int16_t co = (int16_t)cout;
@@ -1005,10 +1022,10 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
         for (int o = 0; o < cout; ++o)
           for (int c = 0; c < 32; ++c) {
             if (half == 0) {
-              host[(size_t)o * K + ns * 64 + c] = f32_to_bf16_bits(W(a * 3 + 0, c, o));
-              host[(size_t)o * K + ns * 64 + 32 + c] = f32_to_bf16_bits(W(a * 3 + 1, c, o));
+              host[(size_t)o * K + ns * 64 + c] = f32_to_h16_bits(W(a * 3 + 0, c, o));
+              host[(size_t)o * K + ns * 64 + 32 + c] = f32_to_h16_bits(W(a * 3 + 1, c, o));
             } else {
-              host[(size_t)o * K + ns * 64 + c] = f32_to_bf16_bits(W(a * 3 + 2, c, o));
+              host[(size_t)o * K + ns * 64 + c] = f32_to_h16_bits(W(a * 3 + 2, c, o));
             }
           }
         ++ns;
@@ -1031,7 +1048,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   int ns = 0;
   for (int tap = 0; tap < kh * kw; ++tap) {
     for (int c = 0; c < cin; ++c)
-      for (int o = 0; o < cout; ++o) host[(size_t)o * K + (size_t)tap * t.cin_pad + c] = f32_to_bf16_bits(W(tap, c, o));
+      for (int o = 0; o < cout; ++o) host[(size_t)o * K + (size_t)tap * t.cin_pad + c] = f32_to_h16_bits(W(tap, c, o));
     for (int cb = 0; cb < ncb;) {
       const int na = (pair_k && ncb - cb >= 2) ? 2 : 1;
       TcStep& s = t.steps[ns];
@@ -1069,7 +1086,7 @@ inline bool pack_tc_weights_phase(TmaEncoder& tma, int phase, int cin, int cout,
     const int tap = taps[ti];
     for (int c = 0; c < cin; ++c)
       for (int o = 0; o < cout; ++o)
-        host[(size_t)o * K + ti * t.cin_pad + c] = f32_to_bf16_bits(w[((size_t)tap * cin + c) * cout + o]);
+        host[(size_t)o * K + ti * t.cin_pad + c] = f32_to_h16_bits(w[((size_t)tap * cin + c) * cout + o]);
     for (int cb = 0; cb < ncb;) {
       const int na = (!getenv("BSR_NO_KPAIR") && ncb - cb >= 2) ? 2 : 1;
       TcStep& s = t.steps[ns];
@@ -1097,7 +1114,7 @@ struct TmapKey {
 // pack_tc_weights_phase).
 inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, int in_ld, int in_coff, int H, int W,
                           int stride, int n, const EpiParams& e, const EpiExtra& x, int phase, int num_sms,
-                          int* errflag, cudaStream_t st, int* launches) {
+                          int* errflag, cudaStream_t st, int* launches, const Knobs& kn, PlanCounters* pc) {
   static thread_local std::map<TmapKey, CUtensorMap> cache;
   static thread_local ConvTcParams p;           // 2 KB: keep it off the stack
   memset(&p, 0, sizeof p);
@@ -1160,20 +1177,20 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.epi_bytes = (epi_bytes + 127) / 128 * 128;
   p.steps_bytes = (int)((t.n_steps * sizeof(TcStep) + 127) / 128 * 128);
   p.b_res_kblocks = t.b_res_kblocks;
-  { const char* ab = getenv("BSR_ABLATE"); p.ablate = ab ? atoi(ab) : 0; }
+  p.ablate = kn.ablate;
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
   const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * p.b_res_rows * 128 : 0) + 192 + p.steps_bytes + p.epi_bytes + 512 + 64;
   p.a_sub = t.a_sub;
   p.stage_bytes = t.a_sub * (TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128));
   const int max_smem = 227 * 1024;
-  // Staged TMA-store epilogue (bf16 NHWC outputs whose column groups are multiples of 32 channels), used when the
+  // Staged TMA-store epilogue (h16 NHWC outputs whose column groups are multiples of 32 channels), used when the
   // staging fits without shortening the TMA->MMA pipeline; otherwise the direct-store epilogue runs.
   p.st_chunk = 0;
   int staging = 0;
   const int stages_direct = std::min(8, (max_smem - fixed_bytes) / p.stage_bytes);
   const bool st_ok = p.epi_mode == EPI_GENERIC && e.res1 == nullptr && e.res2 == nullptr && e.out_mode == OUT_T &&
                      t.n_tiles == 1 && p.group_cols % 32 == 0 && e.out_c == p.group_cols && e.out_ld % 8 == 0 &&
-                     e.out_coff % 8 == 0 && p.OH % p.out_scale == 0 && p.OW % p.out_scale == 0 && !getenv("BSR_NO_TMA_STORE");
+                     e.out_coff % 8 == 0 && p.OH % p.out_scale == 0 && p.OW % p.out_scale == 0 && !kn.no_tma_store;
   if (st_ok) {
     // 64 accumulator columns per iteration; double-buffered (2 x 16 KB) if the pipeline keeps its depth, else one buffer
     for (int bufs = 2; bufs >= 1 && !p.st_chunk; --bufs) {
@@ -1183,8 +1200,8 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       // (measured: up2 -13 %, conv1 -10 %, but up3 / clr_up3 with 2 stages +14 %)
       if (ns >= 2 && (ns >= stages_direct || ns >= 4) && (bufs == 2 || ns >= 3)) { p.st_chunk = 16; p.st_bufs = bufs; staging = need; }
     }
-    if (const char* sb = getenv("BSR_ST_BUFS")) {      // experiment knob: force the buffer count where it fits
-      const int bufs = atoi(sb), need = bufs * 128 * 64 * 2;
+    if (kn.st_bufs) {      // experiment knob: force the buffer count where it fits
+      const int bufs = kn.st_bufs, need = bufs * 128 * 64 * 2;
       if ((bufs == 1 || bufs == 2) && (max_smem - fixed_bytes - need) / p.stage_bytes >= 2) { p.st_chunk = 16; p.st_bufs = bufs; staging = need; }
     }
   }
@@ -1213,7 +1230,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       strides[0] = 128;
       box[1] = (uint32_t)p.bw; es[1] = 1;
     }
-    if (!tma.encode_bf16(&m, (void*)((const bf16*)in + in_coff), 4, dims, strides, box, es)) return -3;
+    if (!tma.encode_h16(&m, (void*)((const h16*)in + in_coff), 4, dims, strides, box, es)) return -3;
     if (cache.size() > 4096) cache.clear();
     it = cache.emplace(key, m).first;
   }
@@ -1231,7 +1248,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       uint64_t dims[5] = {(uint64_t)e.out_ld, (uint64_t)sc, (uint64_t)(p.OW / sc), (uint64_t)sc, (uint64_t)n * (uint64_t)(p.OH / sc)};
       uint64_t strides[4] = {ld2, (uint64_t)sc * ld2, (uint64_t)p.OW * ld2, (uint64_t)sc * p.OW * ld2};
       uint32_t box[5] = {32, 1, (uint32_t)p.bw, 1, (uint32_t)p.bh};
-      if (!tma.encode_bf16_store(&m, e.out, 5, dims, strides, box)) return -3;
+      if (!tma.encode_h16_store(&m, e.out, 5, dims, strides, box)) return -3;
       ot = cache.emplace(okey, m).first;       // std::map: `it` (the input map) stays valid
     }
     omap = &ot->second;
@@ -1247,7 +1264,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("BSR_NO_PDL") ? 0 : 1;
+  cfg.numAttrs = kn.no_pdl ? 0 : 1;
   static const ClrWeights no_clr = {};
   const ClrWeights& cw = (p.epi_mode == EPI_CLR && t.clr) ? *t.clr : no_clr;
   cudaError_t le;
@@ -1257,6 +1274,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x, cw, *omap);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }
   (*launches)++;
+  if (pc) { pc->resident += resident && !t.b_resident; pc->pinned += pinned; pc->staged += p.st_chunk != 0; }
   return 0;
 }
 

@@ -1,6 +1,6 @@
 // Bandwidth-bound glue between the convolutions: 256->32 resizes, grey composition, hole mask,
 // temporal sharing (ShareLayer), colour tail, caller-side blends.  T = activation storage type
-// (bf16 in the product path, float in FP32CHECK).  Reference lines are cited per kernel.
+// (h16 in the product path, float in FP32CHECK).  Reference lines are cited per kernel.
 #pragma once
 #include "common.cuh"
 
@@ -26,9 +26,9 @@ __global__ void uv_small_kernel(const float* __restrict__ uv, float* __restrict_
   uvs[idx] = resize8(uv, n, i, j, 3, c);
 }
 
-// conv1 input packing: img fp32 [N,256,256,3] -> bf16 [N][256][264][8]; packed pixel xp holds image pixel
+// conv1 input packing: img fp32 [N,256,256,3] -> h16 [N][256][264][8]; packed pixel xp holds image pixel
 // xp-3 (zero outside the image, channels 3..7 zero), so the 7-tap row window of output x starts at xp = x.
-__global__ void pack_img_kernel(const float* __restrict__ img, bf16* __restrict__ out, long long n_rows) {
+__global__ void pack_img_kernel(const float* __restrict__ img, h16* __restrict__ out, long long n_rows) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_rows * (IMG + 8)) return;
   int xp = (int)(idx % (IMG + 8));
@@ -37,10 +37,8 @@ __global__ void pack_img_kernel(const float* __restrict__ img, bf16* __restrict_
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (x >= 0 && x < IMG) {
     const float* s = img + (row * IMG + x) * 3;
-    __nv_bfloat162 a = __floats2bfloat162_rn(s[0], s[1]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(s[2], 0.f);
-    o.x = *reinterpret_cast<uint32_t*>(&a);
-    o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.x = pack_h16x2(s[0], s[1]);
+    o.y = pack_h16x2(s[2], 0.f);
   }
   reinterpret_cast<uint4*>(out)[idx] = o;
 }
@@ -125,9 +123,9 @@ __global__ void assemble_uv_kernel(T* __restrict__ x, int ld, const float* __res
   else stf<T>(x, pix * ld + z0 + (k - 3), 0.f);
 }
 
-// bf16 product-path version of assemble_uv_kernel: one thread per 16-byte (8-channel) chunk of the written range
+// h16 product-path version of assemble_uv_kernel: one thread per 16-byte (8-channel) chunk of the written range
 // [uv_off & ~7, ld): channels [uv_off, uv_off+3) = uv, everything above = 0, channels below uv_off are preserved.
-__global__ void assemble_uv_vec_kernel(bf16* __restrict__ x, int ld, const float* __restrict__ uvs, int uv_off, int n_pix) {
+__global__ void assemble_uv_vec_kernel(h16* __restrict__ x, int ld, const float* __restrict__ uvs, int uv_off, int n_pix) {
   const int k0 = uv_off >> 3, nk = (ld >> 3) - k0;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n_pix * nk) return;
@@ -137,12 +135,12 @@ __global__ void assemble_uv_vec_kernel(bf16* __restrict__ x, int ld, const float
   uint4 w = make_uint4(0u, 0u, 0u, 0u);
   if (8 * k < uv_off + 3) {                      // chunk holds preserved and / or uv channels
     if (8 * k < uv_off) w = *dst;
-    bf16* e = reinterpret_cast<bf16*>(&w);
+    h16* e = reinterpret_cast<h16*>(&w);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = 8 * k + i;
-      if (c >= uv_off + 3) e[i] = __float2bfloat16_rn(0.f);
-      else if (c >= uv_off) e[i] = __float2bfloat16_rn(uvs[pix * 3 + (c - uv_off)]);
+      if (c >= uv_off + 3) e[i] = f32_to_h16(0.f);
+      else if (c >= uv_off) e[i] = f32_to_h16(uvs[pix * 3 + (c - uv_off)]);
     }
   }
   *dst = w;
@@ -291,8 +289,8 @@ __global__ void res_tail_kernel(const T* __restrict__ x, int ldx, T* __restrict_
   stf<T>(out, pix * ldo + c, leaky(ldf<T>(x, pix * ldx + c)));
 }
 
-// bf16 product-path version: 8 channels (16 bytes) per thread; needs c0, c1, ldx, ldo multiples of 8.
-__global__ void res_tail_vec_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, int c0, int c1,
+// h16 product-path version: 8 channels (16 bytes) per thread; needs c0, c1, ldx, ldo multiples of 8.
+__global__ void res_tail_vec_kernel(const h16* __restrict__ x, int ldx, h16* __restrict__ out, int ldo, int c0, int c1,
                                     long long n_pix) {
   const int span = (c1 - c0) >> 3;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,11 +298,11 @@ __global__ void res_tail_vec_kernel(const bf16* __restrict__ x, int ldx, bf16* _
   const size_t pix = (size_t)(idx / span);
   const int c = c0 + 8 * (int)(idx % span);
   uint4 v = *reinterpret_cast<const uint4*>(x + pix * ldx + c);
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  uint32_t* h = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    h[i] = __floats2bfloat162_rn(leaky(f.x), leaky(f.y));
+    const float2 f = unpack_h16x2(h[i]);
+    h[i] = pack_h16x2(leaky(f.x), leaky(f.y));
   }
   *reinterpret_cast<uint4*>(out + pix * ldo + c) = v;
 }

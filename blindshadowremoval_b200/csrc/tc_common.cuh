@@ -8,7 +8,15 @@
 
 #include <string>
 
+#include "common.cuh"
+
 namespace bsr {
+
+#ifdef BSR_ACT_BF16
+constexpr CUtensorMapDataType kTmaH16 = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+constexpr CUtensorMapDataType kTmaH16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
 
 // ------------------------------------------------------------------------------------------
 // host: cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no libcuda link,
@@ -32,14 +40,14 @@ struct TmaEncoder {
     return true;
   }
 
-  // bf16 tensor, `rank` dims innermost-first, 128-byte swizzle, zero fill out of bounds.
-  bool encode_bf16(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+  // h16 tensor, `rank` dims innermost-first, 128-byte swizzle, zero fill out of bounds.
+  bool encode_h16(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides) {
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
+    CUresult r = fn(out, kTmaH16, (cuuint32_t)rank, base, gd, gs, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -54,14 +62,14 @@ struct TmaEncoder {
     return true;
   }
 
-  // Output-side map for TMA stores: bf16, 64-byte swizzle (inner box = 32 channels), no L2 promotion.
-  bool encode_bf16_store(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+  // Output-side map for TMA stores: h16, 64-byte swizzle (inner box = 32 channels), no L2 promotion.
+  bool encode_h16_store(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box) {
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
+    CUresult r = fn(out, kTmaH16, (cuuint32_t)rank, base, gd, gs, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -198,8 +206,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate, issued by one thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem] . B[smem]^T, h16 inputs, fp32 accumulate, issued by one thread.
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -213,12 +221,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=h16 (bits 7-9, 10-12 = 1), both
 // K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+__host__ __device__ constexpr uint32_t umma_idesc_h16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 B (64 bf16 of K),
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 B (64 h16 of K),
 // 8-row groups 1024 B apart (SBO), version 1 (sm_100), layout type 2 (SWIZZLE_128B).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -233,7 +241,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Descriptor built from its two 32-bit halves: lo = (addr >> 4) | LBO field, hi = SBO | version | swizzle (constant).
 constexpr uint32_t kUmmaDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+__device__ __forceinline__ void umma_h16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
@@ -272,11 +280,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
 }
 
 }  // namespace bsr

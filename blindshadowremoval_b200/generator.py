@@ -21,13 +21,21 @@ from .weights import VARIANTS, random_weights
 _LIB = None
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsr.so")
-PRECISIONS = ("bf16", "fp32check")
+# 'tc16' = the 16-bit tensor-core product path (binary16 storage, see include/bsr.h); 'bf16' and 'f16' are accepted
+# aliases of it ('bf16' is the name round 1 used and north_star's wording), 'fp32check' the CUDA-core check mode.
+PRECISIONS = ("tc16", "fp32check")
+_PRECISION_ALIASES = {"bf16": "tc16", "f16": "tc16", "fp16": "tc16"}
+PLAN_COUNTERS = ("resident", "pinned", "staged", "attn_fused", "graph_replays")
 IMG = 256
 FEAT = 32
 
 _F = ctypes.POINTER(ctypes.c_float)
 _SYMBOLS = {
     "bsr_version": (ctypes.c_char_p, []),
+    "bsr_act_dtype": (ctypes.c_char_p, []),
+    "bsr_convert_h16": (None, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "bsr_check": (ctypes.c_int, [ctypes.c_void_p]),
+    "bsr_plan_counter": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bsr_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t]),
     "bsr_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "bsr_destroy": (ctypes.c_int, [ctypes.c_void_p]),
@@ -49,11 +57,13 @@ _SYMBOLS = {
 }
 
 
-def load_library(path: str = LIB_PATH):
-    """dlopen libbsr.so and bind every symbol of include/bsr.h; raises if anything is missing."""
+def load_library(path: Optional[str] = None):
+    """dlopen libbsr.so and bind every symbol of include/bsr.h; raises if anything is missing.
+    BSR_LIB=<path> selects another build of the same ABI (e.g. the bfloat16-storage A/B build, `make bf16`)."""
     global _LIB
     if _LIB is not None:
         return _LIB
+    path = path or os.environ.get("BSR_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)" % path)
@@ -113,17 +123,45 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _as_host_array(x):
+    """The reference hands the model TF EagerTensors (train_test_GSC.py:419-422); anything that is not a CUDA torch
+    tensor but converts to NumPy (``.numpy()`` / ``__array__``) takes the host path."""
+    if x is None or isinstance(x, np.ndarray):
+        return x
+    if getattr(x, "is_cuda", False):
+        return x
+    if hasattr(x, "numpy"):
+        return np.asarray(x.numpy())
+    if hasattr(x, "__array__"):
+        return np.asarray(x)
+    return x
+
+
+def act_dtype() -> str:
+    """Storage type of the 16-bit path of the loaded library: 'f16' (default build) or 'bf16'."""
+    return load_library().bsr_act_dtype().decode()
+
+
+def convert_h16(x: np.ndarray) -> np.ndarray:
+    """The library's host-side float -> 16-bit storage rounding (uint16 bit patterns)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.shape, np.uint16)
+    load_library().bsr_convert_h16(x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), x.size)
+    return out
+
+
 class Generator:
     """B200 replacement of ``Generator()`` (train_test_GSC.py:120 / train_with_TSM.py).
 
     variant   'gsc' (model.py) or 'tsm' (model_with_TSM.py)
-    precision 'bf16' (tcgen05 product path) or 'fp32check' (CUDA-core check mode)
+    precision 'tc16' (tcgen05 product path; aliases 'bf16', 'f16') or 'fp32check' (CUDA-core check mode)
     """
 
-    def __init__(self, variant: str = "gsc", precision: str = "bf16", device: int = 0, micro_batch: int = 128,
+    def __init__(self, variant: str = "gsc", precision: str = "tc16", device: int = 0, micro_batch: int = 128,
                  weights: Optional[Dict[str, np.ndarray]] = None, seed: Optional[int] = None):
         if variant not in VARIANTS:
             raise ValueError("variant must be one of %r" % (VARIANTS,))
+        precision = _PRECISION_ALIASES.get(precision, precision)
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %r" % (PRECISIONS,))
         self.variant, self.precision, self.device = variant, precision, int(device)
@@ -157,12 +195,23 @@ class Generator:
                  training: bool = False, want=("gs", "con_rgb", "mask22", "dif")):
         if training:
             raise BsrError("training=True is not supported: this is the inference forward only")
+        if hasattr(share, "numpy") and not hasattr(share, "item"):
+            share = share.numpy()                                   # tf.constant(True) (train_with_TSM.py:676)
         share = bool(share.item() if hasattr(share, "item") else share)
-        if isinstance(inputs, np.ndarray):
+        inputs, uv, reg = _as_host_array(inputs), _as_host_array(uv), _as_host_array(reg)
+        host = [isinstance(a, np.ndarray) for a in (inputs, uv, reg) if a is not None]
+        if all(host):
             return self._call_host(inputs, uv, reg, frame, share, want)
+        if any(host):
+            raise BsrError("inputs, uv and reg must all be CUDA tensors (device path) or all host arrays (host path)")
         import torch
-        if not (inputs.is_cuda and uv.is_cuda):
-            raise BsrError("pass CUDA tensors (device path) or NumPy arrays (host path)")
+        for name, a in (("inputs", inputs), ("uv", uv), ("reg", reg)):
+            if a is None:
+                continue
+            if not getattr(a, "is_cuda", False):
+                raise BsrError("%s: pass CUDA tensors (device path) or NumPy arrays (host path)" % name)
+            if a.device.index != self.device:
+                raise BsrError("%s lives on cuda:%s, this generator on cuda:%d" % (name, a.device.index, self.device))
         n = self._check_shapes(tuple(inputs.shape), tuple(uv.shape), None if reg is None else tuple(reg.shape), frame)
         inputs = inputs.contiguous().float()
         uv = uv.contiguous().float()
@@ -242,11 +291,15 @@ class Generator:
         ``want_raw``, ``(rgb, mask_pred, gs, mask22)``."""
         import torch
         is_np = isinstance(chunk, np.ndarray)
+        if not is_np and not getattr(chunk, "is_cuda", False) and (hasattr(chunk, "numpy") or hasattr(chunk, "__array__")):
+            chunk, is_np = _as_host_array(chunk), True             # TF EagerTensor and friends
         t = torch.from_numpy(np.ascontiguousarray(chunk, dtype=np.float32)).cuda(self.device) if is_np else chunk
         if t.dim() != 4 or tuple(t.shape[1:3]) != (IMG, IMG) or int(t.shape[3]) not in CHUNK_LAYOUTS:
             raise ValueError("chunk must be [F,256,256,C] with C in {13, 16, 17}, got %r" % (tuple(t.shape),))
         if not t.is_cuda:
             raise BsrError("pass a CUDA tensor (device path) or a NumPy array")
+        if t.device.index != self.device:
+            raise BsrError("chunk lives on cuda:%s, this generator on cuda:%d" % (t.device.index, self.device))
         n = int(t.shape[0])
         if n <= 0:
             raise ValueError("empty chunk")
@@ -326,23 +379,40 @@ class Generator:
     def caller_glue(self, con_rgb, dif, face):
         import torch
         n = con_rgb.shape[0]
-        rgb_c, mask_pred = torch.empty_like(con_rgb), torch.empty_like(dif)
+        self._same_device(con_rgb=con_rgb, dif=dif, face=face)
+        # dense outputs: the kernel writes contiguous NHWC whatever the strides of the inputs were
+        rgb_c = torch.empty(tuple(con_rgb.shape), dtype=torch.float32, device=con_rgb.device)
+        mask_pred = torch.empty(tuple(dif.shape), dtype=torch.float32, device=con_rgb.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(con_rgb.device).cuda_stream)
-        self._check(self._lib.bsr_caller_glue(self._h, _ptr(con_rgb.contiguous()), _ptr(dif.contiguous()),
+        self._check(self._lib.bsr_caller_glue(self._h, _ptr(con_rgb.contiguous().float()), _ptr(dif.contiguous().float()),
                                               _ptr(face.contiguous().float()), n, _ptr(rgb_c), _ptr(mask_pred), stream))
         return rgb_c, mask_pred
 
+    def _same_device(self, **tensors):
+        for name, a in tensors.items():
+            if not getattr(a, "is_cuda", False) or a.device.index != self.device:
+                raise BsrError("%s must be a CUDA tensor on cuda:%d" % (name, self.device))
+
     def composite(self, pred, inp, m):
         import torch
-        out = torch.empty_like(pred)
+        self._same_device(pred=pred, inp=inp, m=m)
+        out = torch.empty(tuple(pred.shape), dtype=torch.float32, device=pred.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(pred.device).cuda_stream)
-        self._check(self._lib.bsr_composite(self._h, _ptr(pred.contiguous()), _ptr(inp.contiguous()),
-                                            _ptr(m.expand_as(pred).contiguous()), pred.numel(), _ptr(out), stream))
+        self._check(self._lib.bsr_composite(self._h, _ptr(pred.contiguous().float()), _ptr(inp.contiguous().float()),
+                                            _ptr(m.expand_as(pred).contiguous().float()), pred.numel(), _ptr(out), stream))
         return out
 
     # -- introspection -----------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._lib.bsr_launch_count(self._h))
+
+    def check(self) -> None:
+        """Synchronise the last forward and raise BsrError if a device watchdog fired (bsr_check)."""
+        self._check(self._lib.bsr_check(self._h))
+
+    def plan_counters(self) -> Dict[str, int]:
+        """Launch-plan counters of the last forward (bsr_plan_counter)."""
+        return {k: int(self._lib.bsr_plan_counter(self._h, i)) for i, k in enumerate(PLAN_COUNTERS)}
 
     def workspace_bytes(self) -> int:
         return int(self._lib.bsr_workspace_bytes(self._h))

@@ -11,7 +11,12 @@
  * success or a negative BSR_E* code; bsr_last_error() gives the message.  A handle is bound to one
  * device and is not thread-safe (one handle per GPU per process, as the reference drives one model
  * from one Python thread).  forward_* calls are asynchronous on the given CUDA stream and perform no
- * allocation; training=True has no equivalent here (inference only).
+ * allocation: the workspace, the staging of the host / chunk entry points and every tensor map are
+ * sized at bsr_create / bsr_load_weights time (the only exception is a handle created with
+ * BSR_DEBUG_KEEP=1, whose debug captures allocate).  Consecutive forwards of one handle share that
+ * workspace, so the library orders them itself: every forward waits (on the device, no host sync) for
+ * the previous forward of the same handle, whatever streams the two were issued on.
+ * training=True has no equivalent here (inference only).
  */
 #ifndef BSR_H_
 #define BSR_H_
@@ -26,17 +31,26 @@ extern "C" {
 typedef struct bsr_handle bsr_handle;
 
 enum { BSR_VARIANT_GSC = 0, BSR_VARIANT_TSM = 1 };
-/* BF16: bf16 activations/weights, tcgen05 tensor-core convs, fp32 accumulation (the product path).
- * FP32CHECK: fp32 activations/weights on CUDA cores — the check mode north_star asks for (<=1e-4). */
-enum { BSR_PRECISION_BF16 = 0, BSR_PRECISION_FP32CHECK = 1 };
+/* TC16: 16-bit activations/weights, tcgen05 tensor-core convs + attention, fp32 accumulation (the product path).
+ *   The storage type is IEEE binary16 (bsr_act_dtype() == "f16"): kind::f16 UMMAs take it at the bfloat16 rate and
+ *   its 11-bit significand is what keeps the outputs within north_star's 1e-2 of the fp32 reference; conversions
+ *   saturate at +-65504.  BSR_PRECISION_BF16 is the historical name of the same mode.
+ * FP32CHECK: fp32 activations/weights on CUDA cores - the check mode north_star asks for (<=1e-4). */
+enum { BSR_PRECISION_TC16 = 0, BSR_PRECISION_BF16 = 0, BSR_PRECISION_FP32CHECK = 1 };
 enum {
-  BSR_OK = 0, BSR_EINVAL = -1, BSR_ECUDA = -2, BSR_ENOMEM = -3, BSR_ESTATE = -4, BSR_EUNSUPPORTED = -5
+  BSR_OK = 0, BSR_EINVAL = -1, BSR_ECUDA = -2, BSR_ENOMEM = -3, BSR_ESTATE = -4, BSR_EUNSUPPORTED = -5,
+  BSR_EDEVICE = -6   /* a kernel's in-kernel watchdog fired (mbarrier wait timed out): outputs are invalid */
 };
 
 #define BSR_IMG 256   /* Config.IMG_SIZE, train_test_GSC.py:31 */
 #define BSR_FEAT 32   /* bottleneck resolution after three stride-2 convs, model.py:231-234 */
 
 const char* bsr_version(void);
+/* "f16" (default build) or "bf16" (-DBSR_ACT_BF16): storage type of the TC16 path. */
+const char* bsr_act_dtype(void);
+/* Host utility (no device work): the library's own float -> 16-bit storage conversion (round to nearest even,
+ * binary16 saturating at +-65504), exposed so the converter's rounding can be tested against NumPy. */
+void bsr_convert_h16(const float* in, unsigned short* out, size_t n);
 /* Host utility for the checkpoint converter (no device work): CRC-32C (Castagnoli) of `n` bytes, the checksum
  * TensorFlow stores (masked) per leveldb block of `ckpt-N.index` and per tensor in BundleEntryProto.crc32c - what
  * `checkpoint.restore` verifies (train_test_GSC.py:362-365).  crc = 0 starts a new checksum; pass the previous result
@@ -116,8 +130,19 @@ int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const flo
 int bsr_composite(bsr_handle* h, const float* pred, const float* inp, const float* m, size_t n_elems,
                   float* out, void* cuda_stream);
 
+/* Device-side error check.  Kernels never hang on a protocol error: a 2 s watchdog in every mbarrier wait sets a
+ * device flag and the kernel drains.  The flag is copied to pinned host memory at the end of every forward; every
+ * forward_* entry point first looks at it (no sync) and returns BSR_EDEVICE if an EARLIER forward tripped it.
+ * bsr_check() synchronises the handle's last forward and reports the flag of everything issued so far (and clears
+ * it): BSR_OK or BSR_EDEVICE.  The *_host entry points do this themselves before returning. */
+int bsr_check(bsr_handle* h);
+
 /* Introspection for tests/bench. */
 int bsr_launch_count(const bsr_handle* h);          /* kernels launched by the last forward call */
+/* Launch-plan counters of the last forward (tests assert that the benchmarked code paths really ran):
+ * which = 0: conv launches with resident weights, 1: with per-CTA pinned weights (qkv), 2: staged TMA-store epilogues,
+ * 3: fused attention+w launches, 4: micro-batches replayed from a captured CUDA graph. */
+int bsr_plan_counter(const bsr_handle* h, int which);
 size_t bsr_workspace_bytes(const bsr_handle* h);
 /* Copy a named intermediate of the LAST micro-batch to host as fp32 (dense NHWC, logical channels).
  * Names: x1 x2 x3 x_in0 res0..res5 up1 up2 up3 x_in3 clr_up1 clr_up2 clr_up3 bmask dif_small.

@@ -16,8 +16,8 @@ from blindshadowremoval_b200.weights import random_weights
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
-BF16_TOL = 1e-2          # max-abs on clipped [0,1] outputs (north_star)
-BF16_TOL_RAW = 3e-2      # unclipped tensors (gs, raw con_rgb range is about [-0.3, 1.3] with random weights)
+BF16_TOL = 1e-2          # north_star: max-abs <= 1e-2 for the 16-bit tensor-core path, on every output, raw (unclipped)
+BF16_TOL_RAW = 1e-2
 BF16_PSNR_DB = 40.0
 
 
@@ -87,10 +87,10 @@ def test_bf16_tensor_core_path_matches_oracle(G, variant, n, frame):
     ref0 = oracle(variant, w, d, frame)
     flipped = bm != ref0["bmask"]
     # a flipped cell must be a near-threshold cell of the oracle, and there must be few of them
-    assert flipped.mean() < 0.03, flipped.mean()
+    assert flipped.mean() < 0.006, flipped.mean()
     if flipped.any():
-        assert np.abs(ref0["dif_small"][flipped] - 0.1).max() < 2e-2
-    assert np.abs(dsm - ref0["dif_small"]).max() < 2e-2
+        assert np.abs(ref0["dif_small"][flipped] - 0.1).max() < 4e-3
+    assert np.abs(dsm - ref0["dif_small"]).max() < 4e-3
     ref = oracle(variant, w, d, frame, bmask=bm)
     clip = lambda a: np.clip(a, 0.0, 1.0)
     report = {}
@@ -100,10 +100,9 @@ def test_bf16_tensor_core_path_matches_oracle(G, variant, n, frame):
     assert psnr(clip(got["con_rgb"]), clip(ref["con_rgb"])) >= BF16_PSNR_DB
     assert psnr(got["dif"], ref["dif"]) >= BF16_PSNR_DB
     assert psnr(got["mask22"], ref["mask22"]) >= BF16_PSNR_DB
-    assert np.abs(clip(got["con_rgb"]) - clip(ref["con_rgb"])).max() <= 2 * BF16_TOL
-    assert np.mean(np.abs(clip(got["con_rgb"]) - clip(ref["con_rgb"])) <= BF16_TOL) > 0.9995
+    assert np.abs(got["con_rgb"] - ref["con_rgb"]).max() <= BF16_TOL_RAW
     assert np.abs(got["dif"] - ref["dif"]).max() <= BF16_TOL
-    assert np.abs(got["mask22"] - ref["mask22"]).max() <= 2 * BF16_TOL
+    assert np.abs(got["mask22"] - ref["mask22"]).max() <= BF16_TOL
     assert np.abs(got["gs"] - ref["gs"]).max() <= BF16_TOL_RAW
     gen.close()
 
@@ -121,7 +120,7 @@ def test_bf16_intermediates_track_oracle(G):
         a, b = gen.debug_read(name), ref[name].reshape(-1)
         assert a.size == b.size, name
         rel = np.sqrt(((a - b) ** 2).mean()) / np.sqrt((b ** 2).mean())
-        assert rel < 1.5e-2, (name, rel)
+        assert rel < 2.5e-3, (name, rel)
     gen.close()
 
 
@@ -402,4 +401,193 @@ def test_evaluate_sfw_runs_on_device_and_matches_manual_metrics(G):
     auc = np.mean([sfw_auc((chunks[i][0, ..., 6:7] == 2), mp) for i, mp in seen])
     ss = np.mean([ssim(chunks[i][0, ..., 6:7], mp) for i, mp in seen])
     assert abs(out["auc"] - auc) < 1e-12 and abs(out["ssim"] - ss) < 1e-12 and np.isfinite(out["psnr"])
+    gen.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the BENCHMARKED configuration (256 images, micro-batch 128: resident / pinned weights, staged stores,
+# 64/128-image host chunks) against the oracle, peaked softmax rows, and the attention kernel on its own.
+def _check_against_oracle(variant, w, d, frame, got, bm, idx, tol=BF16_TOL):
+    """Compare device outputs of the images `idx` (whole TSM chunks) with the oracle run on exactly those images
+    with the device's hole mask."""
+    sub = {k: v[idx] for k, v in d.items()}
+    ref = oracle(variant, w, sub, frame, bmask=bm[idx])
+    ref0 = oracle(variant, w, sub, frame)
+    flips = float((bm[idx] != ref0["bmask"]).mean())
+    assert flips < 0.006, flips
+    worst = {}
+    for k in ("gs", "con_rgb", "mask22", "dif"):
+        worst[k] = float(np.abs(got[k][idx] - ref[k]).max())
+        assert worst[k] <= tol, (k, worst[k])
+        assert psnr(got[k][idx], ref[k]) >= BF16_PSNR_DB, k
+    return worst, flips
+
+
+def test_benchmark_configuration_gsc_256_images_mb128_matches_oracle(G):
+    """BASELINE config 4 exactly as bench.py runs it: n = 256, micro_batch = 128, device path and host path.  The second
+    micro-batch repeats the first, so (i) both must agree bit for bit, (ii) 16 images sampled from the last micro-batch
+    (whose hole mask the handle keeps) are compared with the oracle, (iii) the launch plan must really have used the
+    large-batch code paths (per-CTA pinned qkv weights, resident weights, staged TMA-store epilogues)."""
+    w, _ = case("gsc", 2, 1)
+    base = make_inputs(128, seed=21, with_reg=True)
+    d = {k: np.concatenate([v, v]) for k, v in base.items()}
+    gen = G.Generator("gsc", "tc16", device=0, micro_batch=128, weights=w)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    out = gen(t["img"], t["uv"], None)
+    gen.check()
+    pc = gen.plan_counters()
+    assert pc["pinned"] >= 12 and pc["resident"] >= 12 and pc["staged"] >= 8 and pc["attn_fused"] == 12, pc
+    got = dict(zip(("gs", "con_rgb", "mask22", "dif"), (o.cpu().numpy() for o in out)))
+    for k, v in got.items():
+        assert np.array_equal(v[:128], v[128:]), k                      # micro-batch 0 == micro-batch 1
+    bm = gen.debug_read("bmask").reshape(128, 32, 32, 1)
+    idx = np.arange(0, 128, 8)                                           # 16 images
+    half = {k: v[128:] for k, v in got.items()}
+    worst, flips = _check_against_oracle("gsc", w, base, 1, half, bm, idx)
+    print("gsc n=256 mb=128: worst", worst, "flip rate", flips)
+    # host path (pipelined 64-image chunks, ramped schedule) gives the same bits
+    hg, hrgb, hm, hdif = gen(d["img"], d["uv"], None)
+    assert np.array_equal(hrgb, got["con_rgb"]) and np.array_equal(hdif, got["dif"]) and np.array_equal(hg, got["gs"])
+    gen.close()
+
+
+@pytest.mark.parametrize("frame,n", [(2, 256), (10, 240)])
+def test_benchmark_configuration_tsm_mb128_matches_oracle(G, frame, n):
+    """The TSM variant at micro-batch 128 (frame 2: 64 chunks per micro-batch; frame 10: 12 chunks = 120 images per
+    micro-batch): sampled whole chunks of the last micro-batch against the oracle."""
+    w, _ = case("tsm", 4, 2)
+    d = make_inputs(n, seed=22, with_reg=True)
+    gen = G.Generator("tsm", "tc16", device=0, micro_batch=128, weights=w)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    out = gen(t["img"], t["uv"], t["reg"], frame=frame, share=True)
+    gen.check()
+    got = dict(zip(("gs", "con_rgb", "mask22", "dif"), (o.cpu().numpy() for o in out)))
+    step = 128 // frame * frame
+    last0 = (n - 1) // step * step                                       # first image of the last micro-batch
+    m = n - last0
+    bm_last = gen.debug_read("bmask").reshape(m, 32, 32, 1)
+    n_chunks = m // frame
+    pick = sorted(set(np.linspace(0, n_chunks - 1, 16 // frame if frame == 2 else 2).astype(int)))
+    idx_local = np.concatenate([np.arange(c * frame, (c + 1) * frame) for c in pick])
+    bm = np.zeros((n, 32, 32, 1), np.float32)
+    bm[last0:] = bm_last
+    worst, flips = _check_against_oracle("tsm", w, d, frame, got, bm, last0 + idx_local)
+    print("tsm frame", frame, "n", n, "worst", worst, "flip rate", flips)
+    gen.close()
+
+
+def _peaked_weights(variant, gain, wseed=1234):
+    """theta x gain (logits are unscaled in the reference, model.py:51-52) and the damping of non_local/w removed."""
+    w = dict(random_weights(variant, wseed))
+    for i in range(6):
+        w["res_stack/%d/non_local/theta/kernel" % i] = w["res_stack/%d/non_local/theta/kernel" % i] * np.float32(gain)
+        w["res_stack/%d/non_local/w/kernel" % i] = w["res_stack/%d/non_local/w/kernel" % i] * np.float32(1.0 / 0.35)
+    return w
+
+
+def _attention_ref(qk, vt):
+    """softmax(theta.phi^T).g in float64 from the projections the device actually read (model.py:51-53)."""
+    q, k = qk[..., :128].astype(np.float64), qk[..., 128:].astype(np.float64)
+    v = vt.astype(np.float64).transpose(0, 2, 1)                          # [n,1024,128]
+    s = q @ k.transpose(0, 2, 1)
+    mx = s.max(-1, keepdims=True)
+    p = np.exp(s - mx)
+    return (p / p.sum(-1, keepdims=True)) @ v, mx[..., 0]
+
+
+@pytest.mark.parametrize("gain", [1.0, 8.0, 64.0])
+def test_attention_kernel_alone_matches_float64_softmax(G, gain):
+    """The attention kernel in isolation: O = softmax(QK^T)V against float64 on the very Q, K, V the device read
+    (debug captures of res block 0 and 5), for the calibrated weights (gain 1), peaked rows (gain 8: row-max logits of
+    50-100) and near-one-hot rows (gain 64)."""
+    w = _peaked_weights("gsc", gain)
+    d = make_inputs(2, seed=5, with_reg=True)
+    gen, _ = run_device(G, "gsc", "tc16", w, d, 1)
+    for blk in (0, 5):
+        qk = gen.debug_read("qk%d" % blk).reshape(2, 1024, 256)
+        vt = gen.debug_read("vt%d" % blk).reshape(2, 128, 1024)
+        o = gen.debug_read("attn_o%d" % blk).reshape(2, 1024, 128)
+        ref, mx = _attention_ref(qk, vt)
+        scale = np.abs(ref).max()
+        err = np.abs(o - ref).max()
+        print("gain", gain, "block", blk, "row-max logit median %.1f max %.1f" % (np.median(mx), mx.max()),
+              "max|O - ref| %.2e of scale %.2f" % (err, scale))
+        assert np.isfinite(o).all()
+        if gain == 8.0:
+            assert np.median(mx) > 30.0                                   # the case really has peaked rows
+        assert err <= 2.5e-3 * max(scale, 1.0), (blk, err, scale)         # P and O are stored with 11-bit significands
+    gen.close()
+
+
+def test_large_logit_network_matches_oracle(G):
+    """End to end with peaked softmax rows (theta x 8, non_local/w undamped): the network output still tracks the
+    oracle.  The comparison is worse conditioned than the calibrated case (a near-one-hot softmax amplifies rounding of
+    its logits), hence PSNR and a relaxed max-abs, stated here: 3e-2."""
+    w = _peaked_weights("gsc", 8.0)
+    d = make_inputs(2, seed=6, with_reg=True)
+    from oracle.calibrate import centre_hole_threshold
+    w = centre_hole_threshold(w, d["img"], d["uv"], None, variant="gsc", frame=1)
+    gen, got = run_device(G, "gsc", "tc16", w, d, 1)
+    bm = gen.debug_read("bmask").reshape(2, 32, 32, 1)
+    ref = oracle("gsc", w, d, 1, bmask=bm)
+    rep = {k: (float(np.abs(got[k] - ref[k]).max()), psnr(got[k], ref[k])) for k in ("gs", "con_rgb", "mask22", "dif")}
+    print("large-logit e2e", rep)
+    for k, (mx, ps) in rep.items():
+        assert ps >= BF16_PSNR_DB and mx <= 3e-2, (k, mx, ps)
+    gen.close()
+
+
+def test_device_error_flag_and_ordering_across_streams(G):
+    """bsr_check() needs no debug handle; forwards of one handle issued on different streams are ordered by the library
+    (they share one workspace), so interleaving the device path on a side stream with the host path gives the bits of
+    serial execution."""
+    w, d = case("gsc", 2, 1)
+    os.environ.pop("BSR_DEBUG_KEEP", None)
+    try:
+        gen = G.Generator("gsc", "tc16", device=0, micro_batch=2, weights=w)
+    finally:
+        os.environ["BSR_DEBUG_KEEP"] = "1"
+    img, uv = torch.from_numpy(d["img"]).cuda(), torch.from_numpy(d["uv"]).cuda()
+    ref = gen(img, uv, None, want=("con_rgb",))[1].clone()
+    gen.check()
+    assert gen.debug_read("errflag")[0] == 0                              # readable without BSR_DEBUG_KEEP
+    with pytest.raises(G.BsrError):
+        gen.debug_read("bmask")                                           # intermediates do need it
+    side = torch.cuda.Stream()
+    other = {k: np.ascontiguousarray(v[::-1]) for k, v in d.items()}
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            a = gen(img, uv, None, want=("con_rgb",))[1]                  # async on the side stream
+        b = gen(other["img"], other["uv"], None, want=("con_rgb",))[1]    # host path on the handle's own streams
+        c = gen(img, uv, None, want=("con_rgb",))[1]                      # async on the default stream
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref) and torch.equal(c, ref)
+        assert np.array_equal(b[::-1], ref.cpu().numpy())
+    gen.check()
+    # a CPU `reg` with CUDA inputs is rejected instead of being handed to the kernel as a device pointer
+    t = G.Generator("tsm", "tc16", device=0, micro_batch=2, seed=1)
+    with pytest.raises(G.BsrError):
+        t(img, uv, torch.zeros(2, 256, 256, 6), frame=2)
+    t.close()
+    gen.close()
+
+
+def test_eager_tensor_like_inputs_take_the_host_path(G):
+    """The reference passes TF EagerTensors: objects that are neither NumPy nor torch but have .numpy()."""
+    class Eager:
+        def __init__(self, a):
+            self._a = a
+            self.shape = a.shape
+
+        def numpy(self):
+            return self._a
+    w, d = case("gsc", 2, 1)
+    gen = G.Generator("gsc", "tc16", device=0, micro_batch=2, weights=w)
+    a = gen(Eager(d["img"]), Eager(d["uv"]), Eager(d["reg"]), chuck=1, training=False)
+    b = gen(d["img"], d["uv"], None)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    chunk = np.concatenate([d["img"], d["uv"], d["reg"], d["face"]], axis=3)
+    r1, m1 = gen.forward_chunk(Eager(chunk))
+    r2, m2 = gen.forward_chunk(chunk)
+    assert np.array_equal(r1, r2) and np.array_equal(m1, m2)
     gen.close()
