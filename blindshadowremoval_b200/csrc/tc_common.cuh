@@ -221,10 +221,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=h16 (bits 7-9, 10-12 = 1), both
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A / B format at bits 7-9 / 10-12 (0 = f16, 1 = bf16), both
 // K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t umma_idesc_h16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (kUmmaOperandFmt << 7) | (kUmmaOperandFmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 B (64 h16 of K),
 // 8-row groups 1024 B apart (SBO), version 1 (sm_100), layout type 2 (SWIZZLE_128B).

@@ -181,6 +181,70 @@ def frame_maps_compact(lm: np.ndarray, uv: Optional[np.ndarray] = None, lm_ref: 
     return out
 
 
+# landmark order after a horizontal flip (utils.py:360-364, 1-based there)
+_MIRROR_ORDER = np.asarray([17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18,
+                            28, 29, 30, 31, 36, 35, 34, 33, 32, 46, 45, 44, 43, 48, 47, 40, 39, 38, 37, 42, 41,
+                            55, 54, 53, 52, 51, 50, 49, 60, 59, 58, 57, 56, 65, 64, 63, 62, 61, 68, 67, 66], np.int64) - 1
+
+
+def crop_and_resize(img: np.ndarray, lm: np.ndarray, fsize: int = IMG):
+    """``face_crop_and_resize(img, lm, fsize)`` of utils.py:356-433 with aug=False (the test-time call of
+    dataset.py:165, 632): square box of half-size 1.4 x the larger landmark half-extent around the landmark centre,
+    shifted up by 20 % of it; the image is zero-padded when the box leaves it; ``cv2.resize`` (bilinear) to fsize.
+    Returns (crop[fsize,fsize,C] float64, lm / (2 length), mirrored lm / (2 length), box[4]) like the reference.
+    Pinned against the reference's own function on its real files (tests/golden/crop_reference.npz)."""
+    import cv2
+    img = np.asarray(img)
+    lm = np.array(lm, copy=True)
+    h, w = img.shape[0], img.shape[1]
+    lm_mirror = np.array(lm, copy=True)
+    lm_mirror[:, 0] = w - lm_mirror[:, 0]
+    lm_mirror = lm_mirror[_MIRROR_ORDER, :]
+    x0, x1, y0, y1 = np.min(lm[:, 0]), np.max(lm[:, 0]), np.min(lm[:, 1]), np.max(lm[:, 1])
+    cx, cy = (x0 + x1) / 2, (y0 + y1) / 2
+    length = np.max([(x1 - x0) / 2, (y1 - y0) / 2]) * 1.4
+    il, iu = int(length), int(length * 1.2)
+    box = [int(cx) - il, int(cy) - iu, int(cx) + il, int(cy) + il + il - iu]
+    box0 = list(box)
+    box_m = [w - box[2], box[1], w - box[0], box[3]]
+    lm[:, 0] -= box[0]
+    lm[:, 1] -= box[1]
+    lm_mirror[:, 0] -= box_m[0]
+    lm_mirror[:, 1] -= box_m[1]
+    pad_x = max(-box[0], box[2] - w) if (box[0] < 0 or box[2] > w) else 0
+    pad_y = max(-box[1], box[3] - h) if (box[1] < 0 or box[3] > h) else 0
+    if pad_x > 0 or pad_y > 0:
+        big = np.zeros((h + 2 * pad_y + 2, w + 2 * pad_x + 2, img.shape[2]))
+        big[pad_y:pad_y + h, pad_x:pad_x + w, :] = img
+        img = big
+        box = [box[0] + pad_x, box[1] + pad_y, box[2] + pad_x, box[3] + pad_y]
+    crop = img[box[1]:box[3], box[0]:box[2], :]
+    if crop.shape[0] == crop.shape[1] and crop.shape[0] > 0:
+        crop = cv2.resize(crop, (fsize, fsize))
+    else:
+        crop = np.zeros((fsize, fsize, img.shape[2]))
+    return crop, lm / (length * 2), lm_mirror / (length * 2), box0
+
+
+def load_frame(png_path: str, npy_path: Optional[str] = None, gt_path: Optional[str] = None) -> Dict[str, np.ndarray]:
+    """One real sample as dataset.py:157-170 / 625-637 builds it: PNG -> RGB / 255, ground truth (the image itself for
+    in-the-wild data, dataset.py:623), crop, landmark maps.  Returns img[256,256,3], gt[256,256,3], uv, reg, face
+    (float32), lm[68,2] and box."""
+    import cv2
+    npy_path = npy_path or png_path[:-4] + ".npy"
+    img = cv2.cvtColor(cv2.imread(png_path), cv2.COLOR_BGR2RGB) / 255.
+    gt = cv2.cvtColor(cv2.imread(gt_path or png_path), cv2.COLOR_BGR2RGB) / 255.
+    crop, lm, _, box = crop_and_resize(np.concatenate([img, gt], axis=2), np.load(npy_path), IMG)
+    m = frame_maps(lm)
+    return {"img": crop[..., 0:3].astype(np.float32), "gt": crop[..., 3:6].astype(np.float32), "uv": m["uv"], "reg": m["reg"],
+            "face": m["face"], "lm": lm, "box": np.asarray(box)}
+
+
+def build_chunk(frames) -> np.ndarray:
+    """[F,256,256,16] = img3|gt3|uv3|reg6|face1 per frame (dataset.py:170, 296-302), float32."""
+    return np.stack([np.concatenate([f["img"], f["gt"], f["uv"], f["reg"], f["face"]], axis=2) for f in frames]).astype(np.float32)
+
+
 def build_frame(img6: np.ndarray, lm: np.ndarray) -> np.ndarray:
     """One frame of the 16-channel chunk, dataset.py:637: concat([img|gt (6), uvm, reg_in, reg_out, face])."""
     m = frame_maps(lm)
