@@ -1,0 +1,452 @@
+// Non-local attention core on tcgen05, single pass (16-bit operands, fp32 logits / softmax / accumulation):
+//   O = softmax(theta . phi^T) . g      S = 1024 tokens, d = 128, one head, logits NOT scaled
+// (/root/reference/model.py:51-53).  The 1024 x 1024 logit matrix never leaves the SM.
+//
+// Persistent CTAs (one per SM) loop over work items = (image, PAIR of 128-query tiles A and B); the two tiles share every
+// K / V tile (half the L2 -> shared-memory traffic per MMA) and ping-pong on the tensor core: while the softmax warps of
+// A turn S_A(j+1) into P_A(j+1), the tensor core runs  O_B += P_B(j) V_j  and  S_B(j+1) = Q_B K_(j+1)^T, and vice versa.
+//   * one pass over the 8 key tiles with an ONLINE softmax: each thread owns one query row (TMEM lane), keeps a reference
+//     maximum m and the running sum; the accumulator row in TMEM is rescaled only when the row maximum grows by more than
+//     2^8 over m ("lazy rescale"): p = 2^(s log2e - m) <= 256 stays exact in the 16-bit P, and O / sum does not depend on m;
+//   * P never touches shared memory: the softmax warps write it (16-bit pairs, tcgen05.st) over the first 64 columns of
+//     the S tile they just read, and  O += P V  is a TS-mode MMA (A operand from TMEM);
+//   * MMAs execute in issue order, so S_X(j+1) (which overwrites P_X(j)) is simply issued after O_X += P_X(j) V_j, and
+//     a completed S_X(j+1) implies that O_X is quiescent until P_X(j+1) is published: the softmax warps rescale their own
+//     accumulator rows without another barrier.
+// TMEM (512 columns): [S_A | O_A | S_B | O_B], 128 fp32 columns each.   Shared memory: Q_A, Q_B (32 KB each), a ring of
+// four 32 KB stages fed in the order K0 V0 K1 V1 ..., two 16 KB output staging buffers (64 channels x 128 rows).
+// Layouts: QK[n][1024][256] = theta | phi;  VT[n][128][1024] = g transposed (every UMMA operand K-major);  O[n][1024][128].
+// Warp roles (320 threads): warps 0-3 softmax / epilogue of tile A, 4-7 of tile B (warp % 4 = TMEM lane quarter),
+// warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
+// Watchdog: a wait that times out (2 s) raises the error flag and a CTA-wide abort flag; from then on every wait of the
+// CTA returns immediately and the roles run their loops to the end ("skip the wait, not the work"), so no thread is left
+// behind at a named barrier and the kernel always terminates.
+#pragma once
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace bsr {
+
+constexpr int FA_S = 1024, FA_D = 128, FA_BQ = 128, FA_BK = 128;
+constexpr int FA_NK = FA_S / FA_BK;                   // 8 key tiles
+constexpr int FA_PAIRS = FA_S / (2 * FA_BQ);          // 4 work items per image
+constexpr uint32_t FA_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 x 16 bit] as two 16 KB k-blocks
+constexpr uint32_t FA_OSTAGE = 128 * 64 * 2;          // 16 KB: one 64-channel half of an output tile
+constexpr int FA_THREADS = 320;
+constexpr size_t kAttnFaSmem = 1024 + 6 * (size_t)FA_TILE + 2 * FA_OSTAGE + 512;
+constexpr float kFaRescaleLog2 = 8.f;                 // lazy-rescale threshold (log2 units)
+
+struct FaCtx { int* errflag; volatile int* abort_s; };
+
+__device__ __forceinline__ void fa_wait(uint32_t bar, uint32_t parity, const FaCtx& c, int code, bool hot = false) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (*c.abort_s) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    if (hot ? mbar_try_wait(bar, parity) : mbar_try_wait_sleep(bar, parity, 20000u)) return;
+    if ((++spins & 63u) == 0) {
+      if (*c.abort_s) return;
+      if (globaltimer_ns() - t0 > 2000000000ull) {
+        *c.abort_s = 1;
+        atomicExch(c.errflag, code);
+        return;
+      }
+    }
+  }
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T (TS mode): A = 128 rows (lanes) x 16 K elements = 8 columns of 16-bit pairs.
+__device__ __forceinline__ void umma_h16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
+      : "memory");
+}
+
+// 32 lanes x 32 consecutive columns, no wait (pair with tmem_wait_ld before touching the registers)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// 2^x on the SFU (ex2.approx: 2 ulp, flushes results below 2^-126 to zero - far below anything a 16-bit P can hold)
+__device__ __forceinline__ float fa_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __grid_constant__ CUtensorMap tmQK,
+                                                                     const __grid_constant__ CUtensorMap tmVT,
+                                                                     const __grid_constant__ CUtensorMap tmO,
+                                                                     const int n_items, int* errflag) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sR = sQ + 2 * FA_TILE, sO = sR + 4 * FA_TILE, bars = sO + 2 * FA_OSTAGE;
+  const uint32_t b_rfull = bars, b_rempty = bars + 32, b_qfull = bars + 64, b_qempty = bars + 80, b_sfull = bars + 96,
+                 b_pready = bars + 112, b_ofull = bars + 128, b_odrained = bars + 144, tmem_slot = bars + 160;
+  uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
+  volatile int* abort_s = reinterpret_cast<volatile int*>(smem_al + (tmem_slot + 4 - base));
+  const FaCtx ctx{errflag, abort_s};
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQK);
+    prefetch_tmap(&tmVT);
+    prefetch_tmap(&tmO);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(b_rfull + 8 * s, 1);
+      mbar_init(b_rempty + 8 * s, 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(b_qfull + 8 * x, 1);
+      mbar_init(b_qempty + 8 * x, 1);
+      mbar_init(b_sfull + 8 * x, 1);
+      mbar_init(b_pready + 8 * x, 4);
+      mbar_init(b_ofull + 8 * x, 1);
+      mbar_init(b_odrained + 8 * x, 4);
+    }
+    *abort_s = 0;
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  // programmatic dependent launch: everything above overlapped the tail of the qkv conv; everything below reads its output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 8) {
+    // ================= TMA producer (converged warp, elected lane issues) =================
+    const bool leader = elect_one();
+    uint32_t w = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+      const int n = item / FA_PAIRS, q0 = (item % FA_PAIRS) * 2 * FA_BQ;
+      for (int x = 0; x < 2; ++x) {
+        fa_wait(b_qempty + 8 * x, (w & 1u) ^ 1u, ctx, 40 + x);          // S_x(7) of the previous item has retired
+        if (leader) {
+          mbar_expect_tx(b_qfull + 8 * x, FA_TILE);
+          tma_load_3d(sQ + x * FA_TILE, &tmQK, b_qfull + 8 * x, 0, q0 + x * FA_BQ, n);
+          tma_load_3d(sQ + x * FA_TILE + FA_TILE / 2, &tmQK, b_qfull + 8 * x, 64, q0 + x * FA_BQ, n);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < FA_NK; ++j) {
+        const uint32_t ik = 16u * w + 2u * j, iv = ik + 1u;               // ring items: K(j), V(j)
+        fa_wait(b_rempty + 8 * (ik & 3u), ((ik >> 2) & 1u) ^ 1u, ctx, 42);
+        if (leader) {
+          const uint32_t dst = sR + (ik & 3u) * FA_TILE, bar = b_rfull + 8 * (ik & 3u);
+          mbar_expect_tx(bar, FA_TILE);
+          tma_load_3d(dst, &tmQK, bar, 128, j * FA_BK, n);
+          tma_load_3d(dst + FA_TILE / 2, &tmQK, bar, 192, j * FA_BK, n);
+        }
+        __syncwarp();
+        fa_wait(b_rempty + 8 * (iv & 3u), ((iv >> 2) & 1u) ^ 1u, ctx, 43);
+        if (leader) {
+          const uint32_t dst = sR + (iv & 3u) * FA_TILE, bar = b_rfull + 8 * (iv & 3u);
+          mbar_expect_tx(bar, FA_TILE);
+          tma_load_3d(dst, &tmVT, bar, j * FA_BK, 0, n);
+          tma_load_3d(dst + FA_TILE / 2, &tmVT, bar, j * FA_BK + 64, 0, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 9) {
+    // ================= MMA issuer (converged warp, elected lane issues) =================
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_h16(128, 128);
+    // S_x = Q_x . K^T  (SS mode) into columns [256 x, 256 x + 128)
+    auto issue_s = [&](const int x, const uint32_t slot) {
+      if (leader) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint32_t a_lo = umma_desc_lo(sQ + x * FA_TILE + kb * (FA_TILE / 2));
+          const uint32_t b_lo = umma_desc_lo(sR + slot * FA_TILE + kb * (FA_TILE / 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_h16_lo(tmem + 256u * x, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+      }
+    };
+    // O_x (+)= P_x . V  (TS mode: P = 16-bit pairs in columns [256 x, 256 x + 64), 8 columns per 16 keys)
+    auto issue_pv = [&](const int x, const uint32_t slot, const bool acc) {
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t b_lo = umma_desc_lo(sR + slot * FA_TILE + (kk >> 2) * (FA_TILE / 2)) + 2 * (kk & 3);
+          umma_h16_ts(tmem + 256u * x + 128u, tmem + 256u * x + 8u * kk, b_lo, idesc, (acc || kk != 0) ? 1u : 0u);
+        }
+      }
+    };
+    uint32_t w = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+      {
+        const uint32_t ik = 16u * w;                                       // K(0)
+        fa_wait(b_qfull, w & 1u, ctx, 50, true);
+        fa_wait(b_rfull + 8 * (ik & 3u), (ik >> 2) & 1u, ctx, 51, true);
+        tc_fence_after();
+        issue_s(0, ik & 3u);
+        if (leader) umma_commit(b_sfull);
+        __syncwarp();
+        fa_wait(b_qfull + 8, w & 1u, ctx, 52, true);
+        tc_fence_after();
+        issue_s(1, ik & 3u);
+        if (leader) {
+          umma_commit(b_sfull + 8);
+          umma_commit(b_rempty + 8 * (ik & 3u));
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < FA_NK; ++j) {
+        const uint32_t iv = 16u * w + 2u * j + 1u, ik = iv + 1u;           // V(j), K(j+1)
+        const uint32_t sp = (8u * w + (uint32_t)j) & 1u;                   // parity of the j-th S / P hand-over
+        const bool more = j + 1 < FA_NK;
+        // ---- tile A
+        fa_wait(b_pready, sp, ctx, 53, true);
+        if (j == 0) fa_wait(b_odrained, (w & 1u) ^ 1u, ctx, 54, true);     // epilogue of the previous item has read O_A
+        fa_wait(b_rfull + 8 * (iv & 3u), (iv >> 2) & 1u, ctx, 55, true);
+        tc_fence_after();
+        issue_pv(0, iv & 3u, j != 0);
+        if (!more && leader) umma_commit(b_ofull);
+        if (more) {
+          fa_wait(b_rfull + 8 * (ik & 3u), (ik >> 2) & 1u, ctx, 56, true);
+          tc_fence_after();
+          issue_s(0, ik & 3u);
+          if (leader) {
+            umma_commit(b_sfull);
+            if (j + 2 == FA_NK) umma_commit(b_qempty);                     // last S_A of this item: Q_A may be refilled
+          }
+        }
+        __syncwarp();
+        // ---- tile B
+        fa_wait(b_pready + 8, sp, ctx, 57, true);
+        if (j == 0) fa_wait(b_odrained + 8, (w & 1u) ^ 1u, ctx, 58, true);
+        tc_fence_after();
+        issue_pv(1, iv & 3u, j != 0);
+        if (leader) {
+          umma_commit(b_rempty + 8 * (iv & 3u));                           // V(j) consumed by both tiles
+          if (!more) umma_commit(b_ofull + 8);
+        }
+        if (more) {
+          issue_s(1, ik & 3u);
+          if (leader) {
+            umma_commit(b_sfull + 8);
+            umma_commit(b_rempty + 8 * (ik & 3u));                         // K(j+1) consumed by both tiles
+            if (j + 2 == FA_NK) umma_commit(b_qempty + 8);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= softmax + epilogue: warps 0-3 tile A, 4-7 tile B; thread = query row = TMEM lane =================
+    const int x = warp >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem + 256u * x + lane_addr, tO = tS + 128u;
+    const float kLog2e = 1.4426950408889634f;
+    const bool wg_leader = (threadIdx.x & 127) == 0;
+    uint8_t* stage = smem_al + (sO + x * FA_OSTAGE - base);
+    const uint32_t stage_u32 = sO + x * FA_OSTAGE;
+    uint32_t w = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+      const int n = item / FA_PAIRS, q0 = (item % FA_PAIRS) * 2 * FA_BQ + x * FA_BQ;
+      float m_ref = 0.f, l = 0.f;
+      for (int j = 0; j < FA_NK; ++j) {
+        fa_wait(b_sfull + 8 * x, (8u * w + (uint32_t)j) & 1u, ctx, 60 + x);
+        tc_fence_after();
+        uint32_t v[64];
+        // ---- sweep 1: row maximum of this key tile
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;      // four chains: latency, not issue, bound
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          tmem_ld32_nowait(tS + 64u * hf, v);
+          tmem_ld32_nowait(tS + 64u * hf + 32u, v + 32);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+          }
+        }
+        const float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * kLog2e;
+        if (j == 0) {
+          m_ref = mt;
+        } else {
+          const bool need = mt > m_ref + kFaRescaleLog2;
+          if (__any_sync(0xffffffffu, need)) {
+            // lazy rescale: O_x is quiescent here (S_x(j) complete => every earlier MMA complete; the next P V waits for us)
+            const float m_new = need ? mt : m_ref;
+            const float f = fa_exp2(m_ref - m_new);
+            m_ref = m_new;
+            l *= f;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              tmem_ld32_nowait(tO + 64u * hf, v);
+              tmem_ld32_nowait(tO + 64u * hf + 32u, v + 32);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st32(tO + 64u * hf, v);
+              tmem_st32(tO + 64u * hf + 32u, v + 32);
+            }
+            tmem_wait_st();
+          }
+        }
+        // ---- sweep 2: p = 2^(s log2e - m_ref) -> 16-bit pairs over the columns of S already consumed
+        const float mneg = -m_ref;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          tmem_ld32_nowait(tS + 64u * hf, v);
+          tmem_ld32_nowait(tS + 64u * hf + 32u, v + 32);
+          tmem_wait_ld();
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = fa_exp2(fmaf(__uint_as_float(v[2 * i]), kLog2e, mneg));
+            const float p1 = fa_exp2(fmaf(__uint_as_float(v[2 * i + 1]), kLog2e, mneg));
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_h16x2(p0, p1);
+          }
+          tmem_st16(tS + 32u * hf, pk);
+          tmem_st16(tS + 32u * hf + 16u, pk + 16);
+        }
+        l += l0 + l1;
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pready + 8 * x);
+      }
+      // ---- epilogue: O / sum -> 16 bit -> swizzled staging (64 channels at a time) -> TMA store
+      fa_wait(b_ofull + 8 * x, w & 1u, ctx, 62 + x);
+      tc_fence_after();
+      const float inv = 1.f / l;
+      const int pix0 = n * FA_S + q0;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[64];
+        tmem_ld32_nowait(tO + 64u * hf, v);
+        tmem_ld32_nowait(tO + 64u * hf + 32u, v + 32);
+        tmem_wait_ld();
+        if (hf == 1) {                                   // accumulator fully read: the next item's P V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_odrained + 8 * x);
+        }
+        // the bulk store that last read this staging buffer has finished reading it
+        if (wg_leader) bulk_wait_read0();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+        uint8_t* dst = stage + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 o;
+          o.x = pack_h16x2(__uint_as_float(v[8 * ch + 0]) * inv, __uint_as_float(v[8 * ch + 1]) * inv);
+          o.y = pack_h16x2(__uint_as_float(v[8 * ch + 2]) * inv, __uint_as_float(v[8 * ch + 3]) * inv);
+          o.z = pack_h16x2(__uint_as_float(v[8 * ch + 4]) * inv, __uint_as_float(v[8 * ch + 5]) * inv);
+          o.w = pack_h16x2(__uint_as_float(v[8 * ch + 6]) * inv, __uint_as_float(v[8 * ch + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = o;
+        }
+        fence_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+        if (wg_leader) {
+          tma_store_2d(&tmO, stage_u32, 64 * hf, pix0);
+          bulk_commit();
+        }
+      }
+    }
+    if (wg_leader) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// O[n][1024][128] = softmax(QK^T) V for n images; persistent grid of min(num_sms, 4 n) CTAs.
+inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h16* o, int n, int num_sms, int* errflag,
+                               cudaStream_t st, const Knobs& kn) {
+  static thread_local std::map<std::tuple<const void*, const void*, const void*, int>, std::tuple<CUtensorMap, CUtensorMap, CUtensorMap>> cache;
+  auto key = std::make_tuple((const void*)qk, (const void*)vt, (const void*)o, n);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap mq, mv, mo;
+    uint64_t dq[3] = {256, FA_S, (uint64_t)n}, sq[2] = {256 * 2, (uint64_t)FA_S * 256 * 2};
+    uint32_t bq[3] = {64, 128, 1};
+    if (!tma.encode_h16(&mq, (void*)qk, 3, dq, sq, bq, nullptr)) return -1;
+    uint64_t dv[3] = {FA_S, FA_D, (uint64_t)n}, sv[2] = {(uint64_t)FA_S * 2, (uint64_t)FA_D * FA_S * 2};
+    uint32_t bv[3] = {64, 128, 1};
+    if (!tma.encode_h16(&mv, (void*)vt, 3, dv, sv, bv, nullptr)) return -2;
+    uint64_t d2[2] = {FA_D, (uint64_t)n * FA_S}, s2[1] = {(uint64_t)FA_D * 2};
+    uint32_t b2[2] = {64, 128};
+    if (!tma.encode_h16(&mo, (void*)o, 2, d2, s2, b2, nullptr)) return -4;
+    if (cache.size() > 256) cache.clear();
+    it = cache.emplace(key, std::make_tuple(mq, mv, mo)).first;
+  }
+  const int n_items = n * FA_PAIRS;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)(n_items < num_sms ? n_items : num_sms));
+  cfg.blockDim = dim3(FA_THREADS);
+  cfg.dynamicSmemBytes = kAttnFaSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kn.no_pdl ? 0 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, attention_fa_kernel, std::get<0>(it->second), std::get<1>(it->second),
+                                      std::get<2>(it->second), n_items, errflag);
+  if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
+  return 0;
+}
+
+inline int configure_tc_kernels_attn_fa() {
+  cudaError_t e = cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnFaSmem);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace bsr

@@ -16,6 +16,7 @@
 
 #include "../../include/bsr.h"
 #include "attention_simple.cuh"
+#include "attention_fa.cuh"
 #include "attention_tc.cuh"
 #include "common.cuh"
 #include "conv_direct.cuh"
@@ -94,6 +95,7 @@ namespace {
 
 int configure_tc_kernels() {
   if (int r = configure_tc_kernels_conv()) return r;
+  if (int r = configure_tc_kernels_attn_fa()) return r;
   return configure_tc_kernels_attn();
 }
 
@@ -264,6 +266,13 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
     h->launches++;
     return BSR_OK;
   }
+  if (!h->force_direct && !wl && !h->kn.attn_v1) {
+    // single-pass kernel (attention_fa.cuh): O = softmax(QK^T) V; the output conv w runs as its own launch
+    int rc = launch_attention_fa(h->tma, (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, n, h->num_sms, h->errflag, st, h->kn);
+    if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
+    h->launches++;
+    return BSR_OK;
+  }
   if (!h->force_direct) {
     EpiParams e2;
     if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
@@ -326,7 +335,7 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   // NonLocal output conv + block tail: fused into the attention kernel on the tensor-core path
   const Layer& wl = h->layers[nm[4]];
   const bool fuse_w = h->precision == BSR_PRECISION_BF16 && !h->force_direct && wl.tc.ready && wl.tc.kind == TC_CONV &&
-                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !h->kn.no_fuse_w;
+                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !h->kn.no_fuse_w && h->kn.attn_v1;
   if (fuse_w) {
     if ((rc = run_attention(h, st, n, &wl, &ew))) return rc;
   } else {
@@ -830,6 +839,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.no_fuse_w = env_set("BSR_NO_FUSE_W");
   h->kn.host_chunk = env_int("BSR_HOST_CHUNK");
   h->kn.no_graph = env_set("BSR_NO_GRAPH");
+  h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
   h->ld1 = pad16(h->c_first > 257 ? h->c_first : 257);

@@ -64,6 +64,7 @@ struct Knobs {
   int no_fuse_w = 0;       // BSR_NO_FUSE_W: NonLocal output conv as its own launch
   int host_chunk = 0;      // BSR_HOST_CHUNK: images per pipelined host-path chunk
   int no_graph = 0;        // BSR_NO_GRAPH: never replay micro-batches from captured CUDA graphs
+  int attn_v1 = 0;         // BSR_ATTN_V1=1: round-1 two-pass attention kernel with the fused output conv (A/B measurements)
 };
 // Launch-plan counters of one forward (bsr_plan_counter).
 struct PlanCounters { int resident = 0, pinned = 0, staged = 0, attn_fused = 0, graph_replays = 0; };

@@ -195,8 +195,8 @@ def test_layer_times_and_launch_count(G):
     torch.cuda.synchronize()
     times = gen.layer_times()
     names = [n for n, _ in times]
-    assert gen.launch_count() == 49 and len(times) >= 40          # 49 launches per GSC forward (w fused into attention)
-    for must in ("conv1", "down1", "res0.conv2", "res5.qkv", "attention+w", "up3", "heads", "clr_up3", "clr_conv1"):
+    assert gen.launch_count() == 55 and len(times) >= 46          # 55 launches per GSC forward
+    for must in ("conv1", "down1", "res0.conv2", "res5.qkv", "attention", "res5.w", "up3", "heads", "clr_up3", "clr_conv1"):
         assert must in names, must
     assert all(ms > 0 for _, ms in times)
     assert gen.workspace_bytes() > 2 * 30e6
@@ -436,7 +436,7 @@ def test_benchmark_configuration_gsc_256_images_mb128_matches_oracle(G):
     out = gen(t["img"], t["uv"], None)
     gen.check()
     pc = gen.plan_counters()
-    assert pc["pinned"] >= 12 and pc["resident"] >= 12 and pc["staged"] >= 8 and pc["attn_fused"] == 12, pc
+    assert pc["pinned"] >= 12 and pc["resident"] >= 12 and pc["staged"] >= 8, pc
     got = dict(zip(("gs", "con_rgb", "mask22", "dif"), (o.cpu().numpy() for o in out)))
     for k, v in got.items():
         assert np.array_equal(v[:128], v[128:]), k                      # micro-batch 0 == micro-batch 1
@@ -492,7 +492,7 @@ def _attention_ref(qk, vt):
     s = q @ k.transpose(0, 2, 1)
     mx = s.max(-1, keepdims=True)
     p = np.exp(s - mx)
-    return (p / p.sum(-1, keepdims=True)) @ v, mx[..., 0]
+    return (p / p.sum(-1, keepdims=True)) @ v, s.max(-1) - s.min(-1)
 
 
 @pytest.mark.parametrize("gain", [1.0, 8.0, 64.0])
@@ -507,14 +507,14 @@ def test_attention_kernel_alone_matches_float64_softmax(G, gain):
         qk = gen.debug_read("qk%d" % blk).reshape(2, 1024, 256)
         vt = gen.debug_read("vt%d" % blk).reshape(2, 128, 1024)
         o = gen.debug_read("attn_o%d" % blk).reshape(2, 1024, 128)
-        ref, mx = _attention_ref(qk, vt)
+        ref, spread = _attention_ref(qk, vt)
         scale = np.abs(ref).max()
         err = np.abs(o - ref).max()
-        print("gain", gain, "block", blk, "row-max logit median %.1f max %.1f" % (np.median(mx), mx.max()),
+        print("gain", gain, "block", blk, "logit spread (row max - row min) median %.1f max %.1f" % (np.median(spread), spread.max()),
               "max|O - ref| %.2e of scale %.2f" % (err, scale))
         assert np.isfinite(o).all()
         if gain == 8.0:
-            assert np.median(mx) > 30.0                                   # the case really has peaked rows
+            assert np.median(spread) > 50.0                               # the case really has peaked rows
         assert err <= 2.5e-3 * max(scale, 1.0), (blk, err, scale)         # P and O are stored with 11-bit significands
     gen.close()
 
