@@ -365,9 +365,11 @@ int run_share(bsr_handle* h, cudaStream_t st, char* x, int ld, int C, int coff, 
     h->launches++;
     return BSR_OK;
   }
-  int chunks = n / frame;
-  share_reduce_kernel<T><<<chunks * FEAT * FEAT, 128, 0, st>>>((const T*)x, ld, C, h->OFF, frame, h->SH);
-  share_out_kernel<T><<<n * FEAT * FEAT, 128, 0, st>>>(h->SH, 2 * C, h->OFF, frame, (T*)x, ld, coff);
+  if ((ld & 3) || (coff & 3)) return fail(h, BSR_EINVAL, "share layer needs 4-channel aligned stride / offset (ld %d, coff %d)", ld, coff);
+  const int chunks = n / frame, ldsh = (2 * C + 3) / 4 * 4;
+  const long long t1 = (long long)chunks * FEAT * FEAT * ((C + 3) / 4), t2 = (long long)n * FEAT * FEAT * ((2 * C + 3) / 4);
+  share_reduce_kernel<T><<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>((const T*)x, ld, C, h->OFF, frame, (T*)h->SH, ldsh, t1);
+  share_out_kernel<T><<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>((const T*)h->SH, ldsh, 2 * C, h->OFF, frame, (T*)x, ld, coff, t2);
   h->launches += 2;
   return BSR_OK;
 }
@@ -860,7 +862,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {(char**)&h->RAW, mb * IMG * IMG * 2 * 4}, {(char**)&h->GS32, mb * IMG * IMG * 4}, {(char**)&h->DIFGS, mb * IMG * IMG * 4},
       {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
       {(char**)&h->DIFSMALL, mb * 1024 * 4},
-      {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 2 * 291 * 4 : 256},
+      {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 584 * 4 : 256},
       {(char**)&h->errflag, 16384}};
   // staging of the host / chunk entry points (include/bsr.h: no allocation inside forward_*): host-path chunks are
   // capped at 128 images (the measured optimum is 64-128), chunk entry at one micro-batch
@@ -1131,6 +1133,38 @@ int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int 
   h->launches = total;
   h->pc = pc_total;
   return finish_forward(h, st);        // the in-place caller glue above is part of this forward
+}
+
+int bsr_share_layer(bsr_handle* h, const float* x, const float* reg, int n, int C, int frame, int share, float* out,
+                    void* cuda_stream) {
+  if (!h) return BSR_EINVAL;
+  if (h->variant != BSR_VARIANT_TSM) return fail(h, BSR_EINVAL, "ShareLayer exists in the TSM generator only");
+  if (!x || !reg || !out || n <= 0 || frame <= 0 || n % frame) return fail(h, BSR_EINVAL, "x, reg, out non-NULL and n %% frame == 0 required");
+  if (n > h->mb) return fail(h, BSR_EINVAL, "n %d exceeds micro_batch %d", n, h->mb);
+  if (C < 1 || C > 291) return fail(h, BSR_EINVAL, "C must be in [1, 291] (the generator uses 96 and 291)");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (int rc = pending_device_error(h)) return rc;
+  DeviceScope dev_scope(h->device);
+  if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
+  if (h->have_done && h->last_stream != st) CK(h, cudaStreamWaitEvent(st, h->ev_done, 0));
+  const long long npix = (long long)n * FEAT * FEAT;
+  const int ld = h->ld2, coff = (C + 3) / 4 * 4;
+  const int tot4 = n * FEAT * FEAT * 4;
+  reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
+  h->launches = 1;
+  int rc;
+  if (h->precision == BSR_PRECISION_FP32CHECK) {
+    pack_act_kernel<float><<<(unsigned)((npix * C + 255) / 256), 256, 0, st>>>(x, C, (float*)h->XA, ld, npix);
+    if ((rc = run_share<float>(h, st, h->XA, ld, C, coff, n, frame, share))) return rc;
+    slice_to_f32_kernel<float><<<(unsigned)((npix * 2 * C + 255) / 256), 256, 0, st>>>((const float*)h->XA, ld, coff, 2 * C, out, npix);
+  } else {
+    pack_act_kernel<h16><<<(unsigned)((npix * C + 255) / 256), 256, 0, st>>>(x, C, (h16*)h->XA, ld, npix);
+    if ((rc = run_share<h16>(h, st, h->XA, ld, C, coff, n, frame, share))) return rc;
+    slice_to_f32_kernel<h16><<<(unsigned)((npix * 2 * C + 255) / 256), 256, 0, st>>>((const h16*)h->XA, ld, coff, 2 * C, out, npix);
+  }
+  h->launches += 2;
+  CK(h, cudaGetLastError());
+  return finish_forward(h, st);
 }
 
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n, float* rgb_clipped,

@@ -222,45 +222,107 @@ __device__ __forceinline__ float warp_mix(float lt, float rt, float lb, float rb
   return vt + (vb - vt) * o1;
 }
 
-// sh[chunk][pix][0:C] = max_f warp_in(x_f), sh[chunk][pix][C:2C] = mean_f warp_in(x_f)
-template <typename T>
-__global__ void share_reduce_kernel(const T* __restrict__ x, int ld, int C, const float* __restrict__ off,
-                                    int frame, float* __restrict__ sh) {
-  int pix = blockIdx.x % (FEAT * FEAT), chunk = blockIdx.x / (FEAT * FEAT);
-  int i = pix / FEAT, j = pix % FEAT;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float mx = -INFINITY, sum = 0.f;
-    for (int f = 0; f < frame; ++f) {
-      size_t n = (size_t)chunk * frame + f;
-      const float* o = off + (n * FEAT * FEAT + pix) * 4;
-      WarpTap w = warp_tap(o[0], o[1], i, j);
-      const T* b = x + n * FEAT * FEAT * ld + c;
-      float v = warp_mix(ldf<T>(b, (size_t)w.lt * ld), ldf<T>(b, (size_t)w.rt * ld),
-                         ldf<T>(b, (size_t)w.lb * ld), ldf<T>(b, (size_t)w.rb * ld), w.o0, w.o1);
-      mx = fmaxf(mx, v);
-      sum += v;
-    }
-    float* d = sh + ((size_t)chunk * FEAT * FEAT + pix) * 2 * C;
-    d[c] = mx;
-    d[C + c] = sum / (float)frame;
-  }
+// 4 consecutive channels per thread: 8-byte (16-bit storage) / 16-byte (fp32) accesses, fully coalesced across a warp.
+template <typename T> __device__ __forceinline__ void ld4(const T* p, float* v);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float* v) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld4<h16>(const h16* p, float* v) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_h16x2(t.x), b = unpack_h16x2(t.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, const float* v);
+template <> __device__ __forceinline__ void st4<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st4<h16>(h16* p, const float* v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_h16x2(v[0], v[1]), pack_h16x2(v[2], v[3]));
 }
 
-// x[n][pix][coff + c] = warp_out(sh[chunk])[pix][c], c < 2C
+// ShareLayer, first half (model_with_TSM.py:204-222): sh[chunk][pix][0:C] = max_f warp_in(x_f), sh[chunk][pix][C:2C] =
+// mean_f warp_in(x_f), stored in the activation type with row stride ldsh (a multiple of 4).  One thread per (chunk,
+// pixel, 4 channels): the four bilinear corners of every frame are 4-channel vector loads, the frames of a chunk are
+// reduced in registers (F = 2 or 10 - too few for a cross-lane reduction to pay).  Needs ld % 4 == 0.
 template <typename T>
-__global__ void share_out_kernel(const float* __restrict__ sh, int C2, const float* __restrict__ off, int frame,
-                                 T* __restrict__ x, int ld, int coff) {
-  int pix = blockIdx.x % (FEAT * FEAT);
-  size_t n = blockIdx.x / (FEAT * FEAT);
-  size_t chunk = n / frame;
-  int i = pix / FEAT, j = pix % FEAT;
-  const float* o = off + (n * FEAT * FEAT + pix) * 4;
-  WarpTap w = warp_tap(o[2], o[3], i, j);
-  const float* b = sh + chunk * FEAT * FEAT * C2;
-  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
-    float v = warp_mix(b[(size_t)w.lt * C2 + c], b[(size_t)w.rt * C2 + c], b[(size_t)w.lb * C2 + c],
-                       b[(size_t)w.rb * C2 + c], w.o0, w.o1);
-    stf<T>(x, (n * FEAT * FEAT + pix) * ld + coff + c, v);
+__global__ void share_reduce_kernel(const T* __restrict__ x, int ld, int C, const float* __restrict__ off, int frame,
+                                    T* __restrict__ sh, int ldsh, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Cv = (C + 3) >> 2;
+  const int cv = (int)(idx % Cv);
+  const long long cell = idx / Cv;
+  const int pix = (int)(cell % (FEAT * FEAT));
+  const size_t chunk = (size_t)(cell / (FEAT * FEAT));
+  const int i = pix / FEAT, j = pix % FEAT, c0 = 4 * cv;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int f = 0; f < frame; ++f) {
+    const size_t n = chunk * frame + f;
+    const float2 o = *reinterpret_cast<const float2*>(off + (n * FEAT * FEAT + pix) * 4);
+    const WarpTap w = warp_tap(o.x, o.y, i, j);
+    const T* b = x + n * FEAT * FEAT * ld + c0;
+    float lt[4], rt[4], lb[4], rb[4];
+    ld4<T>(b + (size_t)w.lt * ld, lt);
+    ld4<T>(b + (size_t)w.rt * ld, rt);
+    ld4<T>(b + (size_t)w.lb * ld, lb);
+    ld4<T>(b + (size_t)w.rb * ld, rb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = warp_mix(lt[k], rt[k], lb[k], rb[k], w.o0, w.o1);
+      mx[k] = fmaxf(mx[k], v);
+      sum[k] += v;
+    }
+  }
+  T* d = sh + (chunk * FEAT * FEAT + pix) * ldsh;
+  const float invf = 1.f / (float)frame;
+  if (c0 + 4 <= C) {
+    st4<T>(d + c0, mx);
+    if ((C & 3) == 0) {
+      float mean[4] = {sum[0] / (float)frame, sum[1] / (float)frame, sum[2] / (float)frame, sum[3] / (float)frame};
+      st4<T>(d + C + c0, mean);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stf<T>(d, C + c0 + k, sum[k] / (float)frame);
+    }
+  } else {
+    for (int k = 0; c0 + k < C; ++k) {
+      stf<T>(d, c0 + k, mx[k]);
+      stf<T>(d, C + c0 + k, sum[k] / (float)frame);
+    }
+  }
+  (void)invf;
+}
+
+// ShareLayer, second half (model_with_TSM.py:223-226): x[n][pix][coff + c] = warp_out(sh[chunk])[pix][c], c < 2C.
+// One thread per (frame, pixel, 4 channels); coff % 4 == 0, ld % 4 == 0, ldsh % 4 == 0.
+template <typename T>
+__global__ void share_out_kernel(const T* __restrict__ sh, int ldsh, int C2, const float* __restrict__ off, int frame,
+                                 T* __restrict__ x, int ld, int coff, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Qv = (C2 + 3) >> 2;
+  const int qv = (int)(idx % Qv);
+  const long long cell = idx / Qv;
+  const int pix = (int)(cell % (FEAT * FEAT));
+  const size_t n = (size_t)(cell / (FEAT * FEAT));
+  const size_t chunk = n / frame;
+  const int i = pix / FEAT, j = pix % FEAT, c0 = 4 * qv;
+  const float2 o = *reinterpret_cast<const float2*>(off + (n * FEAT * FEAT + pix) * 4 + 2);
+  const WarpTap w = warp_tap(o.x, o.y, i, j);
+  const T* b = sh + chunk * FEAT * FEAT * ldsh + c0;
+  float lt[4], rt[4], lb[4], rb[4], v[4];
+  ld4<T>(b + (size_t)w.lt * ldsh, lt);
+  ld4<T>(b + (size_t)w.rt * ldsh, rt);
+  ld4<T>(b + (size_t)w.lb * ldsh, lb);
+  ld4<T>(b + (size_t)w.rb * ldsh, rb);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = warp_mix(lt[k], rt[k], lb[k], rb[k], w.o0, w.o1);
+  T* d = x + (n * FEAT * FEAT + pix) * ld + coff;
+  if (c0 + 4 <= C2) {
+    st4<T>(d + c0, v);
+  } else {
+    for (int k = 0; c0 + k < C2; ++k) stf<T>(d, c0 + k, v[k]);
   }
 }
 
@@ -390,6 +452,16 @@ __global__ void composite_kernel(const float* __restrict__ pred, const float* __
     float mm = m[i];
     out[i] = fminf(fmaxf(pred[i] * mm + inp[i] * (1.f - mm), 0.f), 1.f);
   }
+}
+
+// fp32 [n_pix][C] -> channels [0, C) of an activation buffer with row stride ld (bsr_share_layer entry)
+template <typename T>
+__global__ void pack_act_kernel(const float* __restrict__ in, int C, T* __restrict__ x, int ld, long long n_pix) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pix * C) return;
+  size_t pix = (size_t)(idx / C);
+  int c = (int)(idx % C);
+  stf<T>(x, pix * ld + c, in[idx]);
 }
 
 // debug: dense fp32 copy of channels [coff, coff+C) of an activation buffer

@@ -48,6 +48,7 @@ _SYMBOLS = {
     "bsr_forward_gsc_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 6),
     "bsr_forward_tsm_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 6),
     "bsr_forward_chunk": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5),
+    "bsr_share_layer": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 2),
     "bsr_caller_glue": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3),
     "bsr_composite": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t] + [ctypes.c_void_p] * 2),
     "bsr_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -374,6 +375,23 @@ class Generator:
             rc = self._lib.bsr_forward_tsm_host_compact(self._h, v(img_u8), v(uv32), v(reg32), n // frame, frame,
                                                         int(share), v(gs), v(rgb), v(m22), v(dif), v(rgb_u8), v(dif_f16))
         self._check(rc)
+
+    # -- ShareLayer on its own (model_with_TSM.py:204-229) --------------------------------------
+    def share_layer(self, x, reg, frame: int, share=True):
+        """``ShareLayer.call(x, reg, frame, share)``: x [n,32,32,C] and reg [n,256,256,6] CUDA fp32 -> [n,32,32,2C]."""
+        import torch
+        self._same_device(x=x, reg=reg)
+        n, c = int(x.shape[0]), int(x.shape[3])
+        if tuple(x.shape[1:3]) != (FEAT, FEAT) or tuple(reg.shape) != (n, IMG, IMG, 6):
+            raise ValueError("x must be [n,32,32,C] and reg [n,256,256,6]")
+        if n % frame:
+            raise ValueError("batch %d is not a multiple of frame %d (model_with_TSM.py:218)" % (n, frame))
+        share = bool(share.item() if hasattr(share, "item") else share)
+        out = torch.empty((n, FEAT, FEAT, 2 * c), dtype=torch.float32, device=x.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        self._check(self._lib.bsr_share_layer(self._h, _ptr(x.contiguous().float()), _ptr(reg.contiguous().float()), n, c,
+                                              int(frame), int(share), _ptr(out), stream))
+        return out
 
     # -- caller glue (train_test_GSC.py:808-809, 711-718) ------------------------------------
     def caller_glue(self, con_rgb, dif, face):

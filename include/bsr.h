@@ -122,6 +122,14 @@ enum { BSR_CHUNK_GT = 0, BSR_CHUNK_SFW = 1, BSR_CHUNK_PLAIN = 2 };
 int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int frame, int share,
                       float* rgb_clipped, float* mask_pred, float* gs, float* mask22, void* cuda_stream);
 
+/* ShareLayer.call of model_with_TSM.py:204-229 on its own (the temporal sharing module; inside bsr_forward_tsm it runs
+ * on the 16-bit activations in place): x[n,32,32,C] fp32, reg[n,256,256,6] -> out[n,32,32,2C] fp32 =
+ * warp_out(tile(concat(max_f, mean_f)(warp_in(x)))) per group of `frame` consecutive images, or concat([x, x]) when
+ * share == 0.  Device pointers, TSM handles only, n <= micro_batch, C <= 291.  x is converted to the handle's
+ * activation type first (exact for FP32CHECK handles). */
+int bsr_share_layer(bsr_handle* h, const float* x, const float* reg, int n, int C, int frame, int share, float* out,
+                    void* cuda_stream);
+
 /* Caller glue, train_test_GSC.py:808-809 / 872-873 / 902-903 (TSM: train_with_TSM.py:677-678):
  * mask_pred = dif*face ; rgb_clipped = clip(rgb, 0, 1).  Device pointers; in-place allowed. */
 int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const float* face, int n,
