@@ -22,6 +22,7 @@
 #include "conv_direct.cuh"
 #include "conv_tc.cuh"
 #include "glue.cuh"
+#include "postprocess.cuh"
 
 using namespace bsr;
 
@@ -86,6 +87,10 @@ struct bsr_handle {
   char* stage = nullptr;
   size_t stage_bytes = 0;
   int host_step_cap = 0;   // images per host-path chunk the staging was sized for
+  // scratch of bsr_postprocess_ucb (grown on demand: not part of the forward path)
+  char* pp_buf = nullptr;
+  PpPlanes* pp_planes = nullptr;
+  int pp_cap = 0;
   cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   TmaEncoder tma;
@@ -934,6 +939,8 @@ int bsr_destroy(bsr_handle* h) {
   for (auto& kv : h->dbg) if (kv.second.dev) cudaFree(kv.second.dev);
   for (auto& e : h->ev) cudaEventDestroy(e);
   if (h->arena) cudaFree(h->arena);
+  if (h->pp_buf) cudaFree(h->pp_buf);
+  if (h->pp_planes) cudaFree(h->pp_planes);
   if (h->errflag_host) cudaFreeHost(h->errflag_host);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1186,6 +1193,63 @@ int bsr_composite(bsr_handle* h, const float* pred, const float* inp, const floa
   size_t blocks = (n_elems + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   composite_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(pred, inp, m, out, n_elems);
+  CK(h, cudaGetLastError());
+  return BSR_OK;
+}
+
+int bsr_postprocess_ucb(bsr_handle* h, int n, const float* img, const float* gt, const float* rgb, const float* dif,
+                        const int* sizes, const unsigned char* masks, float* final_out, float* detected_out,
+                        float* metrics, void* cuda_stream) {
+  if (!h) return BSR_EINVAL;
+  if (n <= 0 || !img || !gt || !rgb || !dif || !sizes || !masks || !final_out)
+    return fail(h, BSR_EINVAL, "n > 0 and img, gt, rgb, dif, sizes, masks, final_out non-NULL required");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  DeviceScope dev_scope(h->device);
+  if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
+  if (n > h->pp_cap) {
+    CK(h, cudaStreamSynchronize(st));
+    if (h->pp_buf) cudaFree(h->pp_buf);
+    if (h->pp_planes) cudaFree(h->pp_planes);
+    h->pp_buf = nullptr; h->pp_planes = nullptr; h->pp_cap = 0;
+    const size_t per = (kPpBytesPerImage + 255) / 256 * 256;
+    if (cudaMalloc(&h->pp_buf, per * n) != cudaSuccess || cudaMalloc(&h->pp_planes, sizeof(PpPlanes) * n) != cudaSuccess)
+      return fail(h, BSR_ENOMEM, "post-processing scratch of %zu bytes failed", per * n);
+    std::vector<PpPlanes> pl(n);
+    for (int i = 0; i < n; ++i) {
+      char* b = h->pp_buf + per * i;
+      PpPlanes& P = pl[i];
+      P.tmp = (float*)b; b += (size_t)PP_PIX * 12;
+      P.gt = (float*)b; b += (size_t)PP_PIX * 12;
+      P.pred = (float*)b; b += (size_t)PP_PIX * 12;
+      P.mp = (float*)b; b += (size_t)PP_PIX * 4;
+      P.inten = (float*)b; b += (size_t)PP_PIX * 4;
+      P.label = (int*)b; b += (size_t)PP_PIX * 4;
+      P.csize = (int*)b; b += (size_t)PP_PIX * 4;
+      P.chair = (int*)b; b += (size_t)PP_PIX * 4;
+      P.stats = (int*)b; b += PS_WORDS * 4;
+      P.masks = (unsigned char*)b; b += (size_t)PP_PIX * PP_NMASK;
+      P.detected = (unsigned char*)b; b += PP_PIX;
+      P.img2 = (unsigned char*)b; b += PP_PIX;
+    }
+    CK(h, cudaMemcpy(h->pp_planes, pl.data(), sizeof(PpPlanes) * n, cudaMemcpyHostToDevice));
+    h->pp_cap = n;
+  }
+  const dim3 grid(PP_PIX / 256, n);
+  PpIn in{img, gt, rgb, dif, masks, sizes};
+  pp_reset_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_resize_kernel<<<grid, 256, 0, st>>>(in, h->pp_planes);
+  pp_rules_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_threshold_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_ccl_merge_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_ccl_flatten_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_cc_max_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_select_kernel<<<grid, 256, 0, st>>>(h->pp_planes);
+  pp_final_kernel<<<grid, 256, 0, st>>>(h->pp_planes, final_out, detected_out);
+  if (metrics) {
+    pp_ssim_kernel<<<dim3(256, 3, n), 256, 0, st>>>(h->pp_planes);
+    pp_metrics_kernel<<<(n + 63) / 64, 64, 0, st>>>(h->pp_planes, metrics, n);
+  }
+  h->launches = metrics ? 11 : 9;
   CK(h, cudaGetLastError());
   return BSR_OK;
 }

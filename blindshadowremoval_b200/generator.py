@@ -49,6 +49,7 @@ _SYMBOLS = {
     "bsr_forward_tsm_host_compact": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 6),
     "bsr_forward_chunk": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 5),
     "bsr_share_layer": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 2),
+    "bsr_postprocess_ucb": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 10),
     "bsr_caller_glue": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3),
     "bsr_composite": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t] + [ctypes.c_void_p] * 2),
     "bsr_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -419,6 +420,33 @@ class Generator:
         self._check(self._lib.bsr_composite(self._h, _ptr(pred.contiguous().float()), _ptr(inp.contiguous().float()),
                                             _ptr(m.expand_as(pred).contiguous().float()), pred.numel(), _ptr(out), stream))
         return out
+
+    # -- test_step post-processing (train_test_GSC.py:436-725) -------------------------------
+    MASK_KINDS = ("face_hair", "face", "mouth", "nose", "eyebrow", "eye", "glasses")
+
+    def postprocess_ucb(self, img, gt, con_rgb, dif, sizes, masks, want_metrics: bool = True):
+        """Device post-processing of the UCB test step for n samples (frame 0 of n chunks): CUDA tensors img / gt /
+        con_rgb [n,256,256,3], dif [n,256,256,1], sizes [n] int32, masks [n,7,256,256] uint8 in MASK_KINDS order.
+        Returns (final [n,256,256,3], detected [n,256,256], metrics [n,2] = ssim, psnr or None)."""
+        import torch
+        self._same_device(img=img, gt=gt, con_rgb=con_rgb, dif=dif, sizes=sizes, masks=masks)
+        n = int(img.shape[0])
+        if tuple(img.shape) != (n, IMG, IMG, 3) or tuple(gt.shape) != (n, IMG, IMG, 3) or tuple(con_rgb.shape) != (n, IMG, IMG, 3):
+            raise ValueError("img, gt, con_rgb must be [n,256,256,3]")
+        if dif.numel() != n * IMG * IMG or tuple(masks.shape) != (n, 7, IMG, IMG) or masks.dtype != torch.uint8:
+            raise ValueError("dif must be [n,256,256,1] and masks uint8 [n,7,256,256]")
+        sizes = sizes.to(torch.int32).contiguous()
+        if sizes.numel() != n or int(sizes.min()) < 1 or int(sizes.max()) > IMG:
+            raise ValueError("sizes must be n values in [1, 256]")
+        dev = img.device
+        final = torch.empty((n, IMG, IMG, 3), dtype=torch.float32, device=dev)
+        det = torch.empty((n, IMG, IMG), dtype=torch.float32, device=dev)
+        met = torch.empty((n, 2), dtype=torch.float32, device=dev) if want_metrics else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        f = lambda t: t.contiguous().float()
+        self._check(self._lib.bsr_postprocess_ucb(self._h, n, _ptr(f(img)), _ptr(f(gt)), _ptr(f(con_rgb)), _ptr(f(dif)),
+                                                  _ptr(sizes), _ptr(masks.contiguous()), _ptr(final), _ptr(det), _ptr(met), stream))
+        return final, det, met
 
     # -- introspection -----------------------------------------------------------------------
     def launch_count(self) -> int:

@@ -138,6 +138,23 @@ int bsr_caller_glue(bsr_handle* h, const float* rgb, const float* dif, const flo
 int bsr_composite(bsr_handle* h, const float* pred, const float* inp, const float* m, size_t n_elems,
                   float* out, void* cuda_stream);
 
+/* Post-processing of FSRNet.test_step (train_test_GSC.py:436-725), the block that follows the generator call in the
+ * UCB evaluation `fsr.test` (BASELINE config 2), for n independent samples (frame 0 of n chunks).  Device pointers:
+ *   img, gt, rgb [n,256,256,3], dif [n,256,256,1]  input image, ground truth, generator outputs [1] and [3] of frame 0;
+ *   sizes [n] int32                                  box[3] - box[1] of face_crop_and_resize (:417), 1..256;
+ *   masks [n,7,256,256] uint8 {0,1}                  region masks in the order face+hair, face, mouth, nose, eyebrow,
+ *                                                    eye, glasses (:387-393; single channel: the PNGs are grey).
+ * Steps: resize everything to [size,size] and zero-pad to 256 (:438-476), mustache / mouth false positives (:479-496),
+ * per-pixel threshold with the hair / forehead / mouth-and-below / left-eyebrow rules (:518-570), 4-connected
+ * components keeping those >= 0.45 x the largest and < 80 % hair (:590-611, cv2.connectedComponentsWithStats in the
+ * reference), nose rule (:650-662), final = clip(pred*m + input*(1-m), 0, 1) (:711, 718), SSIM / PSNR vs gt (:724-725).
+ * Outputs: final_out [n,256,256,3]; detected_out [n,256,256] (the {0,1} shadow mask m; may be NULL);
+ * metrics [n,2] = (ssim, psnr) (may be NULL).  Everything runs on the device, no host synchronisation; scratch is grown
+ * on the first call with a larger n (this entry is not part of the forward path). */
+int bsr_postprocess_ucb(bsr_handle* h, int n, const float* img, const float* gt, const float* rgb, const float* dif,
+                        const int* sizes, const unsigned char* masks, float* final_out, float* detected_out,
+                        float* metrics, void* cuda_stream);
+
 /* Device-side error check.  Kernels never hang on a protocol error: a 2 s watchdog in every mbarrier wait sets a
  * device flag and the kernel drains.  The flag is copied to pinned host memory at the end of every forward; every
  * forward_* entry point first looks at it (no sync) and returns BSR_EDEVICE if an EARLIER forward tripped it.

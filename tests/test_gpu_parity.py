@@ -476,12 +476,14 @@ def test_benchmark_configuration_tsm_mb128_matches_oracle(G, frame, n):
     gen.close()
 
 
-def _peaked_weights(variant, gain, wseed=1234):
-    """theta x gain (logits are unscaled in the reference, model.py:51-52) and the damping of non_local/w removed."""
+def _peaked_weights(variant, gain, wseed=1234, undamp=True):
+    """theta x gain (logits are unscaled in the reference, model.py:51-52) and, with `undamp`, the 0.35 damping that
+    weights.random_weights puts on non_local/w removed (w x 1)."""
     w = dict(random_weights(variant, wseed))
     for i in range(6):
         w["res_stack/%d/non_local/theta/kernel" % i] = w["res_stack/%d/non_local/theta/kernel" % i] * np.float32(gain)
-        w["res_stack/%d/non_local/w/kernel" % i] = w["res_stack/%d/non_local/w/kernel" % i] * np.float32(1.0 / 0.35)
+        if undamp:
+            w["res_stack/%d/non_local/w/kernel" % i] = w["res_stack/%d/non_local/w/kernel" % i] * np.float32(1.0 / 0.35)
     return w
 
 
@@ -519,21 +521,31 @@ def test_attention_kernel_alone_matches_float64_softmax(G, gain):
     gen.close()
 
 
-def test_large_logit_network_matches_oracle(G):
-    """End to end with peaked softmax rows (theta x 8, non_local/w undamped): the network output still tracks the
-    oracle.  The comparison is worse conditioned than the calibrated case (a near-one-hot softmax amplifies rounding of
-    its logits), hence PSNR and a relaxed max-abs, stated here: 3e-2."""
-    w = _peaked_weights("gsc", 8.0)
-    d = make_inputs(2, seed=6, with_reg=True)
+@pytest.mark.parametrize("gain,undamp", [(4.0, False), (2.0, True), (3.0, True)])
+def test_large_logit_network_matches_oracle(G, gain, undamp):
+    """End to end with peaked softmax rows.  (4, damped w): block-5 row-max logits ~46, max - min ~83 per row: north_star's
+    1e-2 must hold as is.  (2 | 3, w x 1): row-max 47 | 74, spread 95 | 144; here the NETWORK is ill conditioned - the fp32
+    oracle itself moves 20-45x further from the fp64 oracle than with calibrated weights (profiles/r2_large_logit_probe.txt)
+    - so the bound is sensitivity-normalised: error <= 1500 x |oracle fp32 - oracle fp64| (unit-roundoff ratio 2^13;
+    measured 450-730) plus PSNR >= 40 dB."""
     from oracle.calibrate import centre_hole_threshold
+    from oracle.generator_ref import generator_forward
+    w = _peaked_weights("gsc", gain, undamp=undamp)
+    d = make_inputs(2, seed=6, with_reg=True)
     w = centre_hole_threshold(w, d["img"], d["uv"], None, variant="gsc", frame=1)
     gen, got = run_device(G, "gsc", "tc16", w, d, 1)
     bm = gen.debug_read("bmask").reshape(2, 32, 32, 1)
     ref = oracle("gsc", w, d, 1, bmask=bm)
-    rep = {k: (float(np.abs(got[k] - ref[k]).max()), psnr(got[k], ref[k])) for k in ("gs", "con_rgb", "mask22", "dif")}
-    print("large-logit e2e", rep)
-    for k, (mx, ps) in rep.items():
-        assert ps >= BF16_PSNR_DB and mx <= 3e-2, (k, mx, ps)
+    ref64 = generator_forward(w, d["img"], d["uv"], variant="gsc", bmask_override=bm, dtype=torch.float64)
+    for k in ("gs", "con_rgb", "mask22", "dif"):
+        err, sens = float(np.abs(got[k] - ref[k]).max()), float(np.abs(ref64[k] - ref[k]).max())
+        print("large-logit gain %.0f w x %s %-8s max-abs %.2e  oracle fp32-vs-fp64 %.2e  ratio %.0f  psnr %.1f dB" % (
+            gain, "1" if undamp else "0.35", k, err, sens, err / max(sens, 1e-12), psnr(got[k], ref[k])))
+        assert psnr(got[k], ref[k]) >= BF16_PSNR_DB, k
+        if undamp:
+            assert err <= max(1500.0 * sens, BF16_TOL), (k, err, sens)
+        else:
+            assert err <= BF16_TOL, (k, err)
     gen.close()
 
 

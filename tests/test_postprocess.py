@@ -1,0 +1,107 @@
+"""the post-processing of FSRNet.test_step (train_test_GSC.py:436-725).
+CPU: the oracle restatement (oracle/postprocess_ref.py) - its connected-component routine against
+cv2.connectedComponentsWithStats (the routine the reference calls, :590), its rules on hand-made cases.
+GPU (-m gpu): bsr_postprocess_ucb against that oracle on the reference's real UCB files and region masks."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import postprocess_ref as PP
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = os.path.join(HERE, "fixtures")
+
+
+def test_components_equal_cv2_connected_components_with_stats():
+    import cv2
+    rng = np.random.default_rng(3)
+    for density in (0.3, 0.5, 0.6, 0.9):
+        b = (rng.random((256, 256)) < density).astype(np.uint8)
+        b[100:140, 60:200] = 1                                  # one big blob
+        lab, sizes = PP.components(b)
+        n, lab_cv, stats, _ = cv2.connectedComponentsWithStats(b, connectivity=4)
+        assert len(sizes) == n - 1
+        assert sorted(sizes.tolist()) == sorted(stats[1:, -1].tolist())
+        # same partition: the map between the two labelings is a bijection
+        pairs = np.unique(np.stack([lab.ravel(), lab_cv.ravel()]), axis=1)
+        assert pairs.shape[1] == n and len(set(pairs[0])) == n and len(set(pairs[1])) == n
+    lab, sizes = PP.components(np.zeros((256, 256), np.uint8))
+    assert sizes.size == 0 and lab.max() == 0
+
+
+def _load_case(png, weights=None):
+    import cv2
+    from blindshadowremoval_b200 import feed
+    stem = os.path.basename(png)[:-4]
+    f = feed.load_frame(png, gt_path=png.replace(os.sep + "input" + os.sep, os.sep + "gt" + os.sep))
+    masks = {k: cv2.imread(os.path.join(FIX, "UCB_masks", k, stem + ".png")) / 255.0 for k in PP.MASK_KINDS}
+    return f, masks, int(f["box"][3] - f["box"][1])
+
+
+def _synthetic_outputs(f, seed):
+    """Stand-in generator outputs with the statistics of a trained model's (a soft shadow blob as `dif`, a brightened
+    image as `con_rgb`): the random-init generator saturates the mask, which would leave most rules idle."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[:256, :256]
+    cy, cx, r = rng.uniform(90, 170), rng.uniform(70, 190), rng.uniform(40, 80)
+    blob = np.exp(-(((yy - cy) / r) ** 2 + ((xx - cx) / (1.3 * r)) ** 2))
+    speck = (rng.random((256, 256)) > 0.995) * 0.05
+    dif = (0.06 * blob + speck + 0.004 * rng.standard_normal((256, 256))).astype(np.float32)[..., None]
+    rgb = np.clip(f["img"] * (1.0 + 0.8 * blob[..., None]), 0, 1.2).astype(np.float32)
+    return rgb, dif
+
+
+def test_oracle_postprocess_rules_on_real_files():
+    files = sorted(glob.glob(os.path.join(FIX, "UCB", "input", "*", "*.png")))
+    for i, p in enumerate(files[:4]):
+        f, masks, size = _load_case(p)
+        rgb, dif = _synthetic_outputs(f, i)
+        r = PP.test_step_postprocess(f["img"], f["gt"], rgb, dif, size, masks)
+        det = r["detected"]
+        assert set(np.unique(det)) <= {0.0, 1.0} and 0 < det.sum() < 0.6 * size * size
+        assert det[size:, :].sum() == 0 and det[:, size:].sum() == 0          # nothing in the padding
+        # outside the detected mask the output is the (resized, padded) input, inside it the prediction
+        assert np.array_equal(r["final"][det == 0], np.clip(r["tmp"], 0, 1)[det == 0])
+        assert np.array_equal(r["final"][det == 1], np.clip(r["pred"], 0, 1)[det == 1])
+        assert 0.0 < r["ssim"] <= 1.0 and r["psnr"] > 5.0
+        allowed = (-0.001, 0.004, 0.01, 0.02, 1.0)
+        assert all(min(abs(float(v) - c) for c in allowed) < 1e-6 for v in np.unique(r["threshold"]))
+
+
+@pytest.mark.gpu
+def test_device_postprocess_matches_oracle_on_ucb_files():
+    import torch
+    from blindshadowremoval_b200.generator import Generator
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a B200")
+    files = sorted(glob.glob(os.path.join(FIX, "UCB", "input", "*", "*.png")))
+    cases, refs = [], []
+    for i, p in enumerate(files):
+        f, masks, size = _load_case(p)
+        for variant in range(2):                                 # two different synthetic predictions per file
+            rgb, dif = _synthetic_outputs(f, 10 * i + variant)
+            cases.append((f, masks, size, rgb, dif))
+            refs.append(PP.test_step_postprocess(f["img"], f["gt"], rgb, dif, size, masks))
+    n = len(cases)
+    t = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
+    img = t(np.stack([c[0]["img"] for c in cases]))
+    gt = t(np.stack([c[0]["gt"] for c in cases]))
+    rgb = t(np.stack([c[3] for c in cases]))
+    dif = t(np.stack([c[4] for c in cases]))
+    sizes = t(np.asarray([c[2] for c in cases]), torch.int32)
+    mk = np.stack([np.stack([np.rint(c[1][k][..., 0]).astype(np.uint8) for k in PP.MASK_KINDS]) for c in cases])
+    gen = Generator("gsc", "tc16", device=0, micro_batch=1, seed=1)
+    final, det, met = gen.postprocess_ucb(img, gt, rgb, dif, sizes, t(mk, torch.uint8))
+    final2, det2, met2 = gen.postprocess_ucb(img, gt, rgb, dif, sizes, t(mk, torch.uint8))
+    torch.cuda.synchronize()
+    assert torch.equal(final, final2) and torch.equal(det, det2) and torch.equal(met, met2)      # bit-reproducible
+    final, det, met = final.cpu().numpy(), det.cpu().numpy(), met.cpu().numpy()
+    for i, r in enumerate(refs):
+        mism = int((det[i] != r["detected"]).sum())
+        assert mism == 0, (i, mism)
+        assert np.abs(final[i] - r["final"]).max() <= 1e-6, i
+        assert abs(met[i, 0] - r["ssim"]) < 2e-5 and abs(met[i, 1] - r["psnr"]) < 2e-4, (i, met[i], r["ssim"], r["psnr"])
+    print("post-processing: %d samples, detected pixels %s" % (n, [int(d.sum()) for d in det]))
+    gen.close()
