@@ -18,6 +18,14 @@
 // Layouts: QK[n][1024][256] = theta | phi;  VT[n][128][1024] = g transposed (every UMMA operand K-major);  O[n][1024][128].
 // Warp roles (320 threads): warps 0-3 softmax / epilogue of tile A, 4-7 of tile B (warp % 4 = TMEM lane quarter),
 // warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
+// FUSE = true adds the rest of the NonLocalBlock and the ResBottleneck tail (model.py:56-59, 105-113) per query tile:
+//   out = LeakyReLU(x_in + y + W_w . O + b).   O / sum goes to shared memory (into the retired Q tile) as the A operand of
+//   one more GEMM, D2[128 x 256] = O . W_w[0:256]^T over the tile's whole 256 TMEM columns; W_w arrives through the
+//   ring as two more stages (18 ring items per work item).  Channel 256 - the 257th, the only one beyond a 256-wide MMA
+//   - is a 128-term dot product per row on the CUDA cores.  The epilogue streams the residual tiles y / x_in by TMA in
+//   32-channel batches through the ring stages K7 / V7 just vacated (two 16 KB sub-stages per tile) and the result
+//   leaves by TMA stores from the output staging, so it touches shared memory only.  The next item's S needs D2's
+//   first 128 columns drained, its P V all 256.
 // Watchdog: a wait that times out (2 s) raises the error flag and a CTA-wide abort flag; from then on every wait of the
 // CTA returns immediately and the roles run their loops to the end ("skip the wait, not the work"), so no thread is left
 // behind at a named barrier and the kernel always terminates.
@@ -36,7 +44,8 @@ constexpr int FA_PAIRS = FA_S / (2 * FA_BQ);          // 4 work items per image
 constexpr uint32_t FA_TILE = 128 * 128 * 2;           // 32 KB: [128 rows][128 x 16 bit] as two 16 KB k-blocks
 constexpr uint32_t FA_OSTAGE = 128 * 64 * 2;          // 16 KB: one 64-channel half of an output tile
 constexpr int FA_THREADS = 320;
-constexpr size_t kAttnFaSmem = 1024 + 6 * (size_t)FA_TILE + 2 * FA_OSTAGE + 512;
+constexpr uint32_t FA_MISC = 2048;                    // barriers, TMEM slot, abort flag, bias and channel-256 weights
+constexpr size_t kAttnFaSmem = 1024 + 6 * (size_t)FA_TILE + 2 * FA_OSTAGE + FA_MISC;       // = 227 KB, the per-CTA maximum
 constexpr float kFaRescaleLog2 = 8.f;                 // lazy-rescale threshold (log2 units)
 
 struct FaCtx { int* errflag; volatile int* abort_s; };
@@ -110,19 +119,29 @@ __device__ __forceinline__ float fa_exp2(float x) {
   return y;
 }
 
+template <bool FUSE>
 __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __grid_constant__ CUtensorMap tmQK,
                                                                      const __grid_constant__ CUtensorMap tmVT,
                                                                      const __grid_constant__ CUtensorMap tmO,
+                                                                     const __grid_constant__ CUtensorMap tmW,
+                                                                     const __grid_constant__ CUtensorMap tmY,
+                                                                     const __grid_constant__ CUtensorMap tmX,
+                                                                     const EpiParams e, const h16* __restrict__ w_rows,
                                                                      const int n_items, int* errflag) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sR = sQ + 2 * FA_TILE, sO = sR + 4 * FA_TILE, bars = sO + 2 * FA_OSTAGE;
   const uint32_t b_rfull = bars, b_rempty = bars + 32, b_qfull = bars + 64, b_qempty = bars + 80, b_sfull = bars + 96,
-                 b_pready = bars + 112, b_ofull = bars + 128, b_odrained = bars + 144, tmem_slot = bars + 160;
+                 b_pready = bars + 112, b_ofull = bars + 128, b_odrained = bars + 144, b_a2full = bars + 160,
+                 b_d2full = bars + 176, b_d2half = bars + 192, b_resfull = bars + 208, b_resempty = bars + 240,
+                 tmem_slot = bars + 272;
   uint8_t* smem_al = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - base));
   volatile int* abort_s = reinterpret_cast<volatile int*>(smem_al + (tmem_slot + 4 - base));
+  float* bias_s = reinterpret_cast<float*>(smem_al + (bars + 288 - base));          // [272]
+  float* w256_s = bias_s + 272;                                                    // [128] weights of output channel 256
   const FaCtx ctx{errflag, abort_s};
+  constexpr uint32_t RING = FUSE ? 18u : 16u;                                      // ring items per work item
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -130,9 +149,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
     prefetch_tmap(&tmQK);
     prefetch_tmap(&tmVT);
     prefetch_tmap(&tmO);
+    if (FUSE) { prefetch_tmap(&tmW); prefetch_tmap(&tmY); prefetch_tmap(&tmX); }
     for (int s = 0; s < 4; ++s) {
       mbar_init(b_rfull + 8 * s, 1);
       mbar_init(b_rempty + 8 * s, 1);
+      mbar_init(b_resfull + 8 * s, 1);
+      mbar_init(b_resempty + 8 * s, 4);
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(b_qfull + 8 * x, 1);
@@ -141,9 +163,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
       mbar_init(b_pready + 8 * x, 4);
       mbar_init(b_ofull + 8 * x, 1);
       mbar_init(b_odrained + 8 * x, 4);
+      mbar_init(b_a2full + 8 * x, 4);
+      mbar_init(b_d2full + 8 * x, 1);
+      mbar_init(b_d2half + 8 * x, 4);
     }
     *abort_s = 0;
     fence_barrier_init();
+  }
+  if (FUSE) {          // static data (weights / bias): not produced by the previous kernel
+    for (int i = threadIdx.x; i < 272; i += FA_THREADS) bias_s[i] = __ldg(e.bias + i);
+    for (int i = threadIdx.x; i < 128; i += FA_THREADS) w256_s[i] = h16_to_f32(w_rows[256 * 128 + i]);
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -157,11 +186,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
   if (warp == 8) {
     // ================= TMA producer (converged warp, elected lane issues) =================
     const bool leader = elect_one();
-    uint32_t w = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+    auto load_q = [&](const int item, const uint32_t w) {
       const int n = item / FA_PAIRS, q0 = (item % FA_PAIRS) * 2 * FA_BQ;
       for (int x = 0; x < 2; ++x) {
-        fa_wait(b_qempty + 8 * x, (w & 1u) ^ 1u, ctx, 40 + x);          // S_x(7) of the previous item has retired
+        fa_wait(b_qempty + 8 * x, (w & 1u) ^ 1u, ctx, 40 + x);          // the previous item is done with this Q buffer
         if (leader) {
           mbar_expect_tx(b_qfull + 8 * x, FA_TILE);
           tma_load_3d(sQ + x * FA_TILE, &tmQK, b_qfull + 8 * x, 0, q0 + x * FA_BQ, n);
@@ -169,8 +197,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         }
         __syncwarp();
       }
+    };
+    uint32_t w = 0;
+    if (FUSE && (int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+      const int n = item / FA_PAIRS, q0 = (item % FA_PAIRS) * 2 * FA_BQ;
+      const uint32_t rb = RING * w;
+      if (!FUSE) load_q(item, w);
+      if (FUSE && w > 0) {
+        // the ring stages that held K7 / V7 of the previous item served as residual staging: wait for its epilogues
+        for (int s = 0; s < 4; ++s) fa_wait(b_resempty + 8 * s, 1u, ctx, 44);
+      }
       for (int j = 0; j < FA_NK; ++j) {
-        const uint32_t ik = 16u * w + 2u * j, iv = ik + 1u;               // ring items: K(j), V(j)
+        const uint32_t ik = rb + 2u * j, iv = ik + 1u;                    // ring items: K(j), V(j)
         fa_wait(b_rempty + 8 * (ik & 3u), ((ik >> 2) & 1u) ^ 1u, ctx, 42);
         if (leader) {
           const uint32_t dst = sR + (ik & 3u) * FA_TILE, bar = b_rfull + 8 * (ik & 3u);
@@ -187,6 +226,40 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
           tma_load_3d(dst + FA_TILE / 2, &tmVT, bar, j * FA_BK + 64, 0, n);
         }
         __syncwarp();
+      }
+      if (FUSE) {
+        // ---- W_w[0:256] as two more ring items (one 64-wide K block = 256 rows x 128 B = one stage each)
+        for (uint32_t kb = 0; kb < 2; ++kb) {
+          const uint32_t iw = rb + 16u + kb;
+          fa_wait(b_rempty + 8 * (iw & 3u), ((iw >> 2) & 1u) ^ 1u, ctx, 45);
+          if (leader) {
+            mbar_expect_tx(b_rfull + 8 * (iw & 3u), FA_TILE);
+            tma_load_2d(sR + (iw & 3u) * FA_TILE, &tmW, b_rfull + 8 * (iw & 3u), (int)kb * 64, 0);
+          }
+          __syncwarp();
+        }
+        // ---- residual tiles y / x_in, 32 channels at a time, into the stages of K7 (tile A) and V7 (tile B): free once the
+        // empty barrier the NEXT occupant of the stage would wait for has completed (same stages, since 18 = 2 mod 4)
+        const uint32_t in0 = rb + 18u, in1 = rb + 19u;
+        fa_wait(b_rempty + 8 * (in0 & 3u), ((in0 >> 2) & 1u) ^ 1u, ctx, 46);
+        fa_wait(b_rempty + 8 * (in1 & 3u), ((in1 >> 2) & 1u) ^ 1u, ctx, 47);
+        const int next = item + (int)gridDim.x;
+        for (int b = 0; b < 8; ++b) {
+          if (b == 2 && next < n_items) load_q(next, w + 1);              // Q of the next item: free after the tail MMAs
+          for (int x = 0; x < 2; ++x) {
+            const int sidx = 2 * x + (b & 1);
+            const uint32_t u = 4u * w + (uint32_t)(b >> 1);
+            fa_wait(b_resempty + 8 * sidx, (u & 1u) ^ 1u, ctx, 48);
+            if (leader) {
+              const uint32_t dst = sR + ((rb + 14u + x) & 3u) * FA_TILE + (uint32_t)(b & 1) * 16384u;
+              const int pix0 = n * FA_S + q0 + x * FA_BQ;
+              mbar_expect_tx(b_resfull + 8 * sidx, 16384);
+              tma_load_2d(dst, &tmY, b_resfull + 8 * sidx, 32 * b, pix0);
+              tma_load_2d(dst + 8192u, &tmX, b_resfull + 8 * sidx, 32 * b, pix0);
+            }
+            __syncwarp();
+          }
+        }
       }
     }
   } else if (warp == 9) {
@@ -217,15 +290,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
     };
     uint32_t w = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+      const uint32_t rb = RING * w;
       {
-        const uint32_t ik = 16u * w;                                       // K(0)
+        const uint32_t ik = rb;                                            // K(0)
         fa_wait(b_qfull, w & 1u, ctx, 50, true);
         fa_wait(b_rfull + 8 * (ik & 3u), (ik >> 2) & 1u, ctx, 51, true);
+        if (FUSE) fa_wait(b_d2half, (w & 1u) ^ 1u, ctx, 70, true);         // previous epilogue A has read D2 columns 0-127
         tc_fence_after();
         issue_s(0, ik & 3u);
         if (leader) umma_commit(b_sfull);
         __syncwarp();
         fa_wait(b_qfull + 8, w & 1u, ctx, 52, true);
+        if (FUSE) fa_wait(b_d2half + 8, (w & 1u) ^ 1u, ctx, 71, true);
         tc_fence_after();
         issue_s(1, ik & 3u);
         if (leader) {
@@ -235,12 +311,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         __syncwarp();
       }
       for (int j = 0; j < FA_NK; ++j) {
-        const uint32_t iv = 16u * w + 2u * j + 1u, ik = iv + 1u;           // V(j), K(j+1)
+        const uint32_t iv = rb + 2u * j + 1u, ik = iv + 1u;                // V(j), K(j+1)
         const uint32_t sp = (8u * w + (uint32_t)j) & 1u;                   // parity of the j-th S / P hand-over
         const bool more = j + 1 < FA_NK;
         // ---- tile A
         fa_wait(b_pready, sp, ctx, 53, true);
-        if (j == 0) fa_wait(b_odrained, (w & 1u) ^ 1u, ctx, 54, true);     // epilogue of the previous item has read O_A
+        if (j == 0) fa_wait(b_odrained, (w & 1u) ^ 1u, ctx, 54, true);     // epilogue of the previous item is done with tile A's columns
         fa_wait(b_rfull + 8 * (iv & 3u), (iv >> 2) & 1u, ctx, 55, true);
         tc_fence_after();
         issue_pv(0, iv & 3u, j != 0);
@@ -251,7 +327,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
           issue_s(0, ik & 3u);
           if (leader) {
             umma_commit(b_sfull);
-            if (j + 2 == FA_NK) umma_commit(b_qempty);                     // last S_A of this item: Q_A may be refilled
+            if (!FUSE && j + 2 == FA_NK) umma_commit(b_qempty);            // last S_A of this item: Q_A may be refilled
           }
         }
         __syncwarp();
@@ -269,8 +345,36 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
           if (leader) {
             umma_commit(b_sfull + 8);
             umma_commit(b_rempty + 8 * (ik & 3u));                         // K(j+1) consumed by both tiles
-            if (j + 2 == FA_NK) umma_commit(b_qempty + 8);
+            if (!FUSE && j + 2 == FA_NK) umma_commit(b_qempty + 8);
           }
+        }
+        __syncwarp();
+      }
+      if (FUSE) {
+        // ---- D2_x[128 x 256] = (O_x / sum)[128 x 128] . W_w[0:256]^T : A from the Q_x buffer, B from ring items 16, 17
+        const uint32_t iw0 = rb + 16u, iw1 = rb + 17u;
+        const uint32_t id256 = umma_idesc_h16(128, 256);
+        fa_wait(b_rfull + 8 * (iw0 & 3u), (iw0 >> 2) & 1u, ctx, 72, true);
+        fa_wait(b_rfull + 8 * (iw1 & 3u), (iw1 >> 2) & 1u, ctx, 73, true);
+        for (int x = 0; x < 2; ++x) {
+          fa_wait(b_a2full + 8 * x, w & 1u, ctx, 74 + x, true);            // O_x is in shared memory, its TMEM columns are read
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint32_t a_lo = umma_desc_lo(sQ + x * FA_TILE + kb * (FA_TILE / 2));
+              const uint32_t b_lo = umma_desc_lo(sR + ((kb ? iw1 : iw0) & 3u) * FA_TILE);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_h16_lo(tmem + 256u * x, a_lo + 2 * k, b_lo + 2 * k, id256, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(b_d2full + 8 * x);
+            umma_commit(b_qempty + 8 * x);
+          }
+          __syncwarp();
+        }
+        if (leader) {
+          umma_commit(b_rempty + 8 * (iw0 & 3u));
+          umma_commit(b_rempty + 8 * (iw1 & 3u));
         }
         __syncwarp();
       }
@@ -358,40 +462,155 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(b_pready + 8 * x);
       }
-      // ---- epilogue: O / sum -> 16 bit -> swizzled staging (64 channels at a time) -> TMA store
       fa_wait(b_ofull + 8 * x, w & 1u, ctx, 62 + x);
       tc_fence_after();
       const float inv = 1.f / l;
       const int pix0 = n * FA_S + q0;
+      if (!FUSE) {
+        // ---- epilogue: O / sum -> 16 bit -> swizzled staging (64 channels at a time) -> TMA store
 #pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t v[64];
-        tmem_ld32_nowait(tO + 64u * hf, v);
-        tmem_ld32_nowait(tO + 64u * hf + 32u, v + 32);
-        tmem_wait_ld();
-        if (hf == 1) {                                   // accumulator fully read: the next item's P V may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_odrained + 8 * x);
-        }
-        // the bulk store that last read this staging buffer has finished reading it
-        if (wg_leader) bulk_wait_read0();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
-        uint8_t* dst = stage + row * 128;
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t v[64];
+          tmem_ld32_nowait(tO + 64u * hf, v);
+          tmem_ld32_nowait(tO + 64u * hf + 32u, v + 32);
+          tmem_wait_ld();
+          if (hf == 1) {                                   // accumulator fully read: the next item's P V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_odrained + 8 * x);
+          }
+          // the bulk store that last read this staging buffer has finished reading it
+          if (wg_leader) bulk_wait_read0();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+          uint8_t* dst = stage + row * 128;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 o;
-          o.x = pack_h16x2(__uint_as_float(v[8 * ch + 0]) * inv, __uint_as_float(v[8 * ch + 1]) * inv);
-          o.y = pack_h16x2(__uint_as_float(v[8 * ch + 2]) * inv, __uint_as_float(v[8 * ch + 3]) * inv);
-          o.z = pack_h16x2(__uint_as_float(v[8 * ch + 4]) * inv, __uint_as_float(v[8 * ch + 5]) * inv);
-          o.w = pack_h16x2(__uint_as_float(v[8 * ch + 6]) * inv, __uint_as_float(v[8 * ch + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = o;
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 o;
+            o.x = pack_h16x2(__uint_as_float(v[8 * ch + 0]) * inv, __uint_as_float(v[8 * ch + 1]) * inv);
+            o.y = pack_h16x2(__uint_as_float(v[8 * ch + 2]) * inv, __uint_as_float(v[8 * ch + 3]) * inv);
+            o.z = pack_h16x2(__uint_as_float(v[8 * ch + 4]) * inv, __uint_as_float(v[8 * ch + 5]) * inv);
+            o.w = pack_h16x2(__uint_as_float(v[8 * ch + 6]) * inv, __uint_as_float(v[8 * ch + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = o;
+          }
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+          if (wg_leader) {
+            tma_store_2d(&tmO, stage_u32, 64 * hf, pix0);
+            bulk_commit();
+          }
         }
+      } else {
+        // ---- O / sum -> 16-bit A operand in the retired Q_x buffer (128B-swizzled K-major, 64 channels per k-block);
+        // channel 256 of the output conv as a dot product on the way
+        const size_t pix = (size_t)pix0 + row;
+        uint4 ya[2], xa[2];                              // channels 256..271 of y / x_in: needed at the very end
+        {
+          const uint4* s1 = reinterpret_cast<const uint4*>((const h16*)e.res1 + pix * e.res1_ld + 256);
+          const uint4* s2 = reinterpret_cast<const uint4*>((const h16*)e.res2 + pix * e.res2_ld + 256);
+          ya[0] = s1[0]; ya[1] = s1[1]; xa[0] = s2[0]; xa[1] = s2[1];
+        }
+        float dot0 = 0.f, dot1 = 0.f;
+        uint8_t* qbuf = smem_al + (sQ + x * FA_TILE - base) + row * 128;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t v[64];
+          tmem_ld32_nowait(tO + 64u * hf, v);
+          tmem_ld32_nowait(tO + 64u * hf + 32u, v + 32);
+          tmem_wait_ld();
+          const float* wr = w256_s + 64 * hf;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v[8 * ch + k]) * inv;
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+              dot0 = fmaf(o[k], wr[8 * ch + k], dot0);
+              dot1 = fmaf(o[k + 1], wr[8 * ch + k + 1], dot1);
+            }
+            uint4 pk;
+            pk.x = pack_h16x2(o[0], o[1]); pk.y = pack_h16x2(o[2], o[3]);
+            pk.z = pack_h16x2(o[4], o[5]); pk.w = pack_h16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(qbuf + hf * (FA_TILE / 2) + ((ch ^ (row & 7)) << 4)) = pk;
+          }
+        }
+        tc_fence_before();
         fence_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
-        if (wg_leader) {
-          tma_store_2d(&tmO, stage_u32, 64 * hf, pix0);
-          bulk_commit();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_a2full + 8 * x);
+        fa_wait(b_d2full + 8 * x, w & 1u, ctx, 64 + x);
+        tc_fence_after();
+        // ---- block tail: 8 batches of 32 channels; residuals from the ring stage of K7 (tile A) / V7 (tile B)
+        const uint32_t rs_slot = (RING * w + 14u + (uint32_t)x) & 3u;
+        const uint32_t sw = ((uint32_t)row >> 1) & 3u, rowo = (uint32_t)row * 64u;
+#pragma unroll 1
+        for (int b = 0; b < 8; ++b) {
+          const int sidx = 2 * x + (b & 1);
+          const uint32_t u = 4u * w + (uint32_t)(b >> 1);
+          uint32_t v[32];
+          tmem_ld32_nowait(tS + 32u * b, v);
+          fa_wait(b_resfull + 8 * sidx, u & 1u, ctx, 66 + x);
+          tmem_wait_ld();
+          if (b == 3 || b == 7) {                          // D2 columns 0-127 / all 256 are in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive((b == 3 ? b_d2half : b_odrained) + 8 * x);
+          }
+          const uint8_t* rs = smem_al + (sR + rs_slot * FA_TILE + (uint32_t)(b & 1) * 16384u - base) + rowo;
+          uint8_t* so = stage + (b & 1) * 8192 + rowo;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t po = (((uint32_t)c) ^ sw) << 4;
+            const uint4 yv = *reinterpret_cast<const uint4*>(rs + po);
+            const uint4 xv = *reinterpret_cast<const uint4*>(rs + 8192 + po);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 32 * b + 8 * c);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 32 * b + 8 * c + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 yy = unpack_h16x2(yw[k]), xx = unpack_h16x2(xw[k]);
+              float r0 = __uint_as_float(v[8 * c + 2 * k]) + bb[2 * k] + yy.x + xx.x;
+              float r1 = __uint_as_float(v[8 * c + 2 * k + 1]) + bb[2 * k + 1] + yy.y + xx.y;
+              r0 = fmaxf(r0, kLeaky * r0);
+              r1 = fmaxf(r1, kLeaky * r1);
+              ow[k] = pack_h16x2(r0, r1);
+            }
+            *reinterpret_cast<uint4*>(so + po) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_resempty + 8 * sidx);
+          // the store issued one batch ago has finished reading the OTHER staging half before anyone passes the barrier
+          // and overwrites it in the next batch
+          if (wg_leader) bulk_wait_read0();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+          if (wg_leader) {
+            tma_store_2d(&tmO, stage_u32 + (uint32_t)(b & 1) * 8192u, 32 * b, pix0);
+            bulk_commit();
+          }
+        }
+        // ---- channels 256..271: the 257th channel (CUDA-core dot product) and the 15 padding channels
+        {
+          float t[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t[i] = 0.f;
+          t[0] = dot0 + dot1 + bias_s[256];
+          const uint32_t yw[8] = {ya[0].x, ya[0].y, ya[0].z, ya[0].w, ya[1].x, ya[1].y, ya[1].z, ya[1].w};
+          const uint32_t xw[8] = {xa[0].x, xa[0].y, xa[0].z, xa[0].w, xa[1].x, xa[1].y, xa[1].z, xa[1].w};
+          uint32_t ow[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 yy = unpack_h16x2(yw[k]), xx = unpack_h16x2(xw[k]);
+            float r0 = t[2 * k] + yy.x + xx.x, r1 = t[2 * k + 1] + yy.y + xx.y;
+            r0 = fmaxf(r0, kLeaky * r0);
+            r1 = fmaxf(r1, kLeaky * r1);
+            ow[k] = pack_h16x2(r0, r1);
+          }
+          uint4* d = reinterpret_cast<uint4*>((h16*)e.out + pix * e.out_ld + e.out_coff + 256);
+          d[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          d[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
         }
       }
     }
@@ -406,25 +625,30 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
   }
 }
 
+struct FaMaps { CUtensorMap qk, vt, o; };
+struct FaTailMaps { CUtensorMap w, y, x, out; };
+
 // O[n][1024][128] = softmax(QK^T) V for n images; persistent grid of min(num_sms, 4 n) CTAs.
+// With `w_packed` / `e` (FUSE): out = LeakyReLU(x_in + y + W_w . O + b) is written instead of O (see the kernel comment);
+// w_packed = the [288 rows][128] K-major 16-bit matrix of the output conv, e = bias / res1 = y / res2 = x_in / out.
 inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h16* o, int n, int num_sms, int* errflag,
-                               cudaStream_t st, const Knobs& kn) {
-  static thread_local std::map<std::tuple<const void*, const void*, const void*, int>, std::tuple<CUtensorMap, CUtensorMap, CUtensorMap>> cache;
+                               cudaStream_t st, const Knobs& kn, const h16* w_packed = nullptr, const EpiParams* e = nullptr) {
+  static thread_local std::map<std::tuple<const void*, const void*, const void*, int>, FaMaps> cache;
   auto key = std::make_tuple((const void*)qk, (const void*)vt, (const void*)o, n);
   auto it = cache.find(key);
   if (it == cache.end()) {
-    CUtensorMap mq, mv, mo;
+    FaMaps m;
     uint64_t dq[3] = {256, FA_S, (uint64_t)n}, sq[2] = {256 * 2, (uint64_t)FA_S * 256 * 2};
     uint32_t bq[3] = {64, 128, 1};
-    if (!tma.encode_h16(&mq, (void*)qk, 3, dq, sq, bq, nullptr)) return -1;
+    if (!tma.encode_h16(&m.qk, (void*)qk, 3, dq, sq, bq, nullptr)) return -1;
     uint64_t dv[3] = {FA_S, FA_D, (uint64_t)n}, sv[2] = {(uint64_t)FA_S * 2, (uint64_t)FA_D * FA_S * 2};
     uint32_t bv[3] = {64, 128, 1};
-    if (!tma.encode_h16(&mv, (void*)vt, 3, dv, sv, bv, nullptr)) return -2;
+    if (!tma.encode_h16(&m.vt, (void*)vt, 3, dv, sv, bv, nullptr)) return -2;
     uint64_t d2[2] = {FA_D, (uint64_t)n * FA_S}, s2[1] = {(uint64_t)FA_D * 2};
     uint32_t b2[2] = {64, 128};
-    if (!tma.encode_h16(&mo, (void*)o, 2, d2, s2, b2, nullptr)) return -4;
+    if (!tma.encode_h16(&m.o, (void*)o, 2, d2, s2, b2, nullptr)) return -4;
     if (cache.size() > 256) cache.clear();
-    it = cache.emplace(key, std::make_tuple(mq, mv, mo)).first;
+    it = cache.emplace(key, m).first;
   }
   const int n_items = n * FA_PAIRS;
   cudaLaunchConfig_t cfg;
@@ -438,14 +662,44 @@ inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h1
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = kn.no_pdl ? 0 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, attention_fa_kernel, std::get<0>(it->second), std::get<1>(it->second),
-                                      std::get<2>(it->second), n_items, errflag);
+  EpiParams ep;
+  memset(&ep, 0, sizeof ep);
+  cudaError_t le;
+  if (w_packed && e) {
+    // tail maps: W_w rows 0..255 as [64 K x 256 rows] boxes; y / x_in / out as [pixels x channels], 32-channel boxes, 64B swizzle
+    static thread_local std::map<std::tuple<const void*, const void*, const void*, const void*, int, int>, FaTailMaps> tcache;
+    auto tkey = std::make_tuple((const void*)w_packed, e->res1, e->res2, (const void*)e->out, e->out_ld * 4096 + e->res2_ld, n);
+    auto tt = tcache.find(tkey);
+    if (tt == tcache.end()) {
+      FaTailMaps m;
+      uint64_t dw[2] = {128, 288}, sw[1] = {128 * 2};
+      uint32_t bw[2] = {64, 256};
+      if (!tma.encode_h16(&m.w, (void*)w_packed, 2, dw, sw, bw, nullptr)) return -5;
+      const void* bases[3] = {e->res1, e->res2, (const void*)((const h16*)e->out + e->out_coff)};
+      const int lds[3] = {e->res1_ld, e->res2_ld, e->out_ld};
+      CUtensorMap* dst[3] = {&m.y, &m.x, &m.out};
+      for (int i = 0; i < 3; ++i) {
+        uint64_t d2[2] = {(uint64_t)lds[i], (uint64_t)n * FA_S}, s2[1] = {(uint64_t)lds[i] * 2};
+        uint32_t b2[2] = {32, 128};
+        if (!tma.encode_h16_store(dst[i], (void*)bases[i], 2, d2, s2, b2)) return -6;
+      }
+      if (tcache.size() > 1024) tcache.clear();
+      tt = tcache.emplace(tkey, m).first;
+    }
+    ep = *e;
+    le = cudaLaunchKernelEx(&cfg, attention_fa_kernel<true>, it->second.qk, it->second.vt, tt->second.out, tt->second.w,
+                            tt->second.y, tt->second.x, ep, w_packed, n_items, errflag);
+  } else {
+    le = cudaLaunchKernelEx(&cfg, attention_fa_kernel<false>, it->second.qk, it->second.vt, it->second.o, it->second.qk,
+                            it->second.qk, it->second.qk, ep, (const h16*)nullptr, n_items, errflag);
+  }
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
   return 0;
 }
 
 inline int configure_tc_kernels_attn_fa() {
-  cudaError_t e = cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnFaSmem);
+  cudaError_t e = cudaFuncSetAttribute(attention_fa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnFaSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnFaSmem);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

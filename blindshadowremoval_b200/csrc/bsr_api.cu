@@ -271,11 +271,16 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
     h->launches++;
     return BSR_OK;
   }
-  if (!h->force_direct && !wl && !h->kn.attn_v1) {
-    // single-pass kernel (attention_fa.cuh): O = softmax(QK^T) V; the output conv w runs as its own launch
-    int rc = launch_attention_fa(h->tma, (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, n, h->num_sms, h->errflag, st, h->kn);
+  if (!h->force_direct && !h->kn.attn_v1) {
+    // single-pass kernel (attention_fa.cuh): O = softmax(QK^T) V, or with `wl` the whole rest of the block:
+    // out = LeakyReLU(x_in + y + W_w . O + b)
+    EpiParams e2;
+    if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
+    int rc = launch_attention_fa(h->tma, (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, n, h->num_sms, h->errflag, st, h->kn,
+                                 wl ? (const h16*)wl->tc.dev : nullptr, wl ? &e2 : nullptr);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
     h->launches++;
+    h->pc.attn_fused += wl != nullptr;
     return BSR_OK;
   }
   if (!h->force_direct) {
@@ -340,7 +345,8 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   // NonLocal output conv + block tail: fused into the attention kernel on the tensor-core path
   const Layer& wl = h->layers[nm[4]];
   const bool fuse_w = h->precision == BSR_PRECISION_BF16 && !h->force_direct && wl.tc.ready && wl.tc.kind == TC_CONV &&
-                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !h->kn.no_fuse_w && h->kn.attn_v1;
+                      wl.tc.bn == 144 && wl.tc.n_tiles == 2 && wl.cin == 128 && oc == kLdY && !h->kn.no_fuse_w && wl.tc.b_total_rows == 288 &&
+                      ld % 8 == 0;
   if (fuse_w) {
     if ((rc = run_attention(h, st, n, &wl, &ew))) return rc;
   } else {

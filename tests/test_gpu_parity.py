@@ -195,8 +195,8 @@ def test_layer_times_and_launch_count(G):
     torch.cuda.synchronize()
     times = gen.layer_times()
     names = [n for n, _ in times]
-    assert gen.launch_count() == 55 and len(times) >= 46          # 55 launches per GSC forward
-    for must in ("conv1", "down1", "res0.conv2", "res5.qkv", "attention", "res5.w", "up3", "heads", "clr_up3", "clr_conv1"):
+    assert gen.launch_count() == 49 and len(times) >= 40          # 49 launches per GSC forward (w fused into attention)
+    for must in ("conv1", "down1", "res0.conv2", "res5.qkv", "attention+w", "up3", "heads", "clr_up3", "clr_conv1"):
         assert must in names, must
     assert all(ms > 0 for _, ms in times)
     assert gen.workspace_bytes() > 2 * 30e6
@@ -436,7 +436,7 @@ def test_benchmark_configuration_gsc_256_images_mb128_matches_oracle(G):
     out = gen(t["img"], t["uv"], None)
     gen.check()
     pc = gen.plan_counters()
-    assert pc["pinned"] >= 12 and pc["resident"] >= 12 and pc["staged"] >= 8, pc
+    assert pc["pinned"] >= 12 and pc["resident"] >= 12 and pc["staged"] >= 8 and pc["attn_fused"] == 12, pc
     got = dict(zip(("gs", "con_rgb", "mask22", "dif"), (o.cpu().numpy() for o in out)))
     for k, v in got.items():
         assert np.array_equal(v[:128], v[128:]), k                      # micro-batch 0 == micro-batch 1
