@@ -30,10 +30,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=128)
+    ap.add_argument("--micro-batch", type=int, default=256)
     ap.add_argument("--variant", default="gsc", choices=["gsc", "tsm"])
     ap.add_argument("--frame", type=int, default=2)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32check"])
+    ap.add_argument("--precision", default="tc16", choices=["tc16", "bf16", "f16", "fp32check"],
+                    help="tc16 = the 16-bit tensor-core product path (binary16 storage); bf16 / f16 are aliases of it")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (TSM frames/s, config-3 sharded evaluation over NCCL, strong-scaling split)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer roofline table to stderr")
@@ -191,6 +194,87 @@ def workload_config(args):
                      (args.batch * 256 * 256 * 6 * 4 / 1e6)}
 
 
+def timed_steps(fn, steps, barrier, world, dev):
+    """max-over-ranks device time per step of `fn` (CUDA events on the launching stream, barrier + sync both sides)."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(3):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() / steps
+
+
+def extra_legs(args, gen, w, world, rank, local, dev, barrier):
+    """(a) strong scaling of BASELINE config 4 (256 images split over the N GPUs), (b) the TSM variant at frame 2 and 10,
+    (c) BASELINE config 3: SFW-style chunk evaluation sharded over the ranks with ONE NCCL all-reduce of the accumulators
+    (train_with_TSM.py:619-701, utils.py:136-171), cross-checked against a single process scoring every chunk."""
+    import numpy as np
+    import torch
+    from blindshadowremoval_b200.evaluate import evaluate_sfw
+    from blindshadowremoval_b200.generator import Generator
+    from blindshadowremoval_b200.synthetic import make_inputs
+    from blindshadowremoval_b200.weights import random_weights
+    out = {}
+    steps = max(2, min(args.steps, 6))
+    # ---- (a) strong scaling
+    per = max(1, 256 // world)
+    base = make_inputs(min(per, 32), seed=rank)
+    reps = (per + 31) // 32
+    simg = torch.from_numpy(base["img"]).to(dev).repeat(reps, 1, 1, 1)[:per].contiguous()
+    suv = torch.from_numpy(base["uv"]).to(dev).repeat(reps, 1, 1, 1)[:per].contiguous()
+    sgen = gen if per == args.micro_batch else Generator("gsc", args.precision, device=local, micro_batch=min(per, args.micro_batch), weights=w)
+    ms = timed_steps(lambda: sgen(simg, suv, None, want=("con_rgb", "dif")), steps, barrier, world, dev)
+    out["strong_scaling"] = {"workload": "256 images per step split evenly over the GPUs (BASELINE config 4)", "images_per_gpu": per,
+                             "value": round(per * world / (ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(ms, 4)}
+    if sgen is not gen:
+        sgen.close()
+    # ---- (b) TSM frames/s
+    wt = random_weights("tsm", 1234)
+    tgen = Generator("tsm", args.precision, device=local, micro_batch=args.micro_batch, weights=wt)
+    tb = make_inputs(20, seed=100 + rank, with_reg=True)
+    tsm = {}
+    for frame in (2, 10):
+        nb = args.batch // frame * frame
+        r = (nb + 19) // 20
+        ti, tu, tr = (torch.from_numpy(tb[k]).to(dev).repeat(r, 1, 1, 1)[:nb].contiguous() for k in ("img", "uv", "reg"))
+        ms = timed_steps(lambda: tgen(ti, tu, tr, frame=frame, share=True, want=("con_rgb", "dif")), steps, barrier, world, dev)
+        tsm["frame%d" % frame] = {"value": round(nb * world / (ms / 1e3), 2), "unit": "frames/s", "frames_per_gpu_per_step": nb,
+                                  "ms_per_step": round(ms, 4)}
+        del ti, tu, tr
+    out["tsm"] = tsm
+    # ---- (c) config 3: sharded evaluation, NCCL all-reduce of (sum ssim, sum psnr, sum auc, count)
+    n_chunks, frame = 64, 2
+    pool = []
+    for i in range(8):
+        d = make_inputs(2, seed=500 + i, with_reg=True)
+        blobs = make_inputs(2, seed=900 + i)["img"][..., 0:1]
+        label = np.where(blobs > np.quantile(blobs, 0.8), 2.0, np.where(blobs < np.quantile(blobs, 0.2), 1.0, 0.0)).astype(np.float32)
+        cmap = np.zeros_like(d["img"])
+        pool.append(torch.from_numpy(np.concatenate([d["img"], cmap, label, d["uv"], d["reg"], d["face"]], axis=3)).to(dev))
+    barrier()
+    t0 = time.perf_counter()
+    res = evaluate_sfw(tgen, lambda i: pool[i % 8], n_chunks, frame=frame, rank=rank, world=world, device=dev)
+    barrier()
+    dt = time.perf_counter() - t0
+    single = evaluate_sfw(tgen, lambda i: pool[i % 8], n_chunks, frame=frame, rank=0, world=1, device=dev, reduce=False) if rank == 0 else None
+    out["config3_sfw_eval"] = {"chunks": n_chunks, "frame": frame, "ranks": world, "auc": round(res["auc"], 6), "ssim": round(res["ssim"], 6),
+                               "psnr": round(res["psnr"], 4), "count": res["count"], "seconds": round(dt, 3),
+                               "collective": "one %s all-reduce of [sum_ssim, sum_psnr, sum_auc, count]" % ("NCCL" if world > 1 else "(single rank: no)"),
+                               "auc_single_process": round(single["auc"], 6) if single else None,
+                               "auc_equal_to_3_decimals": (abs(single["auc"] - res["auc"]) < 5e-4) if single else None}
+    tgen.close()
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -199,7 +283,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from blindshadowremoval_b200.generator import Generator
+    from blindshadowremoval_b200.generator import Generator, act_dtype
     from blindshadowremoval_b200.synthetic import make_inputs
     from blindshadowremoval_b200.weights import random_weights
 
@@ -336,6 +420,11 @@ def main():
                        "api": "Generator.forward_compact -> bsr_forward_%s_host_compact (u8 img, 32x32 uv%s in; "
                               "u8 rgb, f16 dif out)" % (args.variant, "/reg" if tsm else "")}
 
+    # ---- extra legs (reported beside the headline, never instead of it)
+    extras = {}
+    if not args.no_extras and args.variant == "gsc" and args.precision != "fp32check":
+        extras = extra_legs(args, gen, w, world, rank, local, dev, barrier)
+
     # ---- roofline of the dominant kernel: per-layer CUDA events on the launching stream (BSR_PROFILE handle)
     roof, table = None, None
     if rank == 0:
@@ -425,11 +514,12 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": act_dtype() if args.precision != "fp32check" else "f32",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks_summary(samples),
             "e2e": e2e, "e2e_compact": e2e_compact, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "checksum_mean_rgb": round(checksum, 6),
         }
+        line.update(extras)
         if args.layers and table:
             line["layers"] = table
         print(json.dumps(line))

@@ -15,7 +15,8 @@
 //     accumulator rows without another barrier.
 // TMEM (512 columns): [S_A | O_A | S_B | O_B], 128 fp32 columns each.   Shared memory: Q_A, Q_B (32 KB each), a ring of
 // four 32 KB stages fed in the order K0 V0 K1 V1 ..., two 16 KB output staging buffers (64 channels x 128 rows).
-// Layouts: QK[n][1024][256] = theta | phi;  VT[n][128][1024] = g transposed (every UMMA operand K-major);  O[n][1024][128].
+// Layouts: QK[n][1024][256] = theta | phi;  V[n][1024][128] = g as the projection conv writes it (an MN-major B operand of
+// the P V MMA);  O[n][1024][128].
 // Warp roles (320 threads): warps 0-3 softmax / epilogue of tile A, 4-7 of tile B (warp % 4 = TMEM lane quarter),
 // warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
 // FUSE = true adds the rest of the NonLocalBlock and the ResBottleneck tail (model.py:56-59, 105-113) per query tile:
@@ -209,6 +210,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         for (int s = 0; s < 4; ++s) fa_wait(b_resempty + 8 * s, 1u, ctx, 44);
       }
       for (int j = 0; j < FA_NK; ++j) {
+        if (FUSE && leader && j >= 2 && j < 6) {
+          // pull this item's residual tiles (y, x_in: written several kernels ago, not L2 resident) into L2 well before
+          // the block tail streams them through two small stages: 4 of the 16 boxes per tensor and key tile
+          const int xq = (j - 2) >> 1, b0 = ((j - 2) & 1) * 4, pix0 = n * FA_S + q0 + xq * FA_BQ;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            tma_prefetch_2d(&tmY, 32 * (b0 + b), pix0);
+            tma_prefetch_2d(&tmX, 32 * (b0 + b), pix0);
+          }
+        }
         const uint32_t ik = rb + 2u * j, iv = ik + 1u;                    // ring items: K(j), V(j)
         fa_wait(b_rempty + 8 * (ik & 3u), ((ik >> 2) & 1u) ^ 1u, ctx, 42);
         if (leader) {
@@ -222,8 +233,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         if (leader) {
           const uint32_t dst = sR + (iv & 3u) * FA_TILE, bar = b_rfull + 8 * (iv & 3u);
           mbar_expect_tx(bar, FA_TILE);
-          tma_load_3d(dst, &tmVT, bar, j * FA_BK, 0, n);
-          tma_load_3d(dst + FA_TILE / 2, &tmVT, bar, j * FA_BK + 64, 0, n);
+          tma_load_3d(dst, &tmVT, bar, 0, j * FA_BK, n);                   // V[n][keys][d]: d 0..63, then d 64..127
+          tma_load_3d(dst + FA_TILE / 2, &tmVT, bar, 64, j * FA_BK, n);
         }
         __syncwarp();
       }
@@ -278,13 +289,17 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         }
       }
     };
-    // O_x (+)= P_x . V  (TS mode: P = 16-bit pairs in columns [256 x, 256 x + 64), 8 columns per 16 keys)
+    // O_x (+)= P_x . V  (TS mode: P = 16-bit pairs in columns [256 x, 256 x + 64), 8 columns per 16 keys).
+    // V is stored as the projection conv writes it, [key][d] with d contiguous, i.e. an MN-major B operand: the stage
+    // holds two [128 keys][64 d] boxes (128-byte rows, 128B swizzle); 16 keys = two 8-row groups (SBO = 1024 B apart),
+    // the second 64-wide d block is LBO = 16 KB away.
+    const uint32_t idesc_pv = idesc | (1u << 16);                          // B operand MN-major
     auto issue_pv = [&](const int x, const uint32_t slot, const bool acc) {
       if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t b_lo = umma_desc_lo(sR + slot * FA_TILE + (kk >> 2) * (FA_TILE / 2)) + 2 * (kk & 3);
-          umma_h16_ts(tmem + 256u * x + 128u, tmem + 256u * x + 8u * kk, b_lo, idesc, (acc || kk != 0) ? 1u : 0u);
+          const uint32_t b_lo = (((sR + slot * FA_TILE + (uint32_t)kk * 2048u) & 0x3FFFFu) >> 4) | ((FA_TILE / 2 / 16) << 16);
+          umma_h16_ts(tmem + 256u * x + 128u, tmem + 256u * x + 8u * kk, b_lo, idesc_pv, (acc || kk != 0) ? 1u : 0u);
         }
       }
     };
@@ -628,7 +643,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
 struct FaMaps { CUtensorMap qk, vt, o; };
 struct FaTailMaps { CUtensorMap w, y, x, out; };
 
-// O[n][1024][128] = softmax(QK^T) V for n images; persistent grid of min(num_sms, 4 n) CTAs.
+// O[n][1024][128] = softmax(QK^T) V for n images (vt = V[n][1024][128], NOT transposed); persistent grid of min(num_sms, 4 n) CTAs.
 // With `w_packed` / `e` (FUSE): out = LeakyReLU(x_in + y + W_w . O + b) is written instead of O (see the kernel comment);
 // w_packed = the [288 rows][128] K-major 16-bit matrix of the output conv, e = bias / res1 = y / res2 = x_in / out.
 inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h16* o, int n, int num_sms, int* errflag,
@@ -641,7 +656,7 @@ inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h1
     uint64_t dq[3] = {256, FA_S, (uint64_t)n}, sq[2] = {256 * 2, (uint64_t)FA_S * 256 * 2};
     uint32_t bq[3] = {64, 128, 1};
     if (!tma.encode_h16(&m.qk, (void*)qk, 3, dq, sq, bq, nullptr)) return -1;
-    uint64_t dv[3] = {FA_S, FA_D, (uint64_t)n}, sv[2] = {(uint64_t)FA_S * 2, (uint64_t)FA_D * FA_S * 2};
+    uint64_t dv[3] = {FA_D, FA_S, (uint64_t)n}, sv[2] = {(uint64_t)FA_D * 2, (uint64_t)FA_D * FA_S * 2};
     uint32_t bv[3] = {64, 128, 1};
     if (!tma.encode_h16(&m.vt, (void*)vt, 3, dv, sv, bv, nullptr)) return -2;
     uint64_t d2[2] = {FA_D, (uint64_t)n * FA_S}, s2[1] = {(uint64_t)FA_D * 2};

@@ -319,6 +319,10 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   EpiParams eq = epi(h->QK, 256, 0, 384, 0, OUT_QKV);
   eq.out2 = h->VT;
   eq.spatial = FEAT * FEAT;
+  // g leaves the projection conv untransposed ([pix][128]) for the single-pass attention kernel (MN-major B operand of
+  // its P V MMA); the round-1 kernel and the fp32 check kernels read V^T
+  const bool v_natural = h->precision != BSR_PRECISION_FP32CHECK && !h->force_direct && !h->kn.attn_v1;
+  eq.v_natural = v_natural ? 1 : 0;
   ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq, no_extra()};
   if ((rc = run_conv(h, st, c4, n))) return rc;
   if (h->debug_keep && (idx == 0 || idx == 5)) {
@@ -329,7 +333,8 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
     char nb[3][16];
     snprintf(nb[0], 16, "qk%d", idx); snprintf(nb[1], 16, "vt%d", idx); snprintf(nb[2], 16, "attn_o%d", idx);
     debug_capture(h, st, nb[0], h->QK, 256, 0, 256, (long long)n * 1024);
-    debug_capture(h, st, nb[1], h->VT, 1024, 0, 1024, (long long)n * 128);
+    if (v_natural) debug_capture(h, st, nb[1], h->VT, 128, 0, 128, (long long)n * 1024);      // V[n][1024][128]
+    else debug_capture(h, st, nb[1], h->VT, 1024, 0, 1024, (long long)n * 128);                  // V^T[n][128][1024]
     if ((rc = run_attention(h, st, n))) return rc;
     debug_capture(h, st, nb[2], h->O, 128, 0, 128, (long long)n * 1024);
     h->launches = launches0;
@@ -378,9 +383,9 @@ int run_share(bsr_handle* h, cudaStream_t st, char* x, int ld, int C, int coff, 
   }
   if ((ld & 3) || (coff & 3)) return fail(h, BSR_EINVAL, "share layer needs 4-channel aligned stride / offset (ld %d, coff %d)", ld, coff);
   const int chunks = n / frame, ldsh = (2 * C + 3) / 4 * 4;
-  const long long t1 = (long long)chunks * FEAT * FEAT * ((C + 3) / 4), t2 = (long long)n * FEAT * FEAT * ((2 * C + 3) / 4);
-  share_reduce_kernel<T><<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>((const T*)x, ld, C, h->OFF, frame, (T*)h->SH, ldsh, t1);
-  share_out_kernel<T><<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>((const T*)h->SH, ldsh, 2 * C, h->OFF, frame, (T*)x, ld, coff, t2);
+  const int cells1 = chunks * FEAT * FEAT, cells2 = n * FEAT * FEAT;          // one warp per cell, 8 warps per block
+  share_reduce_kernel<T><<<(cells1 + 7) / 8, 256, 0, st>>>((const T*)x, ld, C, h->OFF, frame, (T*)h->SH, ldsh, cells1);
+  share_out_kernel<T><<<(cells2 + 7) / 8, 256, 0, st>>>((const T*)h->SH, ldsh, 2 * C, h->OFF, frame, (T*)x, ld, coff, cells2);
   h->launches += 2;
   return BSR_OK;
 }

@@ -90,8 +90,9 @@ struct EpiParams {
   const void* res2; int res2_ld; int res2_c;
   void* out; int out_ld; int out_coff; int out_c;
   int out_mode;
-  void* out2;        // OUT_QKV: V^T base
+  void* out2;        // OUT_QKV: base of g: V^T[n][128][spatial] (v_natural = 0) or V[pix][128] (v_natural = 1)
   int spatial;       // OUT_QKV: pixels per image (1024)
+  int v_natural;
 };
 
 template <typename T>
@@ -115,8 +116,12 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, size_t pix, int c,
     if (c < 256) {
       stf<T>((T*)e.out, pix * 256 + c, v);
     } else {
-      size_t n = pix / e.spatial, s = pix % e.spatial;
-      stf<T>((T*)e.out2, (n * 128 + (c - 256)) * e.spatial + s, v);
+      if (e.v_natural) {
+        stf<T>((T*)e.out2, pix * 128 + (c - 256), v);
+      } else {
+        size_t n = pix / e.spatial, s = pix % e.spatial;
+        stf<T>((T*)e.out2, (n * 128 + (c - 256)) * e.spatial + s, v);
+      }
     }
   }
 }

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 float* dst = (float*)e.out + pix * e.out_ld + e.out_coff + c;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) dst[i] = v[i];
-              } else if (e.out_mode == OUT_QKV && c >= 256) {
+              } else if (e.out_mode == OUT_QKV && c >= 256 && !e.v_natural) {
                 // g -> V^T[n][c-256][s]: for a fixed channel the 32 lanes write consecutive tokens
                 h16* dst = (h16*)e.out2 + ((size_t)n * 128 + (c - 256)) * e.spatial + (gy * OW + gx);
 #pragma unroll
@@ -578,7 +578,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 o1.x = pack_h16x2(v[8], v[9]); o1.y = pack_h16x2(v[10], v[11]);
                 o1.z = pack_h16x2(v[12], v[13]); o1.w = pack_h16x2(v[14], v[15]);
                 const size_t off = e.out_mode == OUT_QKV ? pix * 256 + c : pix * e.out_ld + e.out_coff + c;
-                uint4* dst = reinterpret_cast<uint4*>((h16*)e.out + off);
+                // OUT_QKV with natural V: channels >= 256 go to V[pix][c - 256] (same vector store, other base)
+                uint4* dst = (e.out_mode == OUT_QKV && c >= 256)
+                                 ? reinterpret_cast<uint4*>((h16*)e.out2 + pix * 128 + (c - 256))
+                                 : reinterpret_cast<uint4*>((h16*)e.out + off);
                 if (!(p.ablate & 1)) {
                   dst[0] = o0;
                   dst[1] = o1;

@@ -242,87 +242,87 @@ template <> __device__ __forceinline__ void st4<h16>(h16* p, const float* v) {
 }
 
 // ShareLayer, first half (model_with_TSM.py:204-222): sh[chunk][pix][0:C] = max_f warp_in(x_f), sh[chunk][pix][C:2C] =
-// mean_f warp_in(x_f), stored in the activation type with row stride ldsh (a multiple of 4).  One thread per (chunk,
-// pixel, 4 channels): the four bilinear corners of every frame are 4-channel vector loads, the frames of a chunk are
-// reduced in registers (F = 2 or 10 - too few for a cross-lane reduction to pay).  Needs ld % 4 == 0.
+// mean_f warp_in(x_f), stored in the activation type with row stride ldsh (a multiple of 4).  One WARP per (chunk,
+// pixel): the bilinear taps are warp-uniform, the lanes stride over 4-channel vectors (8-byte / 16-byte accesses, 256 /
+// 512 contiguous bytes per warp instruction); the frames of a chunk are reduced in registers (F = 2 or 10 - the
+// reduction axis is the outer loop of every lane, so no cross-lane step is needed).  Needs ld % 4 == 0.
 template <typename T>
 __global__ void share_reduce_kernel(const T* __restrict__ x, int ld, int C, const float* __restrict__ off, int frame,
-                                    T* __restrict__ sh, int ldsh, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int Cv = (C + 3) >> 2;
-  const int cv = (int)(idx % Cv);
-  const long long cell = idx / Cv;
-  const int pix = (int)(cell % (FEAT * FEAT));
+                                    T* __restrict__ sh, int ldsh, int n_cells) {
+  const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= n_cells) return;
+  const int pix = cell % (FEAT * FEAT);
   const size_t chunk = (size_t)(cell / (FEAT * FEAT));
-  const int i = pix / FEAT, j = pix % FEAT, c0 = 4 * cv;
-  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int f = 0; f < frame; ++f) {
-    const size_t n = chunk * frame + f;
-    const float2 o = *reinterpret_cast<const float2*>(off + (n * FEAT * FEAT + pix) * 4);
-    const WarpTap w = warp_tap(o.x, o.y, i, j);
-    const T* b = x + n * FEAT * FEAT * ld + c0;
-    float lt[4], rt[4], lb[4], rb[4];
-    ld4<T>(b + (size_t)w.lt * ld, lt);
-    ld4<T>(b + (size_t)w.rt * ld, rt);
-    ld4<T>(b + (size_t)w.lb * ld, lb);
-    ld4<T>(b + (size_t)w.rb * ld, rb);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float v = warp_mix(lt[k], rt[k], lb[k], rb[k], w.o0, w.o1);
-      mx[k] = fmaxf(mx[k], v);
-      sum[k] += v;
-    }
-  }
+  const int i = pix / FEAT, j = pix % FEAT, Cv = (C + 3) >> 2;
   T* d = sh + (chunk * FEAT * FEAT + pix) * ldsh;
-  const float invf = 1.f / (float)frame;
-  if (c0 + 4 <= C) {
-    st4<T>(d + c0, mx);
-    if ((C & 3) == 0) {
-      float mean[4] = {sum[0] / (float)frame, sum[1] / (float)frame, sum[2] / (float)frame, sum[3] / (float)frame};
-      st4<T>(d + C + c0, mean);
-    } else {
+  const float fr = (float)frame;
+  for (int cv = lane; cv < Cv; cv += 32) {
+    const int c0 = 4 * cv;
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int f = 0; f < frame; ++f) {
+      const size_t n = chunk * frame + f;
+      const float2 o = *reinterpret_cast<const float2*>(off + (n * FEAT * FEAT + pix) * 4);       // warp-uniform
+      const WarpTap w = warp_tap(o.x, o.y, i, j);
+      const T* b = x + n * FEAT * FEAT * ld + c0;
+      float lt[4], rt[4], lb[4], rb[4];
+      ld4<T>(b + (size_t)w.lt * ld, lt);
+      ld4<T>(b + (size_t)w.rt * ld, rt);
+      ld4<T>(b + (size_t)w.lb * ld, lb);
+      ld4<T>(b + (size_t)w.rb * ld, rb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) stf<T>(d, C + c0 + k, sum[k] / (float)frame);
+      for (int k = 0; k < 4; ++k) {
+        const float v = warp_mix(lt[k], rt[k], lb[k], rb[k], w.o0, w.o1);
+        mx[k] = fmaxf(mx[k], v);
+        sum[k] += v;
+      }
     }
-  } else {
-    for (int k = 0; c0 + k < C; ++k) {
-      stf<T>(d, c0 + k, mx[k]);
-      stf<T>(d, C + c0 + k, sum[k] / (float)frame);
+    if (c0 + 4 <= C) {
+      st4<T>(d + c0, mx);
+      if ((C & 3) == 0) {
+        const float mean[4] = {sum[0] / fr, sum[1] / fr, sum[2] / fr, sum[3] / fr};
+        st4<T>(d + C + c0, mean);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stf<T>(d, C + c0 + k, sum[k] / fr);
+      }
+    } else {
+      for (int k = 0; c0 + k < C; ++k) {
+        stf<T>(d, c0 + k, mx[k]);
+        stf<T>(d, C + c0 + k, sum[k] / fr);
+      }
     }
   }
-  (void)invf;
 }
 
 // ShareLayer, second half (model_with_TSM.py:223-226): x[n][pix][coff + c] = warp_out(sh[chunk])[pix][c], c < 2C.
-// One thread per (frame, pixel, 4 channels); coff % 4 == 0, ld % 4 == 0, ldsh % 4 == 0.
+// One warp per (frame, pixel), lanes over 4-channel vectors; coff % 4 == 0, ld % 4 == 0, ldsh % 4 == 0.
 template <typename T>
 __global__ void share_out_kernel(const T* __restrict__ sh, int ldsh, int C2, const float* __restrict__ off, int frame,
-                                 T* __restrict__ x, int ld, int coff, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int Qv = (C2 + 3) >> 2;
-  const int qv = (int)(idx % Qv);
-  const long long cell = idx / Qv;
-  const int pix = (int)(cell % (FEAT * FEAT));
+                                 T* __restrict__ x, int ld, int coff, int n_cells) {
+  const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= n_cells) return;
+  const int pix = cell % (FEAT * FEAT);
   const size_t n = (size_t)(cell / (FEAT * FEAT));
   const size_t chunk = n / frame;
-  const int i = pix / FEAT, j = pix % FEAT, c0 = 4 * qv;
+  const int i = pix / FEAT, j = pix % FEAT, Qv = (C2 + 3) >> 2;
   const float2 o = *reinterpret_cast<const float2*>(off + (n * FEAT * FEAT + pix) * 4 + 2);
   const WarpTap w = warp_tap(o.x, o.y, i, j);
-  const T* b = sh + chunk * FEAT * FEAT * ldsh + c0;
-  float lt[4], rt[4], lb[4], rb[4], v[4];
-  ld4<T>(b + (size_t)w.lt * ldsh, lt);
-  ld4<T>(b + (size_t)w.rt * ldsh, rt);
-  ld4<T>(b + (size_t)w.lb * ldsh, lb);
-  ld4<T>(b + (size_t)w.rb * ldsh, rb);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = warp_mix(lt[k], rt[k], lb[k], rb[k], w.o0, w.o1);
+  const T* b = sh + chunk * FEAT * FEAT * ldsh;
   T* d = x + (n * FEAT * FEAT + pix) * ld + coff;
-  if (c0 + 4 <= C2) {
-    st4<T>(d + c0, v);
-  } else {
-    for (int k = 0; c0 + k < C2; ++k) stf<T>(d, c0 + k, v[k]);
+  for (int qv = lane; qv < Qv; qv += 32) {
+    const int c0 = 4 * qv;
+    float lt[4], rt[4], lb[4], rb[4], v[4];
+    ld4<T>(b + (size_t)w.lt * ldsh + c0, lt);
+    ld4<T>(b + (size_t)w.rt * ldsh + c0, rt);
+    ld4<T>(b + (size_t)w.lb * ldsh + c0, lb);
+    ld4<T>(b + (size_t)w.rb * ldsh + c0, rb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = warp_mix(lt[k], rt[k], lb[k], rb[k], w.o0, w.o1);
+    if (c0 + 4 <= C2) {
+      st4<T>(d + c0, v);
+    } else {
+      for (int k = 0; c0 + k < C2; ++k) stf<T>(d, c0 + k, v[k]);
+    }
   }
 }
 

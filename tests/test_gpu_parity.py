@@ -507,7 +507,7 @@ def test_attention_kernel_alone_matches_float64_softmax(G, gain):
     gen, _ = run_device(G, "gsc", "tc16", w, d, 1)
     for blk in (0, 5):
         qk = gen.debug_read("qk%d" % blk).reshape(2, 1024, 256)
-        vt = gen.debug_read("vt%d" % blk).reshape(2, 128, 1024)
+        vt = gen.debug_read("vt%d" % blk).reshape(2, 1024, 128).transpose(0, 2, 1)      # the TC16 path keeps g as V[n][1024][128]
         o = gen.debug_read("attn_o%d" % blk).reshape(2, 1024, 128)
         ref, spread = _attention_ref(qk, vt)
         scale = np.abs(ref).max()
