@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <type_traits>
 #include <vector>
 
@@ -43,6 +44,17 @@ struct Layer {
 
 struct DebugBuf { float* dev = nullptr; size_t n = 0; };
 
+// One captured micro-batch: the whole launch sequence of forward_mb for a fixed set of pointers / sizes.
+struct GraphKey {
+  const void *img, *uv, *reg, *gs, *rgb, *m22, *dif;
+  int m, frame, share, in_small;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(img, uv, reg, gs, rgb, m22, dif, m, frame, share, in_small) <
+           std::tie(o.img, o.uv, o.reg, o.gs, o.rgb, o.m22, o.dif, o.m, o.frame, o.share, o.in_small);
+  }
+};
+struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0, seen = 0; PlanCounters pc; };
+
 }  // namespace
 
 struct bsr_handle {
@@ -72,6 +84,8 @@ struct bsr_handle {
   bool have_done = false;
   Knobs kn;
   PlanCounters pc;
+  std::map<GraphKey, GraphEntry> graphs;   // captured micro-batches (replayed when the same buffers come back)
+  cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's stream may be the legacy default stream)
   int launches = 0;
   std::map<std::string, DebugBuf> dbg;
   // profiling
@@ -577,6 +591,12 @@ int finish_forward(bsr_handle* h, cudaStream_t st) {
   return BSR_OK;
 }
 
+void clear_graphs(bsr_handle* h) {
+  for (auto& kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+
 int forward_common(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
                    float* gs, float* rgb, float* mask22, float* dif, cudaStream_t st) {
   if (!h) return BSR_EINVAL;
@@ -603,12 +623,52 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
     int rc;
     const float* uvp = uv + aux_px * 3;
     const float* regp = reg ? reg + aux_px * 6 : nullptr;
-    if (h->precision == BSR_PRECISION_FP32CHECK)
-      rc = forward_mb<float>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
-                             rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
-    else
-      rc = forward_mb<h16>(h, st, img + o3, uvp, regp, m, frame, share, gs ? gs + o1 : nullptr,
-                            rgb ? rgb + o3 : nullptr, mask22 ? mask22 + o3 : nullptr, dif ? dif + o1 : nullptr);
+    float *gsp = gs ? gs + o1 : nullptr, *rgbp = rgb ? rgb + o3 : nullptr, *m22p = mask22 ? mask22 + o3 : nullptr,
+          *difp = dif ? dif + o1 : nullptr;
+    auto run = [&](cudaStream_t s) {
+      return h->precision == BSR_PRECISION_FP32CHECK
+                 ? forward_mb<float>(h, s, img + o3, uvp, regp, m, frame, share, gsp, rgbp, m22p, difp)
+                 : forward_mb<h16>(h, s, img + o3, uvp, regp, m, frame, share, gsp, rgbp, m22p, difp);
+    };
+    // CUDA graphs: a micro-batch whose buffers were seen before is captured once (on a private stream) and replayed
+    // afterwards - one launch instead of ~50 (debug / profiling handles always launch kernel by kernel)
+    if (!h->kn.no_graph && !h->debug_keep && !h->profile) {
+      GraphKey key{img + o3, uvp, regp, gsp, rgbp, m22p, difp, m, frame, share, h->in_small ? 1 : 0};
+      if (h->graphs.size() > 64 && !h->graphs.count(key)) clear_graphs(h);
+      GraphEntry& ge = h->graphs[key];
+      if (!ge.exec && ++ge.seen >= 2) {
+        const int l0 = h->launches;
+        const PlanCounters p0 = h->pc;
+        cudaGraph_t g = nullptr;
+        bool ok = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          const int crc = run(h->cap_stream);
+          ok = cudaStreamEndCapture(h->cap_stream, &g) == cudaSuccess && crc == BSR_OK && g != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&ge.exec, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        if (ok) {
+          ge.launches = h->launches - l0;
+          ge.pc.resident = h->pc.resident - p0.resident; ge.pc.pinned = h->pc.pinned - p0.pinned;
+          ge.pc.staged = h->pc.staged - p0.staged; ge.pc.attn_fused = h->pc.attn_fused - p0.attn_fused;
+        } else {                       // capture unsupported here: fall back to plain launches for good
+          cudaGetLastError();
+          ge.exec = nullptr;
+          h->kn.no_graph = 1;
+        }
+        h->launches = l0;
+        h->pc = p0;
+      }
+      if (ge.exec) {
+        CK(h, cudaGraphLaunch(ge.exec, st));
+        h->launches += ge.launches;
+        h->pc.resident += ge.pc.resident; h->pc.pinned += ge.pc.pinned; h->pc.staged += ge.pc.staged;
+        h->pc.attn_fused += ge.pc.attn_fused;
+        h->pc.graph_replays++;
+        continue;
+      }
+    }
+    rc = run(st);
     if (rc) return rc;
   }
   return finish_forward(h, st);
@@ -899,6 +959,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   size_t off = 0;
   for (auto& r : reqs) { *r.p = (char*)h->arena + off; off += align256(r.bytes); }
   cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
@@ -953,6 +1014,8 @@ int bsr_destroy(bsr_handle* h) {
   if (h->pp_buf) cudaFree(h->pp_buf);
   if (h->pp_planes) cudaFree(h->pp_planes);
   if (h->errflag_host) cudaFreeHost(h->errflag_host);
+  clear_graphs(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_in) cudaStreamDestroy(h->s_in);
@@ -971,6 +1034,8 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
   CK(h, cudaSetDevice(h->device));
   const char* b = (const char*)blob;
   if (nbytes < 16 || memcmp(b, "BSRW0001", 8) != 0) return fail(h, BSR_EINVAL, "bad weight blob magic");
+  CK(h, cudaDeviceSynchronize());
+  clear_graphs(h);                      // captured launches hold pointers to the weights being replaced
   int32_t variant, n_layers;
   memcpy(&variant, b + 8, 4);
   memcpy(&n_layers, b + 12, 4);

@@ -576,6 +576,14 @@ def test_device_error_flag_and_ordering_across_streams(G):
         assert torch.equal(a, ref) and torch.equal(c, ref)
         assert np.array_equal(b[::-1], ref.cpu().numpy())
     gen.check()
+    # repeated calls on the same buffers are replayed from a captured CUDA graph (non-debug handles) - same bits
+    replays = 0
+    for _ in range(8):
+        c = gen(img, uv, None, want=("con_rgb",))[1]
+        replays += gen.plan_counters()["graph_replays"]
+        assert torch.equal(c, ref)
+    assert replays >= 2, replays
+    assert gen.launch_count() == 49                                       # replays report the launches they stand for
     # a CPU `reg` with CUDA inputs is rejected instead of being handed to the kernel as a device pointer
     t = G.Generator("tsm", "tc16", device=0, micro_batch=2, seed=1)
     with pytest.raises(G.BsrError):

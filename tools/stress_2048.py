@@ -26,7 +26,7 @@ NAMES = ["x1", "x2", "x3", "x_in0", "res0", "res1", "res2", "up1", "up2", "up3",
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 MB = 128
 w = random_weights("gsc", 1234)
-bf = Generator("gsc", "bf16", device=0, micro_batch=MB, weights=w)
+bf = Generator("gsc", "tc16", device=0, micro_batch=MB, weights=w)
 fp = Generator("gsc", "fp32check", device=0, micro_batch=MB, weights=w)
 acc = dict(n=0, max_rgb=0.0, sum_rgb=0.0, se_rgb=0.0, max_dif=0.0, sum_dif=0.0, se_dif=0.0, within=0, px=0, flips=0,
            cells=0, max_rgb_same_mask=0.0)
