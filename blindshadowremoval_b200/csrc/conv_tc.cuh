@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == TC_EPI_WARPS) {
     // ================= TMA producer (whole warp converged; one elected lane issues) =================
     {
-      uint32_t it = 0;
+      uint32_t it = 0, s = 0, ph = 0;          // stage / phase kept incrementally (no runtime division on the issue path)
       bool ok = true;
       const bool leader = elect_one();
       const int in_stride = p.in_stride, in_stride_x = p.in_stride_x, pad_l = p.pad_l, pad_t = p.pad_t, b_resident = p.b_resident;
@@ -288,7 +288,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int xbase = gx0 * in_stride_x - pad_l, ybase = gy0 * in_stride - pad_t, brow_base = ntile * bn;
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
-          const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
           const long long tw = BSR_CLK();
           ok = mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.errflag, 1);
           const long long tp0 = BSR_CLK();
@@ -296,7 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (!ok) break;
           const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_sub * a_bytes;
           if (leader) {
-            const uint32_t rowmode = sp.n_a == 3, na = rowmode ? 1u : (uint32_t)sp.n_a, nsub = sp.n_a >= 2 ? 2u : 1u;
+            const uint32_t rowmode = sp.n_a == 3, xmode = sp.n_a == 4, na = rowmode ? 1u : (xmode ? 2u : (uint32_t)sp.n_a),
+                           nsub = sp.n_a >= 2 ? 2u : 1u;
             const uint32_t bbytes = b_resident ? 0u : na * (uint32_t)sp.b_rows * 128u;
             if (ablate & 4) {
               mbar_expect_tx(bar_full + 8 * s, bbytes);
@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const int ax = xbase + sp.a_x0 * in_stride_x + sp.dx, ay = ybase + sp.dy;
               tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, ax, ay, n);
               if (nsub == 2)
-                tma_load_4d(dstA + a_bytes, &tmA, bar_full + 8 * s, sp.a_c0 + (rowmode ? 0 : TC_BK), ax, ay + (int)rowmode, n);
+                tma_load_4d(dstA + a_bytes, &tmA, bar_full + 8 * s, sp.a_c0 + ((rowmode || xmode) ? 0 : TC_BK), ax + (int)xmode,
+                            ay + (int)rowmode, n);
             }
             if (!b_resident) {
               const int row0 = sp.b_row + brow_base;
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           __syncwarp();
           t_tma += BSR_CLK() - tp0;
+          if (++s == n_stages) { s = 0; ph ^= 1u; }
         }
       }
       if (tm) { p.timers[15] = t_tma; p.timers[0] = BSR_CLK() - t_start; p.timers[1] = t_wait; p.timers[2] = t_dep; p.timers[3] = it; }
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == TC_EPI_WARPS + 1) {
     // ================= MMA issuer (whole warp converged; one elected lane issues) =================
     {
-      uint32_t it = 0, tcount = 0;
+      uint32_t it = 0, tcount = 0, s = 0, ph = 0, as = 0, aph = 0;
       bool ok = true;
       const bool leader = elect_one();
       const int b_resident = p.b_resident, b_total_rows = p.b_res_rows, bn = p.bn, ablate = p.ablate;
@@ -339,7 +341,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const long long t_res = BSR_CLK() - t_start;
       const uint32_t idesc_m = umma_idesc_h16(TC_BM, 0);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
-        const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
         const long long tw0 = BSR_CLK();
         ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4, true);
         t_wtempty += BSR_CLK() - tw0;
@@ -349,7 +350,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int brow_base = p.b_pinned ? 0 : (tile % n_tiles) * bn;
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
-          const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
           const long long tw1 = BSR_CLK();
           ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2, true);
           const long long tc0 = BSR_CLK();
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                          : sA + a_sub * a_bytes;
           const uint32_t a_lo = umma_desc_lo(sA), b_lo0 = umma_desc_lo(sB);
           const int nm = (ablate & 2) ? 0 : sp.n_mma;
-          const uint32_t na = (uint32_t)sp.n_a;
+          const uint32_t na = sp.n_a == 4 ? 2u : (uint32_t)sp.n_a;          // 4 = two K blocks whose A tiles are x-neighbours
           if (leader) {
             for (int m = 0; m < nm; ++m) {
               const TcMma mm = sp.mma[m];
@@ -389,9 +389,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (leader) umma_commit(bar_empty + 8 * s);
           __syncwarp();
           t_commit += BSR_CLK() - tc2;
+          if (++s == n_stages) { s = 0; ph ^= 1u; }
         }
         if (leader) umma_commit(bar_tfull + 8 * as);
         __syncwarp();
+        if (++as == acc_stages) { as = 0; aph ^= 1u; }
       }
       if (tm) { p.timers[12] = t_fence; p.timers[13] = t_issue; p.timers[14] = t_commit; }
       if (tm) { p.timers[4] = BSR_CLK() - t_start; p.timers[5] = t_wfull; p.timers[6] = t_wtempty; p.timers[7] = t_res; p.timers[8] = tcount; }
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
       const int ntile = tile % n_tiles, mt = tile / n_tiles;
       const int n = mt / tiles_per_img, tr = mt % tiles_per_img;
-      const uint32_t as = tcount % acc_stages, aph = (tcount / acc_stages) & 1u;
+      const uint32_t as = acc_stages == 2 ? (tcount & 1u) : 0u, aph = (acc_stages == 2 ? (tcount >> 1) : tcount) & 1u;
       const uint32_t acc = tmem_base + as * (uint32_t)bn + lane_addr;
       if (EPI == EPI_GENERIC && !RES && p.st_chunk) {
         // ---- staged epilogue: accumulators -> h16 -> 64B-swizzled shared memory -> TMA store.  Per-thread-row global
@@ -675,11 +677,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int half = cg & 1, slot = cg >> 1;
         const int y0 = tr * rows_per_tile;
         const int xg = half * 128 + r;
-        float* rowbuf = epi_work + slot * (258 * CLR_RS);   // [256 + 2][48 (+4 pad)], one zero column either side
-        if ((ethread & 255) < 96) {
-          const int i = ethread & 255;
-          rowbuf[(i < 48 ? 0 : 257 * CLR_RS) + (i % 48)] = 0.f;
-        }
+        // Horizontal taps: out[x] = Y[x-1][kw=0] + Y[x][kw=1] + Y[x+1][kw=2].  A thread owns pixel x, so the neighbours'
+        // groups come by warp shuffle; only the two edge lanes of a warp go through shared memory (2 x 16 floats per
+        // warp instead of 48 written + 48 read per THREAD: the row-exchange buffer used to compete with the UMMA operand
+        // reads for the shared-memory pipe and slowed the MMAs to 2.4x their floor, profiles/r2_role_timers).
+        // edge[slot][tile parity][warp in row 0..7][side][16]; the parity makes one barrier per tile sufficient.
+        const int wr = half * 4 + q;
+        float* edge = epi_work + ((slot * 2 + (int)(tcount & 1u)) * 8) * 32;
         const float* gsn = x.gs_f32 + (size_t)n * OH * OW;
         // issue the 9 gs taps and the input pixel first: their latency overlaps the accumulator wait
         float gv[9];
@@ -694,33 +698,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
         if (!ok) break;
         tc_fence_after();
+        float y0v[16], y1v[16], y2v[16];
         {
-          float* dst = rowbuf + (xg + 1) * CLR_RS;
-#pragma unroll
-          for (int c = 0; c < 48; c += 16) {
-            float v[16];
-            tmem_ld16(acc + (uint32_t)((half * rows_per_tile + slot) * CLR_NB + c), v);
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
+          const uint32_t ta = acc + (uint32_t)((half * rows_per_tile + slot) * CLR_NB);
+          tmem_ld16(ta, y0v);
+          tmem_ld16(ta + 16u, y1v);
+          tmem_ld16(ta + 32u, y2v);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        if (lane == 31) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(edge + wr * 32 + i) = make_float4(y0v[i], y0v[i + 1], y0v[i + 2], y0v[i + 3]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(edge + wr * 32 + 16 + i) = make_float4(y2v[i], y2v[i + 1], y2v[i + 2], y2v[i + 3]);
+        }
         epi_bar_slot(slot);
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = bias_s[i];
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float* src = rowbuf + (xg + kw) * CLR_RS + kw * 16;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(src + i);
-            v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-          }
+        for (int i = 0; i < 16; ++i) {
+          float l = __shfl_up_sync(0xffffffffu, y0v[i], 1);            // Y[x-1][kw=0]
+          float rg = __shfl_down_sync(0xffffffffu, y2v[i], 1);         // Y[x+1][kw=2]
+          if (lane == 0) l = wr > 0 ? edge[(wr - 1) * 32 + i] : 0.f;
+          if (lane == 31) rg = wr < 7 ? edge[(wr + 1) * 32 + 16 + i] : 0.f;
+          v[i] = ((bias_s[i] + l) + y1v[i]) + rg;
         }
-        epi_bar_slot(slot);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
 #pragma unroll
@@ -1016,23 +1021,30 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
     const size_t K = 6 * 64, rows = t.bn;
     std::vector<uint16_t> host(rows * K, 0);
-    int ns = 0;
+    // one step per filter row: its two K blocks (pixel pair ox and the first half of pair ox + 1) are two A sub-tiles that
+    // are x-neighbours (n_a = 4): 3 steps of 8 MMAs per tile instead of 6 of 4 - the per-step control cost of the issuer
+    // (~400 cycles, profiles/r2_role_timers) is paid half as often
+    const bool pair_x = !getenv("BSR_NO_KPAIR");
+    int ns = 0, kb = 0;
     for (int a = 0; a < 3; ++a)
-      for (int half = 0; half < 2; ++half) {
-        TcStep& sp = t.steps[ns];
-        sp.dy = (int8_t)a; sp.dx = (int8_t)half; sp.a_c0 = 0; sp.b_rows = (int16_t)t.bn; sp.b_k = ns * 64; sp.b_row = 0; sp.n_a = 1;
-        sp.n_mma = 1; sp.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
+      for (int half = 0; half < 2; ++half, ++kb) {
         for (int o = 0; o < cout; ++o)
           for (int c = 0; c < 32; ++c) {
             if (half == 0) {
-              host[(size_t)o * K + ns * 64 + c] = f32_to_h16_bits(W(a * 3 + 0, c, o));
-              host[(size_t)o * K + ns * 64 + 32 + c] = f32_to_h16_bits(W(a * 3 + 1, c, o));
+              host[(size_t)o * K + kb * 64 + c] = f32_to_h16_bits(W(a * 3 + 0, c, o));
+              host[(size_t)o * K + kb * 64 + 32 + c] = f32_to_h16_bits(W(a * 3 + 1, c, o));
             } else {
-              host[(size_t)o * K + ns * 64 + c] = f32_to_h16_bits(W(a * 3 + 2, c, o));
+              host[(size_t)o * K + kb * 64 + c] = f32_to_h16_bits(W(a * 3 + 2, c, o));
             }
           }
+        if (pair_x && half == 1) continue;          // covered by the paired step of half 0
+        TcStep& sp = t.steps[ns];
+        sp.dy = (int8_t)a; sp.dx = (int8_t)half; sp.a_c0 = 0; sp.b_rows = (int16_t)t.bn; sp.b_k = kb * 64; sp.b_row = 0;
+        sp.n_a = (int8_t)(pair_x ? 4 : 1);
+        sp.n_mma = 1; sp.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
         ++ns;
       }
+    if (pair_x) t.a_sub = 2;
     t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
   }
@@ -1176,7 +1188,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.b_res_rows = pinned ? t.bn : t.b_total_rows;
   // bias staging: 512 floats unless the layer provably reads fewer (frees shared memory for the store staging)
   const int bias_floats = (p.epi_mode == EPI_GENERIC && p.n_groups > 1 && p.group_cols <= 128) ? 128 : 512;
-  const int epi_bytes = bias_floats * 4 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 258 * CLR_RS * 4 : 0));
+  const int epi_bytes = bias_floats * 4 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 2 * 8 * 32 * 4 : 0));
   p.epi_bytes = (epi_bytes + 127) / 128 * 128;
   p.steps_bytes = (int)((t.n_steps * sizeof(TcStep) + 127) / 128 * 128);
   p.b_res_kblocks = t.b_res_kblocks;
