@@ -51,9 +51,7 @@ constexpr int TC_THREADS = 576;
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MAX_STEPS = 64;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
-// row-exchange buffers: pixel stride in floats, padded so that 8 consecutive lanes' 16-byte accesses hit 8
-// different 4-bank groups (stride = 20 mod 32 words): 48 -> 52 (colour tail), 16 -> 20 (heads)
-constexpr int CLR_RS = 52, HEADS_RS = 20;
+// (the fp32 row-exchange buffers of round 1 are gone: horizontal taps are summed by warp shuffles)
 constexpr int CLR_NB = 64;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns, padded to 64 (TMEM alignment)
 
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4, TC_PAIRX = 5 };
@@ -618,14 +616,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int half = cg & 1, slot = cg >> 1;
         const int y0 = tr * rows_per_tile;
         const int xg = half * 128 + r;
-        float* rowbuf = epi_work + slot * (262 * HEADS_RS);         // [256 + 6][16 (+4 pad)], 3 zero columns either side
-        const int st = ethread - slot * 256 - (ethread >= 256 && slot == 0 ? 0 : 0);
-        if ((ethread & 255) < 96) {
-          const int i = ethread & 255;                              // zero the two halos (3 x 16 each) of my slot's buffer
-          const int px = i < 48 ? i / 16 : 259 + (i - 48) / 16;
-          rowbuf[px * HEADS_RS + (i & 15)] = 0.f;
-        }
-        (void)st;
+        // Horizontal taps by warp shuffle (see EPI_CLR): pixel x needs Y[x + kw - 3][kw]; only the three edge lanes on
+        // either side of a warp go through shared memory.  edge[slot][row parity][warp in row][side][lane 0..2][kw 0..2][o]:
+        // side 0 = lanes 29..31, groups kw = 0..2 (for the next warp), side 1 = lanes 0..2, groups kw = 4..6 (previous warp).
+        const int wr = half * 4 + q;
+        float* edge_slot = epi_work + slot * (2 * 8 * 40);
         const float b2 = bias_s[0], b3 = bias_s[1];
         const size_t p0 = ((size_t)n * OH + y0 + slot) * OW + xg;
         float i0 = x.img[3 * p0], i1 = x.img[3 * p0 + 1], i2 = x.img[3 * p0 + 2];     // prefetched one row ahead
@@ -646,18 +641,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);        // accumulators drained: MMA may start the next tile
           }
+          float* edge = edge_slot + (((rr - slot) >> 1) & 1) * (8 * 40);       // double-buffered by row parity: one barrier per row
+          if (lane >= 29) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(rowbuf + (xg + 3) * HEADS_RS + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 6; ++i) edge[wr * 40 + (lane - 29) * 6 + i] = v[i];
+          }
+          if (lane < 3) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) edge[wr * 40 + 18 + lane * 6 + i] = v[8 + i];
+          }
           epi_bar_slot(slot);
           float c2 = b2, c3 = b3;
 #pragma unroll
           for (int kw = 0; kw < 7; ++kw) {
-            const float2 t = *reinterpret_cast<const float2*>(rowbuf + (xg + kw) * HEADS_RS + kw * 2);
-            c2 += t.x;
-            c3 += t.y;
+            const int src = lane + kw - 3;
+            float t2 = __shfl_sync(0xffffffffu, v[2 * kw], src & 31), t3 = __shfl_sync(0xffffffffu, v[2 * kw + 1], src & 31);
+            if (kw < 3 && src < 0) {                                  // previous warp's lane 32 + src = 29 + (src + 3)
+              const float* e2 = edge + (wr - 1) * 40 + (src + 3) * 6 + 2 * kw;
+              t2 = wr > 0 ? e2[0] : 0.f;
+              t3 = wr > 0 ? e2[1] : 0.f;
+            }
+            if (kw > 3 && src > 31) {                                 // next warp's lane src - 32
+              const float* e2 = edge + (wr + 1) * 40 + 18 + (src - 32) * 6 + 2 * (kw - 4);
+              t2 = wr < 7 ? e2[0] : 0.f;
+              t3 = wr < 7 ? e2[1] : 0.f;
+            }
+            c2 += t2;
+            c3 += t3;
           }
-          epi_bar_slot(slot);                                       // row buffer free for the next row
           const float mask = tanhf(c2);
           const float gs = g * (1.f + mask) + c3;
           x.difgs[pidx] = gs - g;
@@ -701,9 +712,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         float y0v[16], y1v[16], y2v[16];
         {
           const uint32_t ta = acc + (uint32_t)((half * rows_per_tile + slot) * CLR_NB);
-          tmem_ld16(ta, y0v);
-          tmem_ld16(ta + 16u, y1v);
-          tmem_ld16(ta + 32u, y2v);
+          tmem_ld16_nowait(ta, y0v);
+          tmem_ld16_nowait(ta + 16u, y1v);
+          tmem_ld16_nowait(ta + 32u, y2v);
+          tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
@@ -1188,7 +1200,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.b_res_rows = pinned ? t.bn : t.b_total_rows;
   // bias staging: 512 floats unless the layer provably reads fewer (frees shared memory for the store staging)
   const int bias_floats = (p.epi_mode == EPI_GENERIC && p.n_groups > 1 && p.group_cols <= 128) ? 128 : 512;
-  const int epi_bytes = bias_floats * 4 + (p.epi_mode == EPI_HEADS ? 2 * 262 * HEADS_RS * 4 : (p.epi_mode == EPI_CLR ? 2 * 2 * 8 * 32 * 4 : 0));
+  const int epi_bytes = bias_floats * 4 + (p.epi_mode == EPI_HEADS ? 2 * 2 * 8 * 40 * 4 : (p.epi_mode == EPI_CLR ? 2 * 2 * 8 * 32 * 4 : 0));
   p.epi_bytes = (epi_bytes + 127) / 128 * 128;
   p.steps_bytes = (int)((t.n_steps * sizeof(TcStep) + 127) / 128 * 128);
   p.b_res_kblocks = t.b_res_kblocks;
