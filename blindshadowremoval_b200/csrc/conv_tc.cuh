@@ -57,7 +57,8 @@ constexpr int CLR_NB = 64;         // clr_conv1 accumulator group: 3 kw x 16 cou
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4, TC_PAIRX = 5 };
 enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
 
-struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overwrite (first tap), bit 1 = A sub-tile
+struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overwrite (first tap), bit 1 = A sub-tile,
+                                                         // bit 2 = A view starts one pixel row (128 B) into the tile (halo tiles)
 struct TcStep {
   int8_t dy, dx;           // A tile shift in input pixels
   int8_t n_mma;
@@ -102,6 +103,11 @@ struct TcWeights {
   int can_pin = 0;        // n_tiles > 1: ONE n-tile's rows fit in shared memory -> a CTA may keep "its" n-tile resident
   TcStep steps[TC_MAX_STEPS];
   TcStep* steps_dev = nullptr;
+  // halo variant of the fused transposed conv (tiles that are one image row of 128 pixels): the x-shifted A operands are
+  // views of ONE 129-pixel tile, so a tile needs 2 TMA row loads instead of 4 (see pack_tc_weights)
+  int n_steps_halo = 0;
+  TcStep steps_halo[4];
+  TcStep* steps_halo_dev = nullptr;
   h16* dev = nullptr;
   ClrWeights* clr = nullptr;   // EPI_CLR: host copy of the colour-tail weights (kernel parameter)
   CUtensorMap map;
@@ -109,6 +115,8 @@ struct TcWeights {
     if (dev) cudaFree(dev);
     if (clr) delete clr;
     if (steps_dev) cudaFree(steps_dev);
+    if (steps_halo_dev) cudaFree(steps_halo_dev);
+    steps_halo_dev = nullptr;
     dev = nullptr;
     clr = nullptr;
     steps_dev = nullptr;
@@ -156,6 +164,9 @@ struct ConvTcParams {
                               // iteration (an iteration = 64 columns = two 32-channel SWIZZLE_64B boxes in smem)
   int st_bufs;                // staging buffers: 2 = double-buffered, 1 = single (one more barrier per iteration)
   int steps_bytes, epi_bytes; // shared-memory bytes of the step program / epilogue scratch (multiples of 128)
+  int a_tile_bytes;           // bytes between the A sub-tiles of a stage: 16 KB, or 17 KB for 129-pixel halo tiles
+  int a_box_bytes;            // bytes one A box delivers (expect_tx): 128 or 129 pixel rows of 128 B
+  uint32_t halo_desc_hi;      // descriptor high word of the one-row-in A views (matrix base offset 1)
   int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
   long long* timers;          // [16] per launch (CTA 0): role wait / total cycle counters when ablate & 8
   int* errflag;
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmO) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = TC_BM * 128;
+  const uint32_t a_bytes = (uint32_t)p.a_tile_bytes;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
   const uint32_t sBres = smem_base + (uint32_t)p.n_stages * stage_bytes;            // resident weights (optional)
   const uint32_t bars = sBres + (p.b_resident ? (uint32_t)(p.b_res_kblocks * p.b_res_rows) * 128u : 0u);
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (ablate & 4) {
               mbar_expect_tx(bar_full + 8 * s, bbytes);
             } else {
-              mbar_expect_tx(bar_full + 8 * s, nsub * a_bytes + bbytes);
+              mbar_expect_tx(bar_full + 8 * s, nsub * (uint32_t)p.a_box_bytes + bbytes);
               const int ax = xbase + sp.a_x0 * in_stride_x + sp.dx, ay = ybase + sp.dy;
               tma_load_4d(dstA, &tmA, bar_full + 8 * s, sp.a_c0, ax, ay, n);
               if (nsub == 2)
@@ -368,17 +379,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t b_lo = b_lo0 + (uint32_t)mm.brow * 8u;          // 128-byte rows, address >> 4
               const uint32_t idesc = idesc_m | ((uint32_t)(mm.n >> 3) << 17);
               const uint32_t d = acc + (uint32_t)mm.col;
-              const uint32_t a0 = a_lo + ((mm.first & 2) ? (a_bytes >> 4) : 0u);     // row mode: second input row
-              umma_h16_lo(d, a0, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
-              umma_h16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
-              umma_h16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
-              umma_h16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
+              // halo view: the operand starts one 128-byte pixel row into the tile (base offset 1 in the descriptor)
+              const uint32_t voff = (mm.first & 4) ? 8u : 0u, a_hi = (mm.first & 4) ? p.halo_desc_hi : kUmmaDescHi;
+              const uint32_t a0 = a_lo + ((mm.first & 2) ? (a_bytes >> 4) : 0u) + voff;     // row mode: second input row
+              umma_h16_lo2(d, a0, a_hi, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
+              umma_h16_lo2(d, a0 + 2, a_hi, b_lo + 2, idesc, 1u);
+              umma_h16_lo2(d, a0 + 4, a_hi, b_lo + 4, idesc, 1u);
+              umma_h16_lo2(d, a0 + 6, a_hi, b_lo + 6, idesc, 1u);
               if (na == 2) {       // second 64-wide K block of the step
-                const uint32_t a1 = a_lo + (a_bytes >> 4), b1 = b_lo + b_kb_lo;
-                umma_h16_lo(d, a1, b1, idesc, 1u);
-                umma_h16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
-                umma_h16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
-                umma_h16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
+                const uint32_t a1 = a_lo + (a_bytes >> 4) + voff, b1 = b_lo + b_kb_lo;
+                umma_h16_lo2(d, a1, a_hi, b1, idesc, 1u);
+                umma_h16_lo2(d, a1 + 2, a_hi, b1 + 2, idesc, 1u);
+                umma_h16_lo2(d, a1 + 4, a_hi, b1 + 4, idesc, 1u);
+                umma_h16_lo2(d, a1 + 6, a_hi, b1 + 6, idesc, 1u);
               }
             }
           }
@@ -1022,7 +1035,37 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       cb += na;
     }
     t.n_steps = ns;
-    return tc_upload(tma, t, host, rows, K, why);
+    // Halo program (used when a tile is one image row of 128 pixels and the weights are resident): the four shifted A
+    // operands (0,0), (0,-1), (-1,0), (-1,-1) are two 129-pixel row tiles fetched at x0 - 1; the x-shift is a view that
+    // starts one pixel row later.  2 steps of 2 K blocks per tile: half the L2 -> shared-memory traffic, and two stages
+    // hold a whole tile instead of half of one.
+    t.n_steps_halo = 0;
+    if (ncb == 2 && pair_k && 4 * cout <= 256 && !getenv("BSR_NO_HALO")) {
+      memset(t.steps_halo, 0, sizeof t.steps_halo);
+      for (int r = 0; r < 2; ++r) {
+        TcStep& h = t.steps_halo[r];
+        h.dy = (int8_t)(-r); h.dx = -1; h.a_c0 = 0; h.b_k = 0; h.n_a = 2; h.n_mma = 2;
+        if (r == 0) {
+          h.b_row = 0; h.b_rows = (int16_t)(6 * co);
+          h.mma[0] = TcMma{0, (int16_t)(4 * co), 0, (int16_t)(1 | 4)};                 // shift (0,0): all four phases, view + 1
+          h.mma[1] = TcMma{0, (int16_t)(2 * co), (int16_t)(4 * co), 0};                // shift (0,-1): p10, p00
+        } else {
+          h.b_row = (int16_t)(6 * co); h.b_rows = (int16_t)(3 * co);
+          h.mma[0] = TcMma{co, (int16_t)(2 * co), 0, 4};                                // shift (-1,0): p00, p01, view + 1
+          h.mma[1] = TcMma{co, co, (int16_t)(2 * co), 0};                               // shift (-1,-1): p00
+        }
+      }
+      t.n_steps_halo = 2;
+    }
+    if (!tc_upload(tma, t, host, rows, K, why)) return false;
+    if (t.n_steps_halo) {
+      if (cudaMalloc(&t.steps_halo_dev, sizeof t.steps_halo) != cudaSuccess ||
+          cudaMemcpy(t.steps_halo_dev, t.steps_halo, sizeof t.steps_halo, cudaMemcpyHostToDevice) != cudaSuccess) {
+        *why = "cudaMalloc / cudaMemcpy of the halo step program failed";
+        return false;
+      }
+    }
+    return true;
   }
 
   if (!transposed && kh == 3 && kw == 3 && cin == 32 && name == "down1" && !getenv("BSR_NO_PAIRX")) {
@@ -1204,11 +1247,21 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.epi_bytes = (epi_bytes + 127) / 128 * 128;
   p.steps_bytes = (int)((t.n_steps * sizeof(TcStep) + 127) / 128 * 128);
   p.b_res_kblocks = t.b_res_kblocks;
+  // halo tiles (fused transposed conv, one 128-pixel image row per tile, resident weights): see pack_tc_weights
+  const bool halo = t.kind == TC_CONVT_FUSED && t.n_steps_halo > 0 && resident && p.bw == TC_BM && p.bh == 1 && !kn.no_halo;
+  if (halo) {
+    p.n_steps = t.n_steps_halo;
+    p.steps = t.steps_halo_dev;
+    p.steps_bytes = (int)((t.n_steps_halo * sizeof(TcStep) + 127) / 128 * 128);
+  }
+  p.a_tile_bytes = halo ? 17 * 1024 : TC_BM * 128;
+  p.a_box_bytes = halo ? (TC_BM + 1) * 128 : TC_BM * 128;
+  p.halo_desc_hi = kn.halo_bo0 ? kUmmaDescHi : kUmmaDescHiOff1;
   p.ablate = kn.ablate;
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
   const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * p.b_res_rows * 128 : 0) + 192 + p.steps_bytes + p.epi_bytes + 512 + 64;
   p.a_sub = t.a_sub;
-  p.stage_bytes = t.a_sub * (TC_BM * 128 + (resident ? 0 : t.b_stage_rows * 128));
+  p.stage_bytes = t.a_sub * (p.a_tile_bytes + (resident ? 0 : t.b_stage_rows * 128));
   const int max_smem = 227 * 1024;
   // Staged TMA-store epilogue (h16 NHWC outputs whose column groups are multiples of 32 channels), used when the
   // staging fits without shortening the TMA->MMA pipeline; otherwise the direct-store epilogue runs.
@@ -1237,7 +1290,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
   p.errflag = errflag;
   if ((in_ld % 8) || (in_coff % 8)) { tma.last_error = "input channel stride/offset must be multiples of 8"; return -2; }
-  TmapKey key{in, in_ld, in_coff, t.cin, H, W, n, p.in_stride, p.bw, p.bh, t.kind};
+  TmapKey key{in, in_ld, in_coff, t.cin, H, W, n, p.in_stride, p.bw, p.bh, t.kind + (halo ? 2000 : 0)};
   auto it = cache.find(key);
   if (it == cache.end()) {
     CUtensorMap m;
@@ -1249,7 +1302,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       dims[0] = 64;
       strides[0] = 16; strides[1] = (uint64_t)(W + 8) * 16; strides[2] = (uint64_t)H * (W + 8) * 16;
     }
-    uint32_t box[4] = {TC_BK, (uint32_t)(p.bw * p.in_stride), (uint32_t)(p.bh * p.in_stride), 1};
+    uint32_t box[4] = {TC_BK, (uint32_t)(p.bw * p.in_stride + (halo ? 1 : 0)), (uint32_t)(p.bh * p.in_stride), 1};
     uint32_t es[4] = {1, (uint32_t)p.in_stride, (uint32_t)p.in_stride, 1};
     if (t.kind == TC_PAIRX) {
       // view [N][H][W/2][64]: dim 0 = one pixel pair (2 x 32 channels, 128 contiguous bytes)
