@@ -919,7 +919,6 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.no_graph = env_set("BSR_NO_GRAPH");
   h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->kn.no_halo = env_set("BSR_NO_HALO");
-  h->kn.halo_bo0 = env_set("BSR_HALO_BO0");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
   h->ld1 = pad16(h->c_first > 257 ? h->c_first : 257);

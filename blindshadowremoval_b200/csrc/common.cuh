@@ -65,7 +65,6 @@ struct Knobs {
   int host_chunk = 0;      // BSR_HOST_CHUNK: images per pipelined host-path chunk
   int no_graph = 0;        // BSR_NO_GRAPH: never replay micro-batches from captured CUDA graphs
   int no_halo = 0;         // BSR_NO_HALO: fused transposed convs fetch every shifted A tile separately (round-1 behaviour)
-  int halo_bo0 = 0;        // BSR_HALO_BO0 (bring-up): halo views with matrix base offset 0 in the descriptor
   int attn_v1 = 0;         // BSR_ATTN_V1=1: round-1 two-pass attention kernel with the fused output conv (A/B measurements)
 };
 // Launch-plan counters of one forward (bsr_plan_counter).

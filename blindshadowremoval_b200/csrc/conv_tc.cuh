@@ -166,7 +166,7 @@ struct ConvTcParams {
   int steps_bytes, epi_bytes; // shared-memory bytes of the step program / epilogue scratch (multiples of 128)
   int a_tile_bytes;           // bytes between the A sub-tiles of a stage: 16 KB, or 17 KB for 129-pixel halo tiles
   int a_box_bytes;            // bytes one A box delivers (expect_tx): 128 or 129 pixel rows of 128 B
-  uint32_t halo_desc_hi;      // descriptor high word of the one-row-in A views (matrix base offset 1)
+  int b_kb_rows;              // streamed weights: rows between the K blocks of a step inside a stage
   int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
   long long* timers;          // [16] per launch (CTA 0): role wait / total cycle counters when ablate & 8
   int* errflag;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool leader = elect_one();
       const int in_stride = p.in_stride, in_stride_x = p.in_stride_x, pad_l = p.pad_l, pad_t = p.pad_t, b_resident = p.b_resident;
       const int b_box_rows = p.b_box_rows, bn = p.bn, ablate = p.ablate;
-      const uint32_t a_sub = (uint32_t)p.a_sub, b_kb_stride = (uint32_t)(p.stage_bytes / 128 - p.a_sub * TC_BM) / (uint32_t)p.a_sub;
+      const uint32_t a_sub = (uint32_t)p.a_sub, b_kb_stride = (uint32_t)p.b_kb_rows;
       const int tiles_x = p.tiles_x, tile_h = p.bh * p.rows_per_tile, tile_w = p.bw * p.halves;
       if (b_resident && leader) {          // weights are static: fetched before the dependency wait
         const int row0 = p.b_pinned ? (int)(blockIdx.x % (unsigned)p.n_tiles) * bn : 0;
@@ -304,8 +304,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (!ok) break;
           const uint32_t dstA = smem_base + s * stage_bytes, dstB = dstA + a_sub * a_bytes;
           if (leader) {
-            const uint32_t rowmode = sp.n_a == 3, xmode = sp.n_a == 4, na = rowmode ? 1u : (xmode ? 2u : (uint32_t)sp.n_a),
-                           nsub = sp.n_a >= 2 ? 2u : 1u;
+            // n_a: 1 one A tile; 2 two K blocks (channels + 64); 3 two input rows; 4 two K blocks from x-neighbour tiles;
+            // 5 the same from ONE 129-row halo tile (the second block is a view one row in)
+            const uint32_t rowmode = sp.n_a == 3, xmode = sp.n_a == 4, hmode = sp.n_a == 5,
+                           na = rowmode ? 1u : ((xmode || hmode) ? 2u : (uint32_t)sp.n_a), nsub = (sp.n_a >= 2 && !hmode) ? 2u : 1u;
             const uint32_t bbytes = b_resident ? 0u : na * (uint32_t)sp.b_rows * 128u;
             if (ablate & 4) {
               mbar_expect_tx(bar_full + 8 * s, bbytes);
@@ -341,8 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int b_resident = p.b_resident, b_total_rows = p.b_res_rows, bn = p.bn, ablate = p.ablate;
       const uint32_t a_sub = (uint32_t)p.a_sub;
       // distance (in 16-byte units) between the weight rows of the two K blocks of a step
-      const uint32_t b_kb_lo = b_resident ? (uint32_t)b_total_rows * 8u
-                                          : ((uint32_t)(p.stage_bytes / 128 - p.a_sub * TC_BM) / (uint32_t)p.a_sub) * 8u;
+      const uint32_t b_kb_lo = b_resident ? (uint32_t)b_total_rows * 8u : (uint32_t)p.b_kb_rows * 8u;
       const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
       long long t_wfull = 0, t_wtempty = 0, t_fence = 0, t_issue = 0, t_commit = 0;
       const long long t_start = BSR_CLK();
@@ -372,26 +373,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                          : sA + a_sub * a_bytes;
           const uint32_t a_lo = umma_desc_lo(sA), b_lo0 = umma_desc_lo(sB);
           const int nm = (ablate & 2) ? 0 : sp.n_mma;
-          const uint32_t na = sp.n_a == 4 ? 2u : (uint32_t)sp.n_a;          // 4 = two K blocks whose A tiles are x-neighbours
+          const uint32_t na = sp.n_a >= 4 ? 2u : (uint32_t)sp.n_a;          // 4 / 5 = two K blocks whose A tiles are x-neighbours
           if (leader) {
             for (int m = 0; m < nm; ++m) {
               const TcMma mm = sp.mma[m];
               const uint32_t b_lo = b_lo0 + (uint32_t)mm.brow * 8u;          // 128-byte rows, address >> 4
               const uint32_t idesc = idesc_m | ((uint32_t)(mm.n >> 3) << 17);
               const uint32_t d = acc + (uint32_t)mm.col;
-              // halo view: the operand starts one 128-byte pixel row into the tile (base offset 1 in the descriptor)
-              const uint32_t voff = (mm.first & 4) ? 8u : 0u, a_hi = (mm.first & 4) ? p.halo_desc_hi : kUmmaDescHi;
+              // halo view: the operand starts one 128-byte pixel row into the tile.  The 128B swizzle is a function of the
+              // shared-memory ADDRESS bits (measured: matrix base offset 0 is right, 1 is wrong - tools/halo_probe.py), so a
+              // view that starts anywhere on a 128-byte row boundary of a TMA-written tile reads the right elements.
+              const uint32_t voff = (mm.first & 4) ? 8u : 0u;
               const uint32_t a0 = a_lo + ((mm.first & 2) ? (a_bytes >> 4) : 0u) + voff;     // row mode: second input row
-              umma_h16_lo2(d, a0, a_hi, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
-              umma_h16_lo2(d, a0 + 2, a_hi, b_lo + 2, idesc, 1u);
-              umma_h16_lo2(d, a0 + 4, a_hi, b_lo + 4, idesc, 1u);
-              umma_h16_lo2(d, a0 + 6, a_hi, b_lo + 6, idesc, 1u);
+              umma_h16_lo(d, a0, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
+              umma_h16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
+              umma_h16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
+              umma_h16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
               if (na == 2) {       // second 64-wide K block of the step
-                const uint32_t a1 = a_lo + (a_bytes >> 4) + voff, b1 = b_lo + b_kb_lo;
-                umma_h16_lo2(d, a1, a_hi, b1, idesc, 1u);
-                umma_h16_lo2(d, a1 + 2, a_hi, b1 + 2, idesc, 1u);
-                umma_h16_lo2(d, a1 + 4, a_hi, b1 + 4, idesc, 1u);
-                umma_h16_lo2(d, a1 + 6, a_hi, b1 + 6, idesc, 1u);
+                // n_a = 5: the second K block is the x-neighbour pixel pair = the same halo tile one row further
+                const uint32_t a1 = a_lo + (sp.n_a == 5 ? 8u : (a_bytes >> 4)) + voff, b1 = b_lo + b_kb_lo;
+                umma_h16_lo(d, a1, b1, idesc, 1u);
+                umma_h16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
+                umma_h16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
+                umma_h16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
               }
             }
           }
@@ -1076,9 +1080,10 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
     const size_t K = 6 * 64, rows = t.bn;
     std::vector<uint16_t> host(rows * K, 0);
-    // one step per filter row: its two K blocks (pixel pair ox and the first half of pair ox + 1) are two A sub-tiles that
-    // are x-neighbours (n_a = 4): 3 steps of 8 MMAs per tile instead of 6 of 4 - the per-step control cost of the issuer
-    // (~400 cycles, profiles/r2_role_timers) is paid half as often
+    // one step per filter row: its two K blocks (pixel pair ox and the first half of pair ox + 1) are x-neighbouring rows of
+    // ONE 129-row halo tile (n_a = 5: the second block is a view one row in): 3 steps of 8 MMAs per tile instead of 6 of 4 -
+    // the per-step control cost of the issuer (~400 cycles, profiles/r2_role_timers) is paid half as often - and 3 TMA
+    // boxes per tile instead of 6
     const bool pair_x = !getenv("BSR_NO_KPAIR");
     int ns = 0, kb = 0;
     for (int a = 0; a < 3; ++a)
@@ -1095,12 +1100,11 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
         if (pair_x && half == 1) continue;          // covered by the paired step of half 0
         TcStep& sp = t.steps[ns];
         sp.dy = (int8_t)a; sp.dx = (int8_t)half; sp.a_c0 = 0; sp.b_rows = (int16_t)t.bn; sp.b_k = kb * 64; sp.b_row = 0;
-        sp.n_a = (int8_t)(pair_x ? 4 : 1);
+        sp.n_a = (int8_t)(pair_x ? 5 : 1);
         sp.n_mma = 1; sp.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
         ++ns;
       }
-    if (pair_x) t.a_sub = 2;
-    t.n_steps = ns;
+    t.n_steps = ns;                      // a_sub stays 1: the paired K block is a view of the same (129-row) tile
     return tc_upload(tma, t, host, rows, K, why);
   }
 
@@ -1248,20 +1252,23 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.steps_bytes = (int)((t.n_steps * sizeof(TcStep) + 127) / 128 * 128);
   p.b_res_kblocks = t.b_res_kblocks;
   // halo tiles (fused transposed conv, one 128-pixel image row per tile, resident weights): see pack_tc_weights
-  const bool halo = t.kind == TC_CONVT_FUSED && t.n_steps_halo > 0 && resident && p.bw == TC_BM && p.bh == 1 && !kn.no_halo;
-  if (halo) {
+  const bool halo_ct = t.kind == TC_CONVT_FUSED && t.n_steps_halo > 0 && resident && p.bw == TC_BM && p.bh == 1 && !kn.no_halo;
+  const bool halo = halo_ct || (t.kind == TC_PAIRX && t.steps[0].n_a == 5);
+  if (t.kind == TC_PAIRX && t.steps[0].n_a == 5 && (p.bw != TC_BM || p.bh != 1)) { tma.last_error = "pair-packed halo tiles need 128-pixel rows"; return -8; }
+  if (halo_ct) {
     p.n_steps = t.n_steps_halo;
     p.steps = t.steps_halo_dev;
     p.steps_bytes = (int)((t.n_steps_halo * sizeof(TcStep) + 127) / 128 * 128);
   }
   p.a_tile_bytes = halo ? 17 * 1024 : TC_BM * 128;
   p.a_box_bytes = halo ? (TC_BM + 1) * 128 : TC_BM * 128;
-  p.halo_desc_hi = kn.halo_bo0 ? kUmmaDescHi : kUmmaDescHiOff1;
   p.ablate = kn.ablate;
   p.timers = reinterpret_cast<long long*>(errflag) + 16 + 16 * ((*launches) & 63);
   const int fixed_bytes = 1024 + (resident ? t.b_res_kblocks * p.b_res_rows * 128 : 0) + 192 + p.steps_bytes + p.epi_bytes + 512 + 64;
   p.a_sub = t.a_sub;
-  p.stage_bytes = t.a_sub * (p.a_tile_bytes + (resident ? 0 : t.b_stage_rows * 128));
+  const int b_sub = (t.kind == TC_PAIRX && t.steps[0].n_a == 5) ? 2 : t.a_sub;          // K blocks of weights per step
+  p.b_kb_rows = t.b_stage_rows;
+  p.stage_bytes = t.a_sub * p.a_tile_bytes + (resident ? 0 : b_sub * t.b_stage_rows * 128);
   const int max_smem = 227 * 1024;
   // Staged TMA-store epilogue (h16 NHWC outputs whose column groups are multiples of 32 channels), used when the
   // staging fits without shortening the TMA->MMA pipeline; otherwise the direct-store epilogue runs.
@@ -1308,7 +1315,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       // view [N][H][W/2][64]: dim 0 = one pixel pair (2 x 32 channels, 128 contiguous bytes)
       dims[0] = 64; dims[1] = (uint64_t)(W / 2);
       strides[0] = 128;
-      box[1] = (uint32_t)p.bw; es[1] = 1;
+      box[1] = (uint32_t)p.bw + (halo ? 1u : 0u); es[1] = 1;
     }
     if (!tma.encode_h16(&m, (void*)((const h16*)in + in_coff), 4, dims, strides, box, es)) return -3;
     if (cache.size() > 4096) cache.clear();

@@ -257,22 +257,6 @@ __device__ __forceinline__ void umma_h16_lo(uint32_t d_tmem, uint32_t a_lo, uint
       : "memory");
 }
 
-// Same with an explicit descriptor high word for the A operand (matrix base offset, see kUmmaDescHiOff1).
-__device__ __forceinline__ void umma_h16_lo2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %6};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi), "r"(a_hi)
-      : "memory");
-}
-// Descriptor high word for an operand that starts ONE 128-byte row into a 1024-byte swizzle atom: the matrix base
-// offset field (descriptor bits 49-51 = (start address >> 7) & 7) tells the unit where in the repeating pattern row 0 sits.
-constexpr uint32_t kUmmaDescHiOff1 = kUmmaDescHi | (1u << 17);
-
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (lane = row).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
