@@ -462,10 +462,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
           uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float p0 = fa_exp2(fmaf(__uint_as_float(v[2 * i]), kLog2e, mneg));
-            const float p1 = fa_exp2(fmaf(__uint_as_float(v[2 * i + 1]), kLog2e, mneg));
-            l0 += p0;
-            l1 += p1;
+            float t0, t1;
+            fma2_bc(t0, t1, __uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), kLog2e, mneg);     // packed FFMA2
+            const float p0 = fa_exp2(t0), p1 = fa_exp2(t1);
+            fadd2(l0, l1, p0, p1);
             pk[i] = pack_h16x2(p0, p1);
           }
           tmem_st16(tS + 32u * hf, pk);

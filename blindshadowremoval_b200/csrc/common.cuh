@@ -55,6 +55,41 @@ template <> __device__ __forceinline__ void stf<h16>(h16* p, size_t i, float v) 
 
 __device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : kLeaky * v; }
 
+// Packed fp32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): two IEEE fp32 FMAs per issued instruction, bit-identical to two
+// fmaf().  (d0, d1) += a * (w0, w1)   and   (d0, d1) += (a0, a1) * (w0, w1).  The register-pair moves fold away.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float w0, float w1) {
+  uint64_t d, aa, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w0), "f"(w1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+// (r0, r1) = (a0, a1) * b + c   and   (d0, d1) += (a0, a1)
+__device__ __forceinline__ void fma2_bc(float& r0, float& r1, float a0, float a1, float b, float c) {
+  uint64_t d, aa, bb, cc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(aa), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(d));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  uint64_t d, aa;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(aa));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float w0, float w1) {
+  uint64_t d, aa, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w0), "f"(w1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 // Experiment / bring-up switches, read from the environment ONCE per handle (bsr_create), never on the launch path.
 struct Knobs {
   int ablate = 0;          // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = role timers

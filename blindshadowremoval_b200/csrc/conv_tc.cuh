@@ -755,10 +755,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (lane == 31) rg = wr < 7 ? edge[(wr + 1) * 32 + 16 + i] : 0.f;
           v[i] = ((bias_s[i] + l) + y1v[i]) + rg;
         }
+        // the colour tail is bound by its instruction count (profiles/r2_role_timers_mb256_after.txt): packed FFMA2
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaf(gv[t], cw.wg[t * 16 + i], v[i]);
+          for (int i = 0; i < 16; i += 2) ffma2(v[i], v[i + 1], gv[t], cw.wg[t * 16 + i], cw.wg[t * 16 + i + 1]);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], kLeaky * v[i]);
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) hbuf[i] = fmaf(v[c], cw.w2[c * 16 + i], hbuf[i]);
+          for (int i = 0; i < 16; i += 2) ffma2(hbuf[i], hbuf[i + 1], v[c], cw.w2[c * 16 + i], cw.w2[c * 16 + i + 1]);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) hbuf[i] = fmaxf(hbuf[i], kLeaky * hbuf[i]);
@@ -779,8 +780,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           float s0 = cw.b3[o], s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            s0 = fmaf(hbuf[4 * i], cw.w3t[o * 16 + 4 * i], s0); s1 = fmaf(hbuf[4 * i + 1], cw.w3t[o * 16 + 4 * i + 1], s1);
-            s2 = fmaf(hbuf[4 * i + 2], cw.w3t[o * 16 + 4 * i + 2], s2); s3 = fmaf(hbuf[4 * i + 3], cw.w3t[o * 16 + 4 * i + 3], s3);
+            ffma2v(s0, s1, hbuf[4 * i], hbuf[4 * i + 1], cw.w3t[o * 16 + 4 * i], cw.w3t[o * 16 + 4 * i + 1]);
+            ffma2v(s2, s3, hbuf[4 * i + 2], hbuf[4 * i + 3], cw.w3t[o * 16 + 4 * i + 2], cw.w3t[o * 16 + 4 * i + 3]);
           }
           rgb[o] = (s0 + s1) + (s2 + s3);
         }
