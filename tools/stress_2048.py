@@ -1,4 +1,4 @@
-"""BASELINE config 5: 2048-image synthetic stress run, bf16 tensor-core path vs fp32 check mode.
+"""BASELINE config 5: 2048-image synthetic stress run, 16-bit tensor-core path vs fp32 check mode.
 
 2048 distinct seeded crops in batches of 128 through both precisions of the SAME library (the fp32 check mode is
 itself pinned to the oracle at 1e-4 by tests/test_gpu_parity.py).  Reports, over all 2048 images: max-abs / mean-abs /
