@@ -522,7 +522,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         {
           const uint4* s1 = reinterpret_cast<const uint4*>((const h16*)e.res1 + pix * e.res1_ld + 256);
           const uint4* s2 = reinterpret_cast<const uint4*>((const h16*)e.res2 + pix * e.res2_ld + 256);
-          ya[0] = s1[0]; ya[1] = s1[1]; xa[0] = s2[0]; xa[1] = s2[1];
+          if ((e.res1_ld | e.res2_ld) % 16 == 0) {               // 32-byte aligned rows: 256-bit loads
+            ld_global_256(s1, ya[0], ya[1]);
+            ld_global_256(s2, xa[0], xa[1]);
+          } else {
+            ya[0] = s1[0]; ya[1] = s1[1]; xa[0] = s2[0]; xa[1] = s2[1];
+          }
         }
         float dot0 = 0.f, dot1 = 0.f;
         uint8_t* qbuf = smem_al + (sQ + x * FA_TILE - base) + row * 128;
@@ -624,8 +629,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
             ow[k] = pack_h16x2(r0, r1);
           }
           uint4* d = reinterpret_cast<uint4*>((h16*)e.out + pix * e.out_ld + e.out_coff + 256);
-          d[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          d[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+          if ((e.out_ld | e.out_coff) % 16 == 0) {
+            st_global_256(d, make_uint4(ow[0], ow[1], ow[2], ow[3]), make_uint4(ow[4], ow[5], ow[6], ow[7]));
+          } else {
+            d[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            d[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+          }
         }
       }
     }

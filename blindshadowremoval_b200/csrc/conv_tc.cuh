@@ -516,6 +516,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int bw = p.bw, bh = p.bh, out_scale = p.out_scale, group_cols = p.group_cols;
         const int gyb = (tr / p.tiles_x) * bh * rows_per_tile + r / bw, gx = (tr % p.tiles_x) * bw + r % bw;
         const bool vec_ok = (e.out_ld % 8 == 0) && (e.out_coff % 8 == 0);
+        // 32-byte aligned 16-channel chunks (all chunk starts are multiples of 16 channels): one 256-bit store per chunk
+        const bool vec32_ok = e.out_mode == OUT_QKV || ((e.out_ld % 16 == 0) && (e.out_coff % 16 == 0));
         const int cbase = p.n_groups == 1 ? ntile * bn : 0;
         const int total_cols = p.n_groups * group_cols;
         // residual / skip operands of this thread's first 3 chunks are fetched BEFORE the accumulator wait, so their
@@ -529,12 +531,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int col = (4 * k + cg) * 16, c = cbase + col;
             if (col < bn && c + 16 <= e.out_c) {
               if (e.res1 != nullptr && c + 16 <= e.res1_c) {
-                const uint4* src = reinterpret_cast<const uint4*>((const h16*)e.res1 + pix0 * e.res1_ld + c);
-                rb1[k][0] = src[0]; rb1[k][1] = src[1]; m1 |= 1u << k;
+                const h16* src = (const h16*)e.res1 + pix0 * e.res1_ld + c;
+                if (e.res1_ld % 16 == 0) ld_global_256(src, rb1[k][0], rb1[k][1]);
+                else { rb1[k][0] = reinterpret_cast<const uint4*>(src)[0]; rb1[k][1] = reinterpret_cast<const uint4*>(src)[1]; }
+                m1 |= 1u << k;
               }
               if (e.res2 != nullptr && c + 16 <= e.res2_c) {
-                const uint4* src = reinterpret_cast<const uint4*>((const h16*)e.res2 + pix0 * e.res2_ld + c);
-                rb2[k][0] = src[0]; rb2[k][1] = src[1]; m2 |= 1u << k;
+                const h16* src = (const h16*)e.res2 + pix0 * e.res2_ld + c;
+                if (e.res2_ld % 16 == 0) ld_global_256(src, rb2[k][0], rb2[k][1]);
+                else { rb2[k][0] = reinterpret_cast<const uint4*>(src)[0]; rb2[k][1] = reinterpret_cast<const uint4*>(src)[1]; }
+                m2 |= 1u << k;
               }
             }
           }
@@ -600,8 +606,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                  ? reinterpret_cast<uint4*>((h16*)e.out2 + pix * 128 + (c - 256))
                                  : reinterpret_cast<uint4*>((h16*)e.out + off);
                 if (!(p.ablate & 1)) {
-                  dst[0] = o0;
-                  dst[1] = o1;
+                  if (vec32_ok) {
+                    st_global_256(dst, o0, o1);
+                  } else {
+                    dst[0] = o0;
+                    dst[1] = o1;
+                  }
                 }
               }
             } else {
@@ -613,6 +623,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           while (j >= group_cols) { j -= group_cols; ++g; }
         };
         int col = cg * 16;
+        if (!RES && p.n_groups == 4 && e.out_mode == OUT_T && vec32_ok && group_cols == 64 && e.out_c == 64 && bn == 256) {
+          // Fused 4-phase transposed conv with 64 output channels whose stores cannot be staged (up3 / clr_up3: 144 KB of
+          // resident weights): this warp owns channels [16 cg, 16 cg + 16) of all four sub-pixel phases.  All four
+          // accumulator chunks are fetched with ONE TMEM round trip, the accumulators are released before the stores, and
+          // every chunk leaves as one 256-bit store.
+          float v[4][16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tmem_ld16_nowait(acc + (uint32_t)(cg * 16 + 64 * k), v[k]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          const int cch = cg * 16;
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cch), b1 = *reinterpret_cast<const float4*>(bias_s + cch + 4),
+                       b2 = *reinterpret_cast<const float4*>(bias_s + cch + 8), b3 = *reinterpret_cast<const float4*>(bias_s + cch + 12);
+          const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int phase = p.group_phase[k];
+            const int oy = gyb * out_scale + (phase >> 1), ox = gx * out_scale + (phase & 1);
+            const size_t opix = ((size_t)n * OH + oy) * OW + ox;
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float a0 = v[k][i] + bb[i], a1 = v[k][i + 1] + bb[i + 1];
+              if (e.act) { a0 = fmaxf(a0, kLeaky * a0); a1 = fmaxf(a1, kLeaky * a1); }
+              o[i >> 1] = pack_h16x2(a0, a1);
+            }
+            if (!(p.ablate & 1))
+              st_global_256((h16*)e.out + opix * e.out_ld + e.out_coff + cch, make_uint4(o[0], o[1], o[2], o[3]),
+                            make_uint4(o[4], o[5], o[6], o[7]));
+          }
+          continue;
+        }
         if (RES) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
