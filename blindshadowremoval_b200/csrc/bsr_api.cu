@@ -415,8 +415,8 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
   if (h->precision == BSR_PRECISION_BF16 && !h->force_direct && h->layers["conv1"].tc.ready) {
     {
       Step step(h, st, "pack_img");
-      long long rows = (long long)n * IMG, tot = rows * (IMG + 8);
-      pack_img_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(img, (h16*)h->PIMG, rows);
+      const long long tot = (long long)n * (IMG + 1) * (IMG + 8);
+      pack_img_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(img, (h16*)h->PIMG, n);
       h->launches++;
     }
     ConvCall cv1{"conv1", h->PIMG, 8, 0, false, IMG, IMG, 1, epi(h->X1, 32, 0, 32, 1), no_extra()};
@@ -935,7 +935,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {&h->T2, mb * 1024 * 128 * es}, {&h->Y, mb * 1024 * kLdY * es}, {&h->QK, mb * 1024 * 256 * es},
       {&h->VT, mb * 1024 * 128 * es}, {&h->O, mb * 1024 * 128 * es}, {&h->UP3, mb * IMG * IMG * 64 * es},
       {&h->F1, mb * 64 * 64 * 128 * es}, {&h->F2, mb * 128 * 128 * 96 * es}, {&h->CAT1, mb * IMG * IMG * 72 * es},
-      {&h->C16, mb * IMG * IMG * 16 * es}, {&h->PIMG, mb * IMG * (IMG + 8) * 8 * 2},
+      {&h->C16, mb * IMG * IMG * 16 * es}, {&h->PIMG, mb * (IMG + 1) * (IMG + 8) * 8 * 2},
       {(char**)&h->RAW, mb * IMG * IMG * 2 * 4}, {(char**)&h->GS32, mb * IMG * IMG * 4}, {(char**)&h->DIFGS, mb * IMG * IMG * 4},
       {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
       {(char**)&h->DIFSMALL, mb * 1024 * 4},

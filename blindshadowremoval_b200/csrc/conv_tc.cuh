@@ -958,27 +958,41 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   auto W = [&](int tap, int c, int o) { return w[((size_t)tap * cin + c) * cout + o]; };
 
   if (name == "conv1") {
-    // 7x7 conv over 3 channels (model.py:203): K per filter ROW = 7 taps x 8 (3 real + 5 zero) channels + one
-    // zero-weight pixel = 64 elements, fetched as an overlapping window of the packed image.
-    if (kh != 7 || kw != 7 || cin > 8 || transposed) { *why = "conv1 must be 7x7 with <= 8 input channels"; return false; }
-    // Tile = R = 8 output rows x 128 pixels: input row j (of R+6) feeds output row rr = j-kh with filter row kh, so
-    // every packed row is fetched once per tile; the 28 KB of weights stay resident in shared memory.
+    // 7x7 conv over 3 channels (model.py:203).  The packed image (glue.cuh: pack_img_kernel) holds TWO image rows per
+    // packed row, so one 64-element K block = 8 window pixels x [row y: 3 + 1 channels | row y + 1: 3 + 1 channels] covers
+    // two filter rows (42 of 64 K elements are real, twice the density of one row per block).
+    if (kh != 7 || kw != 7 || cin > 4 || transposed) { *why = "conv1 must be 7x7 with <= 4 input channels"; return false; }
+    // Tile = R = 8 output rows x 128 pixels.  Input row pair p (tile rows 2p-3, 2p-2) feeds output row r with the filter
+    // rows (k, k + 1), k = 2p - r in [-1, 6] (rows -1 and 7 are zero).  Weight blocks are stored in DESCENDING k, so the
+    // output rows a pair updates are consecutive weight rows: ONE wide accumulate MMA for the rows that already hold a
+    // partial sum plus one overwrite MMA for the (up to two) rows whose first pair this is.  32 KB of weights stay resident.
     const int R = 8, nb = (cout + 15) / 16 * 16;
     t.kind = TC_ROWPACK; t.cin_pad = 64; t.bn = R * nb; t.n_tiles = 1;
     t.b_box_rows = nb; t.b_stage_rows = 0; t.b_resident = 1; t.rows_per_tile = R; t.halves = 1;
-    const size_t K = 64, rows = 7 * (size_t)nb;
+    const size_t K = 64, rows = 8 * (size_t)nb;
     std::vector<uint16_t> host(rows * K, 0);
-    for (int a = 0; a < 7; ++a)
+    for (int i = 0; i < 8; ++i) {                       // block i <-> k = 6 - i
+      const int k = 6 - i;
       for (int b = 0; b < 7; ++b)
         for (int c = 0; c < cin; ++c)
-          for (int o = 0; o < cout; ++o) host[((size_t)(6 - a) * nb + o) * K + b * 8 + c] = f32_to_h16_bits(W(a * 7 + b, c, o));
+          for (int o = 0; o < cout; ++o) {
+            if (k >= 0) host[((size_t)i * nb + o) * K + b * 8 + c] = f32_to_h16_bits(W(k * 7 + b, c, o));
+            if (k + 1 <= 6) host[((size_t)i * nb + o) * K + b * 8 + 4 + c] = f32_to_h16_bits(W((k + 1) * 7 + b, c, o));
+          }
+    }
     int ns = 0;
-    const bool rpair = !getenv("BSR_NO_RPAIR");
-    if (rpair) t.a_sub = 2;
-    for (int j = 0; j < R + 6; j += rpair ? 2 : 1) {
+    for (int pr = 0; pr < 7; ++pr) {
       TcStep& sp = t.steps[ns++];
-      sp.dy = (int8_t)(j - 3); sp.dx = 0; sp.a_c0 = 0; sp.b_rows = 0; sp.b_k = 0; sp.b_row = 0;
-      tc_rows_step(sp, j, R, 7, nb, 0, rpair);
+      // packed row yp = y + 1 holds image rows (y, y + 1); the pair starts at image row y0 - 3 + 2 pr
+      sp.dy = (int8_t)(2 * pr - 3 + 1); sp.dx = 0; sp.a_c0 = 0; sp.b_rows = 0; sp.b_k = 0; sp.b_row = 0; sp.n_a = 1;
+      sp.n_mma = 0;
+      const int lo = 2 * pr - 6 > 0 ? 2 * pr - 6 : 0, hi = 2 * pr - 1 < R - 1 ? 2 * pr - 1 : R - 1;
+      if (hi >= lo)
+        sp.mma[sp.n_mma++] = TcMma{(int16_t)(lo * nb), (int16_t)((hi - lo + 1) * nb), (int16_t)((6 - 2 * pr + lo) * nb), 0};
+      if (2 * pr <= R - 1) {
+        const int cnt = 2 * pr + 1 <= R - 1 ? 2 : 1;
+        sp.mma[sp.n_mma++] = TcMma{(int16_t)(2 * pr * nb), (int16_t)(cnt * nb), (int16_t)(6 * nb), 1};
+      }
     }
     t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
@@ -1349,10 +1363,11 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
     uint64_t dims[4] = {(uint64_t)(t.kind == TC_CLR ? 64 : t.cin), (uint64_t)W, (uint64_t)H, (uint64_t)n};
     uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)W * in_ld * 2, (uint64_t)H * W * in_ld * 2};
     if (t.kind == TC_ROWPACK) {
-      // packed image [N][H][W + 8][8]: window of output column x = 64 contiguous elements starting at packed
-      // pixel x (= image pixel x-3); consecutive windows overlap (dim-1 stride 16 B < dim-0 extent 128 B)
-      dims[0] = 64;
-      strides[0] = 16; strides[1] = (uint64_t)(W + 8) * 16; strides[2] = (uint64_t)H * (W + 8) * 16;
+      // packed image [N][H + 1][W + 8][8] (two image rows per packed row): window of output column x = 64 contiguous
+      // elements starting at packed pixel x (= image pixel x-3); consecutive windows overlap (dim-1 stride 16 B < dim-0
+      // extent 128 B)
+      dims[0] = 64; dims[2] = (uint64_t)(H + 1);
+      strides[0] = 16; strides[1] = (uint64_t)(W + 8) * 16; strides[2] = (uint64_t)(H + 1) * (W + 8) * 16;
     }
     uint32_t box[4] = {TC_BK, (uint32_t)(p.bw * p.in_stride + (halo ? 1 : 0)), (uint32_t)(p.bh * p.in_stride), 1};
     uint32_t es[4] = {1, (uint32_t)p.in_stride, (uint32_t)p.in_stride, 1};

@@ -26,19 +26,30 @@ __global__ void uv_small_kernel(const float* __restrict__ uv, float* __restrict_
   uvs[idx] = resize8(uv, n, i, j, 3, c);
 }
 
-// conv1 input packing: img fp32 [N,256,256,3] -> h16 [N][256][264][8]; packed pixel xp holds image pixel
-// xp-3 (zero outside the image, channels 3..7 zero), so the 7-tap row window of output x starts at xp = x.
-__global__ void pack_img_kernel(const float* __restrict__ img, h16* __restrict__ out, long long n_rows) {
+// conv1 input packing: img fp32 [N,256,256,3] -> 16-bit [N][257][264][8].  Packed row yp holds image rows yp-1 and yp,
+// packed pixel xp holds image pixel xp-3: 8 channels = [R G B 0 of row yp-1 | R G B 0 of row yp] (zero outside the
+// image).  The 7-tap window of output x in packed row yp starts at xp = x and is ONE 64-element K block that covers
+// TWO filter rows, so a 7x7 tile needs 7 row-pair steps instead of 14 row steps (K utilisation 42/64 instead of 21/64).
+__global__ void pack_img_kernel(const float* __restrict__ img, h16* __restrict__ out, long long n_img) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_rows * (IMG + 8)) return;
-  int xp = (int)(idx % (IMG + 8));
-  long long row = idx / (IMG + 8);
-  int x = xp - 3;
+  if (idx >= n_img * (IMG + 1) * (IMG + 8)) return;
+  const int xp = (int)(idx % (IMG + 8));
+  const long long t = idx / (IMG + 8);
+  const int yp = (int)(t % (IMG + 1));
+  const long long n = t / (IMG + 1);
+  const int x = xp - 3;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (x >= 0 && x < IMG) {
-    const float* s = img + (row * IMG + x) * 3;
-    o.x = pack_h16x2(s[0], s[1]);
-    o.y = pack_h16x2(s[2], 0.f);
+    if (yp >= 1) {
+      const float* s = img + ((n * IMG + (yp - 1)) * IMG + x) * 3;
+      o.x = pack_h16x2(s[0], s[1]);
+      o.y = pack_h16x2(s[2], 0.f);
+    }
+    if (yp < IMG) {
+      const float* s = img + ((n * IMG + yp) * IMG + x) * 3;
+      o.z = pack_h16x2(s[0], s[1]);
+      o.w = pack_h16x2(s[2], 0.f);
+    }
   }
   reinterpret_cast<uint4*>(out)[idx] = o;
 }
