@@ -95,6 +95,7 @@ struct TcWeights {
   int n_steps = 0;
   int tile_w = 0;         // forced tile width (heads: 128 with two halves per tile), 0 = auto
   int rows_per_tile = 1;  // multi-row tiles: R output rows share their input rows (vertical-tap layers)
+  int zero_acc = 0;       // see ConvTcParams::zero_acc
   int halves = 1;         // 2: a tile row is 256 pixels = two 128-pixel A tiles
   int b_resident = 0;     // whole weight matrix stays in shared memory for the life of the CTA
   int b_total_rows = 0;
@@ -167,6 +168,8 @@ struct ConvTcParams {
   int a_tile_bytes;           // bytes between the A sub-tiles of a stage: 16 KB, or 17 KB for 129-pixel halo tiles
   int a_box_bytes;            // bytes one A box delivers (expect_tx): 128 or 129 pixel rows of 128 B
   int b_kb_rows;              // streamed weights: rows between the K blocks of a step inside a stage
+  int zero_acc;               // the epilogue leaves every accumulator stage zeroed, so NO MMA of the step program overwrites:
+                              // the first tap of an output row rides in the same wide MMA as the rows already accumulating
   int ablate;                 // BSR_ABLATE (profiling only): 1 = no epilogue stores, 2 = no MMA, 4 = no A-tile TMA, 8 = timers
   long long* timers;          // [16] per launch (CTA 0): role wait / total cycle counters when ablate & 8
   int* errflag;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t bars = sBres + (p.b_resident ? (uint32_t)(p.b_res_kblocks * p.b_res_rows) * 128u : 0u);
   // full[8], empty[8], tmem_full[2], tmem_empty[2], bres, tmem slot
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_tfull = bars + 128, bar_tempty = bars + 144;
-  const uint32_t bar_bres = bars + 160, tmem_slot = bars + 168;
+  const uint32_t bar_bres = bars + 160, tmem_slot = bars + 168, bar_zero = bars + 176;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
   TcStep* steps = reinterpret_cast<TcStep*>(smem_al + (bars + 192 - smem_base));
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(bar_tempty + 8 * s, TC_EPI_WARPS);
     }
     mbar_init(bar_bres, 1);
+    mbar_init(bar_zero, TC_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       long long t_wfull = 0, t_wtempty = 0, t_fence = 0, t_issue = 0, t_commit = 0;
       const long long t_start = BSR_CLK();
       if (b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
+      if (ok && p.zero_acc) ok = mbar_wait(bar_zero, 0, p.errflag, 6);      // both accumulator stages start out zeroed
       const long long t_res = BSR_CLK() - t_start;
       const uint32_t idesc_m = umma_idesc_h16(TC_BM, 0);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
@@ -427,6 +432,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float* bias_s = epi_smem;                   // [512] (the device bias buffer is zero-padded past cout)
     float* epi_work = epi_smem + 512;
     for (int i = ethread; i < 512 && i * 4 < p.epi_bytes; i += TC_EPI_WARPS * 32) bias_s[i] = __ldg(e.bias + i);
+    if (p.zero_acc) {
+      // zero this warp's share of the allocated TMEM columns (4 warps per lane quarter: column chunks cg, cg + 4, ...)
+      for (uint32_t c = (uint32_t)cg * 16u; c < tmem_cols; c += 64u) tmem_zero16(tmem_base + lane_addr + c);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_zero);
+    }
     epi_bar_all();
     pdl_wait();
     const int OH = p.OH, OW = p.OW, bn = p.bn, rows_per_tile = p.rows_per_tile;
@@ -457,6 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (col < total_cols) {
             float v[16];
             tmem_ld16(acc + (uint32_t)col, v);
+            if (p.zero_acc) tmem_zero16(acc + (uint32_t)col);
             const int j = col % group_cols;                                    // channel inside the group
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -471,6 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 8; ++i) o[i] = pack_h16x2(v[2 * i], v[2 * i + 1]);
           }
           if (col0 + iter_cols >= total_cols) {          // accumulators drained: the MMA warp may start the next tile
+            if (p.zero_acc) tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
@@ -566,9 +581,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             pix = ((size_t)n * OH + oy) * OW + ox;
           }
           const int c = cbase + j;
+          if (p.zero_acc && c >= e.out_c) tmem_zero16(acc + (uint32_t)col);
           if (c < e.out_c) {
             float v[16];
             tmem_ld16(acc + (uint32_t)col, v);
+            if (p.zero_acc) tmem_zero16(acc + (uint32_t)col);
             if (c + 16 <= e.out_c && (vec_ok || e.out_mode != OUT_T)) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
@@ -666,6 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
 #pragma unroll 1
         for (; col < total_cols; col += 64) chunk(col, false, rb1[0][0], rb1[0][1], false, rb2[0][0], rb2[0][1]);
+        if (p.zero_acc) tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
@@ -697,7 +715,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           float v[16];
           tmem_ld16(acc + (uint32_t)((half * rows_per_tile + rr) * 16), v);
+          if (p.zero_acc) tmem_zero16(acc + (uint32_t)((half * rows_per_tile + rr) * 16));
           if (rr + 2 >= rows_per_tile) {
+            if (p.zero_acc) tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);        // accumulators drained: MMA may start the next tile
@@ -926,20 +946,26 @@ inline bool tc_disabled(const std::string& name) {
 // weight blocks of consecutive output rows are consecutive too: all rows that already hold a partial sum are
 // updated by ONE wide MMA (A read from shared memory once), and the row whose first tap this is by a second MMA
 // with accumulate = 0.  Accumulator column of (group base, row rr) = (base + rr) * nb.
-inline void tc_rows_sub(TcStep& sp, int j, int R, int KH, int nb, int base, int sub) {
+inline void tc_rows_sub(TcStep& sp, int j, int R, int KH, int nb, int base, int sub, bool merge = false) {
   const int lo = j - (KH - 1) > 0 ? j - (KH - 1) : 0, hi = j - 1 < R - 1 ? j - 1 : R - 1;
   const int16_t sb = (int16_t)(sub << 1);
+  if (merge) {        // zero_acc: the row whose first tap this is (row j) accumulates like the others -> one MMA
+    const int hi2 = j < R - 1 ? j : R - 1;
+    if (hi2 >= lo)
+      sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + lo) * nb), (int16_t)((hi2 - lo + 1) * nb), (int16_t)((lo + KH - 1 - j) * nb), sb};
+    return;
+  }
   if (hi >= lo)
     sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + lo) * nb), (int16_t)((hi - lo + 1) * nb), (int16_t)((lo + KH - 1 - j) * nb), sb};
   if (j <= R - 1) sp.mma[sp.n_mma++] = TcMma{(int16_t)((base + j) * nb), (int16_t)nb, (int16_t)((KH - 1) * nb), (int16_t)(sb | 1)};
 }
 // One step = input rows j and j+1 (two A sub-tiles, TMA boxes at dy and dy+1) when `pair` and both rows exist.
-inline void tc_rows_step(TcStep& sp, int j, int R, int KH, int nb, int base, bool pair) {
+inline void tc_rows_step(TcStep& sp, int j, int R, int KH, int nb, int base, bool pair, bool merge = false) {
   sp.n_mma = 0;
-  tc_rows_sub(sp, j, R, KH, nb, base, 0);
+  tc_rows_sub(sp, j, R, KH, nb, base, 0, merge);
   if (pair && j + 1 < R + KH - 1) {
     sp.n_a = 3;
-    tc_rows_sub(sp, j + 1, R, KH, nb, base, 1);
+    tc_rows_sub(sp, j + 1, R, KH, nb, base, 1, merge);
   }
 }
 
@@ -955,6 +981,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   memset(t.steps, 0, sizeof t.steps);
   t.kh = kh; t.kw = kw; t.cin = cin; t.cout = cout; t.transposed = transposed;
   t.tile_w = 0; t.a_sub = 1; t.rows_per_tile = 1; t.halves = 1; t.b_resident = 0; t.can_reside = 0; t.b_res_kblocks = 1;
+  t.zero_acc = 0;
   auto W = [&](int tap, int c, int o) { return w[((size_t)tap * cin + c) * cout + o]; };
 
   if (name == "conv1") {
@@ -969,6 +996,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     const int R = 8, nb = (cout + 15) / 16 * 16;
     t.kind = TC_ROWPACK; t.cin_pad = 64; t.bn = R * nb; t.n_tiles = 1;
     t.b_box_rows = nb; t.b_stage_rows = 0; t.b_resident = 1; t.rows_per_tile = R; t.halves = 1;
+    t.zero_acc = (R * nb <= 256 && !getenv("BSR_NO_ZERO_ACC")) ? 1 : 0;
     const size_t K = 64, rows = 8 * (size_t)nb;
     std::vector<uint16_t> host(rows * K, 0);
     for (int i = 0; i < 8; ++i) {                       // block i <-> k = 6 - i
@@ -987,6 +1015,11 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       sp.dy = (int8_t)(2 * pr - 3 + 1); sp.dx = 0; sp.a_c0 = 0; sp.b_rows = 0; sp.b_k = 0; sp.b_row = 0; sp.n_a = 1;
       sp.n_mma = 0;
       const int lo = 2 * pr - 6 > 0 ? 2 * pr - 6 : 0, hi = 2 * pr - 1 < R - 1 ? 2 * pr - 1 : R - 1;
+      if (t.zero_acc) {      // accumulators start out zeroed: the pair's new rows ride in the same MMA (N <= 8 nb = 256)
+        const int hi2 = 2 * pr + 1 < R - 1 ? 2 * pr + 1 : R - 1;
+        sp.mma[sp.n_mma++] = TcMma{(int16_t)(lo * nb), (int16_t)((hi2 - lo + 1) * nb), (int16_t)((6 - 2 * pr + lo) * nb), 0};
+        continue;
+      }
       if (hi >= lo)
         sp.mma[sp.n_mma++] = TcMma{(int16_t)(lo * nb), (int16_t)((hi - lo + 1) * nb), (int16_t)((6 - 2 * pr + lo) * nb), 0};
       if (2 * pr <= R - 1) {
@@ -1004,6 +1037,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     const int R = 8;
     t.kind = TC_HEADS; t.cin_pad = 64; t.bn = R * 2 * 16; t.n_tiles = 1; t.b_box_rows = 16; t.b_stage_rows = 0;
     t.b_resident = 1; t.rows_per_tile = R; t.halves = 2; t.tile_w = 128;
+    t.zero_acc = getenv("BSR_NO_ZERO_ACC") ? 0 : 1;
     const size_t K = 64, rows = 7 * 16;
     std::vector<uint16_t> host(rows * K, 0);
     for (int a = 0; a < 7; ++a)
@@ -1017,7 +1051,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       for (int j = 0; j < R + 6; j += rpair ? 2 : 1) {
         TcStep& sp = t.steps[ns++];
         sp.dy = (int8_t)(j - 3); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
-        tc_rows_step(sp, j, R, 7, 16, hh * R, rpair);
+        tc_rows_step(sp, j, R, 7, 16, hh * R, rpair, t.zero_acc != 0);
       }
     t.n_steps = ns;
     return tc_upload(tma, t, host, rows, K, why);
@@ -1327,6 +1361,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   p.a_sub = t.a_sub;
   const int b_sub = (t.kind == TC_PAIRX && t.steps[0].n_a == 5) ? 2 : t.a_sub;          // K blocks of weights per step
   p.b_kb_rows = t.b_stage_rows;
+  p.zero_acc = t.zero_acc;
   p.stage_bytes = t.a_sub * p.a_tile_bytes + (resident ? 0 : b_sub * t.b_stage_rows * 128);
   const int max_smem = 227 * 1024;
   // Staged TMA-store epilogue (h16 NHWC outputs whose column groups are multiples of 32 channels), used when the
