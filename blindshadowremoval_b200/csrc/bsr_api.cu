@@ -98,6 +98,7 @@ struct bsr_handle {
   char* chunk_stage = nullptr;      // dense img | uv | reg | face planes of one micro-batch (bsr_forward_chunk)
   size_t chunk_stage_bytes = 0;
   bool in_small = false;   // compact host path: uv/reg arrive already resized to 32x32
+  bool in_rows = false;    // fp32 host path: uv/reg arrive as the two centre rows of every 8-row band ([n][32][2][256][C])
   char* stage = nullptr;
   size_t stage_bytes = 0;
   int host_step_cap = 0;   // images per host-path chunk the staging was sized for
@@ -441,6 +442,9 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     int tot = n * FEAT * FEAT * 3;
     if (h->in_small) {
       CK(h, cudaMemcpyAsync(h->UVS, uv, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (h->in_rows) {
+      uv_rows_small_kernel<<<(tot + 255) / 256, 256, 0, st>>>(uv, h->UVS, n);
+      h->launches++;
     } else {
       uv_small_kernel<<<(tot + 255) / 256, 256, 0, st>>>(uv, h->UVS, n);
       h->launches++;
@@ -448,6 +452,7 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     if (tsm) {
       int tot4 = n * FEAT * FEAT * 4;
       if (h->in_small) reg32_off_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
+      else if (h->in_rows) reg_rows_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
       else reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
       h->launches++;
     }
@@ -619,7 +624,8 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
   for (int i0 = 0; i0 < n; i0 += step) {
     int m = n - i0 < step ? n - i0 : step;
     const size_t o3 = (size_t)i0 * IMG * IMG * 3, o1 = (size_t)i0 * IMG * IMG;
-    const size_t aux_px = h->in_small ? (size_t)i0 * FEAT * FEAT : o1;      // uv/reg pixels per image
+    // uv/reg pixels per image: 32 x 32 (compact), 32 x 2 x 256 (centre rows only), or the full 256 x 256
+    const size_t aux_px = h->in_small ? (size_t)i0 * FEAT * FEAT : (h->in_rows ? (size_t)i0 * FEAT * 2 * IMG : o1);
     int rc;
     const float* uvp = uv + aux_px * 3;
     const float* regp = reg ? reg + aux_px * 6 : nullptr;
@@ -633,7 +639,7 @@ int forward_common(bsr_handle* h, const float* img, const float* uv, const float
     // CUDA graphs: a micro-batch whose buffers were seen before is captured once (on a private stream) and replayed
     // afterwards - one launch instead of ~50 (debug / profiling handles always launch kernel by kernel)
     if (!h->kn.no_graph && !h->debug_keep && !h->profile) {
-      GraphKey key{img + o3, uvp, regp, gsp, rgbp, m22p, difp, m, frame, share, h->in_small ? 1 : 0};
+      GraphKey key{img + o3, uvp, regp, gsp, rgbp, m22p, difp, m, frame, share, h->in_small ? 1 : (h->in_rows ? 2 : 0)};
       if (h->graphs.size() > 64 && !h->graphs.count(key)) clear_graphs(h);
       GraphEntry& ge = h->graphs[key];
       if (!ge.exec && ++ge.seen >= 2) {
@@ -701,8 +707,8 @@ HostSlots host_slots(int step, bool with_reg) {
 }
 struct SmallInputScope {      // forward_mb reads uv/reg as 32x32 maps only while a compact call is in flight
   bsr_handle* h;
-  SmallInputScope(bsr_handle* hh, bool on) : h(hh) { h->in_small = on; }
-  ~SmallInputScope() { h->in_small = false; }
+  SmallInputScope(bsr_handle* hh, bool small, bool rows) : h(hh) { h->in_small = small; h->in_rows = rows; }
+  ~SmallInputScope() { h->in_small = false; h->in_rows = false; }
 };
 
 int forward_host(bsr_handle* h, const float* img, const float* uv, const float* reg, int n, int frame, int share,
@@ -715,7 +721,9 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
   if (!compact && (cp.rgb_u8 || cp.dif_f16)) return fail(h, BSR_EINVAL, "compact outputs need the compact entry point");
   if (h->variant == BSR_VARIANT_TSM && !reg) return fail(h, BSR_EINVAL, "TSM needs reg");
   if (int rc = pending_device_error(h)) return rc;
-  SmallInputScope small_scope(h, compact);
+  // fp32 inputs: upload only the uv / reg rows the model reads (rows 8i+3, 8i+4: one strided 2-D DMA each)
+  const bool rows_only = !compact && !h->kn.host_full_uv;
+  SmallInputScope small_scope(h, compact, rows_only);
   DeviceScope dev_scope(h->device);
   if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
   // transfer/compute chunk of the pipelined host path: smaller than the device micro-batch so that PCIe copies and
@@ -788,8 +796,19 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
       if (reg) CK(h, cudaMemcpyAsync(c_reg, reg + q1 * 6, qm * 6, cudaMemcpyHostToDevice, s_in));
     } else {
       CK(h, cudaMemcpyAsync(d_img, img + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
-      CK(h, cudaMemcpyAsync(d_uv, uv + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
-      if (reg) CK(h, cudaMemcpyAsync(d_reg, reg + o1 * 6, pm * 6, cudaMemcpyHostToDevice, s_in));
+      if (rows_only) {
+        // source: bands of 8 image rows, of which rows 3 and 4 (contiguous) are copied; the band pitch is uniform
+        // across images (256 rows = 32 bands), so one 2-D copy covers the whole chunk
+        const size_t row3 = (size_t)IMG * 3 * sizeof(float), row6 = (size_t)IMG * 6 * sizeof(float);
+        CK(h, cudaMemcpy2DAsync(d_uv, 2 * row3, (const char*)(uv + o1 * 3) + 3 * row3, 8 * row3, 2 * row3, (size_t)m * FEAT,
+                                cudaMemcpyHostToDevice, s_in));
+        if (reg)
+          CK(h, cudaMemcpy2DAsync(d_reg, 2 * row6, (const char*)(reg + o1 * 6) + 3 * row6, 8 * row6, 2 * row6, (size_t)m * FEAT,
+                                  cudaMemcpyHostToDevice, s_in));
+      } else {
+        CK(h, cudaMemcpyAsync(d_uv, uv + o1 * 3, pm * 3, cudaMemcpyHostToDevice, s_in));
+        if (reg) CK(h, cudaMemcpyAsync(d_reg, reg + o1 * 6, pm * 6, cudaMemcpyHostToDevice, s_in));
+      }
     }
     CK(h, cudaEventRecord(h->ev_in[slot], s_in));
     CK(h, cudaStreamWaitEvent(s_c, h->ev_in[slot], 0));
@@ -917,6 +936,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.no_fuse_w = env_set("BSR_NO_FUSE_W");
   h->kn.host_chunk = env_int("BSR_HOST_CHUNK");
   h->kn.no_graph = env_set("BSR_NO_GRAPH");
+  h->kn.host_full_uv = env_set("BSR_HOST_FULL_UV");
   h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->kn.no_halo = env_set("BSR_NO_HALO");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;

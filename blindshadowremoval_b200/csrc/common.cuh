@@ -109,6 +109,7 @@ struct Knobs {
   int st_bufs = 0;         // BSR_ST_BUFS: force the number of staging buffers (1 / 2) where it fits
   int no_fuse_w = 0;       // BSR_NO_FUSE_W: NonLocal output conv as its own launch
   int host_chunk = 0;      // BSR_HOST_CHUNK: images per pipelined host-path chunk
+  int host_full_uv = 0;    // BSR_HOST_FULL_UV: the fp32 host path uploads uv / reg in full instead of the rows the model reads
   int no_graph = 0;        // BSR_NO_GRAPH: never replay micro-batches from captured CUDA graphs
   int no_halo = 0;         // BSR_NO_HALO: fused transposed convs fetch every shifted A tile separately (round-1 behaviour)
   int attn_v1 = 0;         // BSR_ATTN_V1=1: round-1 two-pass attention kernel with the fused output conv (A/B measurements)

@@ -67,6 +67,32 @@ __global__ void reg_small_kernel(const float* __restrict__ reg, float* __restric
   off[idx] = (v == v) ? v : 0.f;
 }
 
+// Host path: only image rows 8i+3 and 8i+4 of uv / reg ever reach the model (resize8 above), so the pipelined host path
+// uploads just those rows (one strided 2-D DMA, a quarter of the bytes): rows[n][32][2][256][C].  Same taps, same
+// operation order as resize8 -> bit-identical results.
+__device__ __forceinline__ float resize8_rows(const float* __restrict__ rows, int n, int i, int j, int C, int c) {
+  const float* b = rows + ((((size_t)n * FEAT + i) * 2) * IMG + (CELL * j + 3)) * C + c;
+  float top = b[0] * 0.5f + b[C] * 0.5f;
+  float bot = b[(size_t)IMG * C] * 0.5f + b[(size_t)IMG * C + C] * 0.5f;
+  return top * 0.5f + bot * 0.5f;
+}
+__global__ void uv_rows_small_kernel(const float* __restrict__ rows, float* __restrict__ uvs, int n_img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * FEAT * FEAT * 3) return;
+  int c = idx % 3, cell = idx / 3;
+  int j = cell % FEAT, i = (cell / FEAT) % FEAT, n = cell / (FEAT * FEAT);
+  uvs[idx] = resize8_rows(rows, n, i, j, 3, c);
+}
+__global__ void reg_rows_small_kernel(const float* __restrict__ rows, float* __restrict__ off, int n_img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * FEAT * FEAT * 4) return;
+  int k = idx & 3, cell = idx >> 2;
+  int j = cell % FEAT, i = (cell / FEAT) % FEAT, n = cell / (FEAT * FEAT);
+  int c = (k < 2) ? k : k + 1;          // channels 0,1,3,4
+  float v = resize8_rows(rows, n, i, j, 6, c) * (float)FEAT;
+  off[idx] = (v == v) ? v : 0.f;
+}
+
 // ---- compact host I/O -------------------------------------------------------
 // img_u8 -> fp32 `/ 255.` (dataset.py:119,159).  16 bytes in, 64 bytes out per thread; n16 = bytes/16.
 __global__ void expand_u8_kernel(const uint4* __restrict__ in, float4* __restrict__ out, long long n16) {
