@@ -380,11 +380,17 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        h2d = n_e * 256 * 256 * (6 + (6 if tsm else 0)) * 4
+        # bytes the host path really copies: the image in full, and of uv / reg the two rows of every 8-row band that the
+        # model reads (rows 8i+3, 8i+4: tf.image.resize to 32 x 32, model.py:237 / warp.py:137) - one strided 2-D DMA each
+        full_uv = bool(os.environ.get("BSR_HOST_FULL_UV"))
+        aux_rows = 256 if full_uv else 64
+        h2d = n_e * (256 * 256 * 3 + aux_rows * 256 * (3 + (6 if tsm else 0))) * 4
         d2h = n_e * 256 * 256 * 4 * 4
         e2e = {"value": round(n_e * world * k_e / tt.item(), 2), "unit": "images/s", "host_numa_binding": numa,
                "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e,
+               "host_buffers": "pinned fp32 img / uv%s in full on the host; uv%s uploaded as the 64 of 256 rows the model reads" % (
+                   ("/reg" if tsm else ""), ("/reg" if tsm else "")) if not full_uv else "pinned fp32, uploaded in full",
                "api": "Generator.__call__ host path -> bsr_forward_%s_host" % args.variant}
 
     # ---- e2e_compact: the same call fed with what the dataset really stores: uint8 images,
