@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // distance (in 16-byte units) between the weight rows of the two K blocks of a step
       const uint32_t b_kb_lo = b_resident ? (uint32_t)b_total_rows * 8u : (uint32_t)p.b_kb_rows * 8u;
       const bool tm = (ablate & 8) && blockIdx.x == 0 && leader;
-      long long t_wfull = 0, t_wtempty = 0, t_fence = 0, t_issue = 0, t_commit = 0;
+      long long t_wfull = 0, t_wtempty = 0, t_fence = 0, t_issue = 0, t_commit = 0, t_tcommit = 0, t_gap_s = 0, t_gap_t = 0, t_prev = 0;
       const long long t_start = BSR_CLK();
       if (b_resident) ok = mbar_wait(bar_bres, 0, p.errflag, 5);
       if (ok && p.zero_acc) ok = mbar_wait(bar_zero, 0, p.errflag, 6);      // both accumulator stages start out zeroed
@@ -357,15 +357,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t idesc_m = umma_idesc_h16(TC_BM, 0);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++tcount) {
         const long long tw0 = BSR_CLK();
+        if (tcount) t_gap_t += tw0 - t_prev;
         ok = mbar_wait(bar_tempty + 8 * as, aph ^ 1u, p.errflag, 4, true);
-        t_wtempty += BSR_CLK() - tw0;
+        const long long tw0b = BSR_CLK();
+        t_wtempty += tw0b - tw0;
         if (!ok) break;
         tc_fence_after();
+        t_prev = BSR_CLK();
+        t_fence += t_prev - tw0b;
         const uint32_t acc = tmem_base + as * (uint32_t)bn;
         const int brow_base = p.b_pinned ? 0 : (tile % n_tiles) * bn;
         for (int si = 0; si < n_steps; ++si, ++it) {
           const TcStep& sp = steps[si];
           const long long tw1 = BSR_CLK();
+          t_gap_s += tw1 - t_prev;
           ok = mbar_wait(bar_full + 8 * s, ph, p.errflag, 2, true);
           const long long tc0 = BSR_CLK();
           t_wfull += tc0 - tw1;
@@ -408,15 +413,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           t_issue += tc2 - tc1;
           if (leader) umma_commit(bar_empty + 8 * s);
           __syncwarp();
-          t_commit += BSR_CLK() - tc2;
+          t_prev = BSR_CLK();
+          t_commit += t_prev - tc2;
           if (++s == n_stages) { s = 0; ph ^= 1u; }
         }
+        const long long tt0 = BSR_CLK();
         if (leader) umma_commit(bar_tfull + 8 * as);
         __syncwarp();
+        t_prev = BSR_CLK();
+        t_tcommit += t_prev - tt0;
         if (++as == acc_stages) { as = 0; aph ^= 1u; }
       }
-      if (tm) { p.timers[12] = t_fence; p.timers[13] = t_issue; p.timers[14] = t_commit; }
-      if (tm) { p.timers[4] = BSR_CLK() - t_start; p.timers[5] = t_wfull; p.timers[6] = t_wtempty; p.timers[7] = t_res; p.timers[8] = tcount; }
+      if (tm) { p.timers[12] = (ablate & 16) ? t_gap_s : t_fence; p.timers[13] = t_issue; p.timers[14] = (ablate & 16) ? t_gap_t : t_commit; }
+      if (tm) { p.timers[4] = BSR_CLK() - t_start; p.timers[5] = t_wfull; p.timers[6] = t_wtempty; p.timers[7] = t_res + t_tcommit; p.timers[8] = tcount; }
     }
   } else {
     // ================= epilogue: 16 warps.  warp ew reads TMEM lanes 32*(warp%4).. (hardware rule) =================
@@ -642,35 +651,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         int col = cg * 16;
         if (!RES && p.n_groups == 4 && e.out_mode == OUT_T && vec32_ok && group_cols == 64 && e.out_c == 64 && bn == 256) {
           // Fused 4-phase transposed conv with 64 output channels whose stores cannot be staged (up3 / clr_up3: 144 KB of
-          // resident weights): this warp owns channels [16 cg, 16 cg + 16) of all four sub-pixel phases.  All four
-          // accumulator chunks are fetched with ONE TMEM round trip, the accumulators are released before the stores, and
-          // every chunk leaves as one 256-bit store.
+          // resident weights): this warp owns ALL 64 channels of ONE sub-pixel phase (accumulator columns [64 cg, 64 cg + 64)),
+          // i.e. one whole 128-byte output pixel per lane.  The four 16-column chunks are fetched with ONE TMEM round trip
+          // and the accumulators are released before the stores.  Every chunk leaves as one 256-bit store, and lane L stores
+          // chunk (j + L) % 4 in store j: a warp-wide store whose 32 lanes all write the SAME 32-byte slice of their
+          // (different) 128-byte lines costs 60 L1 data-pipe wavefronts, with the four slices spread over the lanes it costs
+          // 16 (tools/micro/store_pattern.cu, profiles/r2_store_pattern.txt) - and that pipe also feeds the MMA operands.
           float v[4][16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tmem_ld16_nowait(acc + (uint32_t)(cg * 16 + 64 * k), v[k]);
+          for (int k = 0; k < 4; ++k) tmem_ld16_nowait(acc + (uint32_t)(cg * 64 + 16 * k), v[k]);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-          const int cch = cg * 16;
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cch), b1 = *reinterpret_cast<const float4*>(bias_s + cch + 4),
-                       b2 = *reinterpret_cast<const float4*>(bias_s + cch + 8), b3 = *reinterpret_cast<const float4*>(bias_s + cch + 12);
-          const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+          const int phase = p.group_phase[cg];
+          const int oy = gyb * out_scale + (phase >> 1), ox = gx * out_scale + (phase & 1);
+          h16* const dst = (h16*)e.out + (((size_t)n * OH + oy) * OW + ox) * e.out_ld + e.out_coff;
+          uint32_t o[4][8];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int phase = p.group_phase[k];
-            const int oy = gyb * out_scale + (phase >> 1), ox = gx * out_scale + (phase & 1);
-            const size_t opix = ((size_t)n * OH + oy) * OW + ox;
-            uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float a0 = v[k][i] + bb[i], a1 = v[k][i + 1] + bb[i + 1];
-              if (e.act) { a0 = fmaxf(a0, kLeaky * a0); a1 = fmaxf(a1, kLeaky * a1); }
-              o[i >> 1] = pack_h16x2(a0, a1);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 16 * k + i);
+              float a0 = v[k][i] + b4.x, a1 = v[k][i + 1] + b4.y, a2 = v[k][i + 2] + b4.z, a3 = v[k][i + 3] + b4.w;
+              if (e.act) {
+                a0 = fmaxf(a0, kLeaky * a0); a1 = fmaxf(a1, kLeaky * a1);
+                a2 = fmaxf(a2, kLeaky * a2); a3 = fmaxf(a3, kLeaky * a3);
+              }
+              o[k][i >> 1] = pack_h16x2(a0, a1);
+              o[k][(i >> 1) + 1] = pack_h16x2(a2, a3);
             }
-            if (!(p.ablate & 1))
-              st_global_256((h16*)e.out + opix * e.out_ld + e.out_coff + cch, make_uint4(o[0], o[1], o[2], o[3]),
-                            make_uint4(o[4], o[5], o[6], o[7]));
+          }
+          // rotate the four chunks by (lane % 4) in two conditional stages: afterwards o[j] holds chunk (j + lane) % 4
+          const bool r1 = lane & 1, r2 = lane & 2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t t0 = o[0][i], t1 = o[1][i], t2 = o[2][i], t3 = o[3][i];
+            const uint32_t u0 = r1 ? t1 : t0, u1 = r1 ? t2 : t1, u2 = r1 ? t3 : t2, u3 = r1 ? t0 : t3;
+            o[0][i] = r2 ? u2 : u0; o[1][i] = r2 ? u3 : u1; o[2][i] = r2 ? u0 : u2; o[3][i] = r2 ? u1 : u3;
+          }
+          if (!(p.ablate & 1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_global_256(dst + 16 * ((j + lane) & 3), make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]),
+                            make_uint4(o[j][4], o[j][5], o[j][6], o[j][7]));
+          }
+          continue;
+        }
+        if (!RES && total_cols == 128 && p.n_groups == 1 && rows_per_tile == 1 && out_scale == 1 && !p.zero_acc && vec32_ok &&
+            e.out_mode != OUT_F32 && cbase + 128 <= e.out_c && (e.out_mode != OUT_QKV || cbase < 256 || e.v_natural)) {
+          // 128-column tiles with direct stores (the q / k / v conv): this warp owns the 32 columns [32 cg, 32 cg + 32) and lane
+          // L stores chunk (j + L) % 2 in store j, so the lanes of one warp-wide store write two different 32-byte slices of
+          // their lines instead of one (see the fused transposed-conv path above for the L1 data-pipe cost of the pattern).
+          float v[2][16];
+          tmem_ld16_nowait(acc + (uint32_t)(cg * 32), v[0]);
+          tmem_ld16_nowait(acc + (uint32_t)(cg * 32 + 16), v[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          const int c0 = cbase + cg * 32;
+          const size_t pix1 = ((size_t)n * OH + gyb) * OW + gx;
+          h16* const dst = e.out_mode == OUT_QKV ? (c0 >= 256 ? (h16*)e.out2 + pix1 * 128 + (c0 - 256) : (h16*)e.out + pix1 * 256 + c0)
+                                                 : (h16*)e.out + pix1 * e.out_ld + e.out_coff + c0;
+          uint32_t o[2][8];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 16 * k + i);
+              float a0 = v[k][i] + b4.x, a1 = v[k][i + 1] + b4.y, a2 = v[k][i + 2] + b4.z, a3 = v[k][i + 3] + b4.w;
+              if (e.act) {
+                a0 = fmaxf(a0, kLeaky * a0); a1 = fmaxf(a1, kLeaky * a1);
+                a2 = fmaxf(a2, kLeaky * a2); a3 = fmaxf(a3, kLeaky * a3);
+              }
+              o[k][i >> 1] = pack_h16x2(a0, a1);
+              o[k][(i >> 1) + 1] = pack_h16x2(a2, a3);
+            }
+          }
+          const bool r1 = lane & 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t t0 = o[0][i], t1 = o[1][i];
+            o[0][i] = r1 ? t1 : t0; o[1][i] = r1 ? t0 : t1;
+          }
+          if (!(p.ablate & 1)) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              st_global_256(dst + 16 * ((j + lane) & 1), make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]),
+                            make_uint4(o[j][4], o[j][5], o[j][6], o[j][7]));
           }
           continue;
         }

@@ -1,0 +1,35 @@
+"""-m gpu: compute-sanitizer over one small forward of every product kernel (GSC and TSM): synccheck (mbarrier / named
+barrier protocol of the warp-specialised kernels) and memcheck.  Skipped only when the tool is not installed."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(tool, variant):
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    env = dict(os.environ)
+    env.pop("BSR_DEBUG_KEEP", None)
+    cmd = [exe, "--tool", tool, "--print-limit", "5", sys.executable, os.path.join(ROOT, "tools", "profile_forward.py"), "2", variant]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    assert "launches per forward" in out, out[-2000:]
+    return out
+
+
+@pytest.mark.parametrize("variant", ["gsc", "tsm"])
+def test_synccheck_clean(variant):
+    out = _run("synccheck", variant)
+    assert "ERROR SUMMARY: 0 errors" in out, out[-3000:]
+
+
+def test_memcheck_clean():
+    out = _run("memcheck", "tsm")
+    assert "ERROR SUMMARY: 0 errors" in out, out[-3000:]

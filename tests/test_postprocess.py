@@ -149,3 +149,37 @@ def test_evaluate_ucb_config2_matches_oracle_pipeline():
     assert mism <= 0.002 * 8 * 65536
     assert abs(out["ssim"] - ref_ssim) < 2e-3 and abs(out["psnr"] - ref_psnr) < 0.05
     gen.close()
+
+
+@pytest.mark.gpu
+def test_device_postprocess_edge_cases_match_oracle():
+    """Inputs on which the reference raises (np.min / np.max of an empty array) follow the oracle's stated deviations: an
+    empty nose / mouth / eyebrow mask skips the rules that need its bounding box; a prediction with no connected
+    component gives an empty detected mask, i.e. the (resized, padded, clipped) input comes back."""
+    import torch
+    from blindshadowremoval_b200.generator import Generator
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a B200")
+    files = sorted(glob.glob(os.path.join(FIX, "UCB", "input", "*", "*.png")))
+    f, masks, size = _load_case(files[0])
+    rgb, dif = _synthetic_outputs(f, 3)
+    m1 = {k: (np.zeros_like(v) if k in ("nose", "mouth", "eyebrow") else v) for k, v in masks.items()}
+    cases = [(m1, rgb, dif, size),                               # no nose / mouth / eyebrow masks
+             (masks, rgb, np.full_like(dif, -0.5), size),        # nothing detected
+             (masks, rgb, dif, 256),                             # size 256: the resize is the identity, no padding
+             (masks, rgb, dif, 97)]                              # a small crop: most of the canvas is padding
+    refs = [PP.test_step_postprocess(f["img"], f["gt"], r, d, sz, m) for m, r, d, sz in cases]
+    t = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
+    n = len(cases)
+    mk = np.stack([np.stack([np.rint(m[k][..., 0]).astype(np.uint8) for k in PP.MASK_KINDS]) for m, _, _, _ in cases])
+    gen = Generator("gsc", "tc16", device=0, micro_batch=1, seed=1)
+    final, det, met = gen.postprocess_ucb(t(np.stack([f["img"]] * n)), t(np.stack([f["gt"]] * n)),
+                                          t(np.stack([c[1] for c in cases])), t(np.stack([c[2] for c in cases])),
+                                          t(np.asarray([c[3] for c in cases]), torch.int32), t(mk, torch.uint8))
+    final, det, met = final.cpu().numpy(), det.cpu().numpy(), met.cpu().numpy()
+    for i, r in enumerate(refs):
+        assert int((det[i] != r["detected"]).sum()) == 0, i
+        assert np.abs(final[i] - r["final"]).max() <= 1e-6, i
+        assert abs(met[i, 0] - r["ssim"]) < 2e-5 and abs(met[i, 1] - r["psnr"]) < 2e-4, (i, met[i], r["ssim"], r["psnr"])
+    assert det[1].sum() == 0
+    gen.close()

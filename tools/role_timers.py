@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["BSR_ABLATE"] = str(8 | int(os.environ.get("ABL", "0")))
 os.environ["BSR_DEBUG_KEEP"] = "1"
+os.environ["BSR_PROFILE"] = "1"          # per-launch CUDA-event times next to the cycle counters -> effective SM clock
 from blindshadowremoval_b200.generator import Generator  # noqa: E402
 from blindshadowremoval_b200.synthetic import make_inputs  # noqa: E402
 
@@ -17,9 +18,10 @@ LAUNCHES = open(os.path.join(ROOT, "profiles", "launch_names_gsc.txt")).read().s
 gen = Generator("gsc", "bf16", device=0, micro_batch=mb, seed=1234)
 d = make_inputs(mb, 0)
 img, uv = torch.from_numpy(d["img"]).cuda(), torch.from_numpy(d["uv"]).cuda()
-for _ in range(3):
+for _ in range(int(os.environ.get("REPS", "3"))):
     gen(img, uv, None, want=("con_rgb", "dif"))
 torch.cuda.synchronize()
+lt = gen.layer_times()
 t = gen.debug_read("timers").reshape(64, 16)
 names = dict(enumerate(LAUNCHES))           # launch index inside one forward (h->launches at launch time)
 ATT = {i for i, nm in names.items() if nm.endswith("attn+w")}
@@ -34,4 +36,6 @@ for i in range(64):
     print("%3d %-10s | %9d %9d %8d %5d | %9d %9d %9d %8d %4d | %9d %9d %4d" % (
         i, names.get(i, ""), t[i, 0], t[i, 1], t[i, 2], t[i, 3], t[i, 4], t[i, 5], t[i, 6], t[i, 7], t[i, 8], t[i, 9],
         t[i, 10], t[i, 11]))
-    print("      mma: fence %d issue %d commit %d | producer tma-issue %d" % (t[i, 12], t[i, 13], t[i, 14], t[i, 15]))
+    ms = lt[i][1] if i < len(lt) else 0.0
+    print("      mma: fence %d issue %d commit %d | producer tma-issue %d | %.4f ms (%s) -> %.0f MHz if CTA 0 spans the launch" % (
+        t[i, 12], t[i, 13], t[i, 14], t[i, 15], ms, lt[i][0] if i < len(lt) else "", max(t[i, 0], t[i, 4], t[i, 9]) / max(ms, 1e-9) / 1e3))
