@@ -52,7 +52,7 @@ constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MAX_STEPS = 64;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 // (the fp32 row-exchange buffers of round 1 are gone: horizontal taps are summed by warp shuffles)
-constexpr int CLR_NB = 64;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns, padded to 64 (TMEM alignment)
+constexpr int CLR_NB = 48;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns
 
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4, TC_PAIRX = 5 };
 enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
@@ -881,13 +881,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         epi_bar_slot(slot);
         float v[16];
+        // the neighbour warps' edge groups and the bias come as 128-bit shared-memory loads (one wavefront per four values)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float l = __shfl_up_sync(0xffffffffu, y0v[i], 1);            // Y[x-1][kw=0]
-          float rg = __shfl_down_sync(0xffffffffu, y2v[i], 1);         // Y[x+1][kw=2]
-          if (lane == 0) l = wr > 0 ? edge[(wr - 1) * 32 + i] : 0.f;
-          if (lane == 31) rg = wr < 7 ? edge[(wr + 1) * 32 + 16 + i] : 0.f;
-          v[i] = ((bias_s[i] + l) + y1v[i]) + rg;
+        for (int i = 0; i < 16; i += 4) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = t4;
+          if (lane == 0 && wr > 0) t4 = *reinterpret_cast<const float4*>(edge + (wr - 1) * 32 + i);
+          if (lane == 31 && wr < 7) u4 = *reinterpret_cast<const float4*>(edge + (wr + 1) * 32 + 16 + i);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + i);
+          const float el[4] = {t4.x, t4.y, t4.z, t4.w}, er[4] = {u4.x, u4.y, u4.z, u4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float l = __shfl_up_sync(0xffffffffu, y0v[i + k], 1);            // Y[x-1][kw=0]
+            float rg = __shfl_down_sync(0xffffffffu, y2v[i + k], 1);         // Y[x+1][kw=2]
+            if (lane == 0) l = el[k];
+            if (lane == 31) rg = er[k];
+            v[i + k] = ((bb[k] + l) + y1v[i + k]) + rg;
+          }
         }
         // the colour tail is bound by its instruction count (profiles/r2_role_timers_mb256_after.txt): packed FFMA2
 #pragma unroll
