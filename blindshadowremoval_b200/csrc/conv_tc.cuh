@@ -62,8 +62,10 @@ struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overw
 struct TcStep {
   int8_t dy, dx;           // A tile shift in input pixels
   int8_t n_mma;
-  int8_t n_a;              // 1: one A tile; 2: two 64-wide K blocks (A sub-tiles at a_c0, a_c0+64, same MMAs over both);
+  int8_t n_a;              // bits 0-2: 1: one A tile; 2: two 64-wide K blocks (A sub-tiles at a_c0, a_c0+64, same MMAs over both);
                            // 3: two input ROWS (A sub-tiles at dy, dy+1), each MMA names its sub-tile (TcMma.first bit 1)
+                           // bits 4-5: trailing 16-element K steps of the step's LAST K block that hold no input channel
+                           // (cin = 257 pads to 320: the fifth block is one K step, not four) and are not issued
   int16_t a_c0;            // A channel coordinate (elements)
   int16_t b_rows;          // weight rows fetched for this step
   int32_t b_k;             // weight K coordinate (elements)
@@ -310,8 +312,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (leader) {
             // n_a: 1 one A tile; 2 two K blocks (channels + 64); 3 two input rows; 4 two K blocks from x-neighbour tiles;
             // 5 the same from ONE 129-row halo tile (the second block is a view one row in)
-            const uint32_t rowmode = sp.n_a == 3, xmode = sp.n_a == 4, hmode = sp.n_a == 5,
-                           na = rowmode ? 1u : ((xmode || hmode) ? 2u : (uint32_t)sp.n_a), nsub = (sp.n_a >= 2 && !hmode) ? 2u : 1u;
+            const uint32_t amode = (uint32_t)sp.n_a & 7u;
+            const uint32_t rowmode = amode == 3, xmode = amode == 4, hmode = amode == 5,
+                           na = rowmode ? 1u : ((xmode || hmode) ? 2u : amode), nsub = (amode >= 2 && !hmode) ? 2u : 1u;
             const uint32_t bbytes = b_resident ? 0u : na * (uint32_t)sp.b_rows * 128u;
             if (ablate & 4) {
               mbar_expect_tx(bar_full + 8 * s, bbytes);
@@ -383,8 +386,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                          : sA + a_sub * a_bytes;
           const uint32_t a_lo = umma_desc_lo(sA), b_lo0 = umma_desc_lo(sB);
           const int nm = (ablate & 2) ? 0 : sp.n_mma;
-          const uint32_t na = sp.n_a >= 4 ? 2u : (uint32_t)sp.n_a;          // 4 / 5 = two K blocks whose A tiles are x-neighbours
-          if (leader) {
+          const uint32_t amode = (uint32_t)sp.n_a & 7u;
+          const uint32_t na = amode >= 4 ? 2u : amode;          // 4 / 5 = two K blocks whose A tiles are x-neighbours
+          // SKIP = false is the common program (all four K steps of every block); SKIP = true drops the all-padding K steps
+          // at the end of the step's last K block.  Two instantiations, selected once per step: the issue loop of the
+          // small-N layers is on the critical path and does not tolerate per-MMA conditionals (clr_conv1 +15 % with them).
+          auto issue = [&](auto skip_tag) {
+            constexpr bool SKIP = decltype(skip_tag)::value;
+            const uint32_t nk_last = SKIP ? 4u - (((uint32_t)sp.n_a >> 4) & 3u) : 4u, nk_first = na == 2 ? 4u : nk_last;
             for (int m = 0; m < nm; ++m) {
               const TcMma mm = sp.mma[m];
               const uint32_t b_lo = b_lo0 + (uint32_t)mm.brow * 8u;          // 128-byte rows, address >> 4
@@ -396,18 +405,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t voff = (mm.first & 4) ? 8u : 0u;
               const uint32_t a0 = a_lo + ((mm.first & 2) ? (a_bytes >> 4) : 0u) + voff;     // row mode: second input row
               umma_h16_lo(d, a0, b_lo, idesc, (mm.first & 1) ? 0u : 1u);
-              umma_h16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
-              umma_h16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
-              umma_h16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
+              if (!SKIP || nk_first > 1) umma_h16_lo(d, a0 + 2, b_lo + 2, idesc, 1u);
+              if (!SKIP || nk_first > 2) umma_h16_lo(d, a0 + 4, b_lo + 4, idesc, 1u);
+              if (!SKIP || nk_first > 3) umma_h16_lo(d, a0 + 6, b_lo + 6, idesc, 1u);
               if (na == 2) {       // second 64-wide K block of the step
                 // n_a = 5: the second K block is the x-neighbour pixel pair = the same halo tile one row further
-                const uint32_t a1 = a_lo + (sp.n_a == 5 ? 8u : (a_bytes >> 4)) + voff, b1 = b_lo + b_kb_lo;
+                const uint32_t a1 = a_lo + (amode == 5 ? 8u : (a_bytes >> 4)) + voff, b1 = b_lo + b_kb_lo;
                 umma_h16_lo(d, a1, b1, idesc, 1u);
-                umma_h16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
-                umma_h16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
-                umma_h16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
+                if (!SKIP || nk_last > 1) umma_h16_lo(d, a1 + 2, b1 + 2, idesc, 1u);
+                if (!SKIP || nk_last > 2) umma_h16_lo(d, a1 + 4, b1 + 4, idesc, 1u);
+                if (!SKIP || nk_last > 3) umma_h16_lo(d, a1 + 6, b1 + 6, idesc, 1u);
               }
             }
+          };
+          if (leader) {
+            if ((uint32_t)sp.n_a >> 4) issue(std::true_type{});
+            else issue(std::false_type{});
           }
           const long long tc2 = BSR_CLK();
           t_issue += tc2 - tc1;
@@ -994,7 +1007,7 @@ inline bool tc_upload(TmaEncoder& tma, TcWeights& t, const std::vector<uint16_t>
   uint64_t dims[2] = {K, rows}, strides[1] = {K * 2};
   uint32_t box[2] = {TC_BK, (uint32_t)t.b_box_rows};
   if (!tma.encode_h16(&t.map, t.dev, 2, dims, strides, box, nullptr)) { *why = tma.last_error; return false; }
-  for (int i = 0; i < TC_MAX_STEPS; ++i) if (t.steps[i].n_a == 0) t.steps[i].n_a = 1;
+  for (int i = 0; i < TC_MAX_STEPS; ++i) if ((t.steps[i].n_a & 7) == 0) t.steps[i].n_a |= 1;
   if (cudaMalloc(&t.steps_dev, sizeof t.steps) != cudaSuccess) { *why = "cudaMalloc failed"; return false; }
   if (cudaMemcpy(t.steps_dev, t.steps, sizeof t.steps, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy failed"; return false; }
   t.b_total_rows = (int)rows;
@@ -1164,6 +1177,8 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
 
   t.cin_pad = (cin + 63) / 64 * 64;
   const int ncb = t.cin_pad / 64;
+  // whole 16-element K steps at the end of the last K block that hold only padding: not issued (TcStep.n_a bits 4-5)
+  const int kskip = getenv("BSR_NO_KSKIP") ? 0 : (t.cin_pad - cin) / 16;
   if (transposed && cout % 16 == 0 && cout <= 96 && 4 * ncb <= TC_MAX_STEPS && !tc_disabled("convt_fused")) {
     // fused 4-phase transposed conv
     if (kh != 3 || kw != 3) { *why = "transposed conv must be 3x3"; return false; }
@@ -1189,7 +1204,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       const int16_t f = (int16_t)(cb == 0);
       TcStep s;
       memset(&s, 0, sizeof s);
-      s.a_c0 = (int16_t)(cb * 64); s.b_k = cb * 64; s.n_a = (int8_t)na;
+      s.a_c0 = (int16_t)(cb * 64); s.b_k = cb * 64; s.n_a = (int8_t)(na | (cb + na == ncb ? kskip << 4 : 0));
       if (na == 2) t.a_sub = 2;
       // shift (0,0): all four phases
       s.dy = 0; s.dx = 0; s.b_row = 0; s.b_rows = (int16_t)(4 * co);
@@ -1220,7 +1235,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       memset(t.steps_halo, 0, sizeof t.steps_halo);
       for (int r = 0; r < 2; ++r) {
         TcStep& h = t.steps_halo[r];
-        h.dy = (int8_t)(-r); h.dx = -1; h.a_c0 = 0; h.b_k = 0; h.n_a = 2; h.n_mma = 2;
+        h.dy = (int8_t)(-r); h.dx = -1; h.a_c0 = 0; h.b_k = 0; h.n_a = (int8_t)(2 | (kskip << 4)); h.n_mma = 2;
         if (r == 0) {
           h.b_row = 0; h.b_rows = (int16_t)(6 * co);
           h.mma[0] = TcMma{0, (int16_t)(4 * co), 0, (int16_t)(1 | 4)};                 // shift (0,0): all four phases, view + 1
@@ -1299,7 +1314,8 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       const int na = (pair_k && ncb - cb >= 2) ? 2 : 1;
       TcStep& s = t.steps[ns];
       s.dy = (int8_t)(tap / kw); s.dx = (int8_t)(tap % kw);        // SAME-padding offset subtracted at launch
-      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (tap * ncb + cb) * 64; s.b_row = 0; s.n_a = (int8_t)na;
+      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (tap * ncb + cb) * 64; s.b_row = 0;
+      s.n_a = (int8_t)(na | (cb + na == ncb ? kskip << 4 : 0));
       s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
       if (na == 2) t.a_sub = 2;
       ++ns;
@@ -1320,6 +1336,7 @@ inline bool pack_tc_weights_phase(TmaEncoder& tma, int phase, int cin, int cout,
   t.kind = TC_CONV; t.kh = 3; t.kw = 3; t.cin = cin; t.cout = cout; t.transposed = 1;
   t.cin_pad = (cin + 63) / 64 * 64;
   const int ncb = t.cin_pad / 64, py = phase >> 1, px = phase & 1;
+  const int kskip = getenv("BSR_NO_KSKIP") ? 0 : (t.cin_pad - cin) / 16;          // see pack_tc_weights
   t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1; t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
   std::vector<int> taps;
   for (int a = py; a < 3; a += 2)
@@ -1337,7 +1354,8 @@ inline bool pack_tc_weights_phase(TmaEncoder& tma, int phase, int cin, int cout,
       const int na = (!getenv("BSR_NO_KPAIR") && ncb - cb >= 2) ? 2 : 1;
       TcStep& s = t.steps[ns];
       s.dy = (int8_t)(-((tap / 3) >> 1)); s.dx = (int8_t)(-((tap % 3) >> 1));
-      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (int)((ti * ncb + cb) * 64); s.b_row = 0; s.n_a = (int8_t)na;
+      s.a_c0 = (int16_t)(cb * 64); s.b_rows = (int16_t)t.bn; s.b_k = (int)((ti * ncb + cb) * 64); s.b_row = 0;
+      s.n_a = (int8_t)(na | (cb + na == ncb ? kskip << 4 : 0));
       s.n_mma = 1; s.mma[0] = TcMma{0, (int16_t)t.bn, 0, (int16_t)(ns == 0)};
       if (na == 2) t.a_sub = 2;
       ++ns;

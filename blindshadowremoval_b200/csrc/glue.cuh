@@ -225,7 +225,17 @@ __global__ void hole_kernel(const float* __restrict__ difgs, const T* __restrict
   float keep = 1.f - bm;
   const T* src = xa + (size_t)cell * lda;
   T* dst = xb + (size_t)cell * ldb;
-  for (int c = lane; c < cx; c += 32) stf<T>(dst, c, ldf<T>(src, c) * keep);
+  int c_done = 0;
+  if (sizeof(T) == 2 && (lda & 7) == 0 && (ldb & 7) == 0) {
+    // 16-bit storage: 8 channels (16 bytes) per lane and step; keep is 0 or 1, so the product is a select
+    c_done = cx & ~7;
+    for (int c = lane * 8; c < c_done; c += 256) {
+      uint4 v = *reinterpret_cast<const uint4*>(src + c);
+      if (bm != 0.f) v = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(dst + c) = v;
+    }
+  }
+  for (int c = c_done + lane; c < cx; c += 32) stf<T>(dst, c, ldf<T>(src, c) * keep);
   if (lane == 0) {
     stf<T>(dst, cx, bm);
     bmask_out[cell] = bm;
