@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "conv_direct.cuh"
 #include "conv_tc.cuh"
+#include "conv3x3_halo.cuh"
 #include "glue.cuh"
 #include "postprocess.cuh"
 
@@ -116,6 +117,7 @@ namespace {
 int configure_tc_kernels() {
   if (int r = configure_tc_kernels_conv()) return r;
   if (int r = configure_tc_kernels_attn_fa()) return r;
+  if (!configure_conv3x3_halo()) return -9;
   return configure_tc_kernels_attn();
 }
 
@@ -239,6 +241,15 @@ int run_conv(bsr_handle* h, cudaStream_t st, ConvCall c, int n) {
     return BSR_OK;
   }
   const bool special = L.tc.ready && (L.tc.kind == TC_HEADS || L.tc.kind == TC_CLR);
+  if (!h->force_direct && L.tc.ready && !c.in_f32 && !h->kn.no_halo3 &&
+      conv3x3_halo_ok(L.tc, c.in_ld, c.in_coff, c.H, c.W, c.stride, c.e)) {
+    // 3x3 / stride 1, 128 -> 128 channels (res conv2): one halo tile per K block instead of nine shifted A tiles
+    int rc = launch_conv3x3_halo(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, n, c.e, h->num_sms, h->errflag, st,
+                                 &h->launches, h->kn);
+    if (rc != 0) return fail(h, BSR_ECUDA, "halo conv %s: launch failed (%d): %s", c.layer, rc, h->tma.last_error.c_str());
+    h->pc.halo3++;
+    return BSR_OK;
+  }
   if (!h->force_direct && L.tc.ready && !c.in_f32 && (!special || c.x.gs_f32 != nullptr)) {
     int rc = launch_conv_tc(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, c.x, -1, h->num_sms,
                             h->errflag, st, &h->launches, h->kn, &h->pc);
@@ -837,7 +848,7 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
     }
     total_launches += h->launches + extra_launches;
     pc_total.resident += h->pc.resident; pc_total.pinned += h->pc.pinned; pc_total.staged += h->pc.staged;
-    pc_total.attn_fused += h->pc.attn_fused; pc_total.graph_replays += h->pc.graph_replays;
+    pc_total.attn_fused += h->pc.attn_fused; pc_total.graph_replays += h->pc.graph_replays; pc_total.halo3 += h->pc.halo3;
     CK(h, cudaEventRecord(h->ev_comp[slot], s_c));
     CK(h, cudaStreamWaitEvent(s_out, h->ev_comp[slot], 0));
     if (gs) CK(h, cudaMemcpyAsync(gs + o1, d_gs, pm, cudaMemcpyDeviceToHost, s_out));
@@ -939,6 +950,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.host_full_uv = env_set("BSR_HOST_FULL_UV");
   h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->kn.no_halo = env_set("BSR_NO_HALO");
+  h->kn.no_halo3 = env_set("BSR_NO_HALO3");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
   h->ld1 = pad16(h->c_first > 257 ? h->c_first : 257);
@@ -1231,7 +1243,7 @@ int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int 
     caller_glue_kernel<<<(unsigned)((mpx + 255) / 256), 256, 0, st>>>(rgb_o, mp_o, d_face, rgb_o, mp_o, mpx);   // in place
     total += h->launches + 2;
     pc_total.resident += h->pc.resident; pc_total.pinned += h->pc.pinned; pc_total.staged += h->pc.staged;
-    pc_total.attn_fused += h->pc.attn_fused; pc_total.graph_replays += h->pc.graph_replays;
+    pc_total.attn_fused += h->pc.attn_fused; pc_total.graph_replays += h->pc.graph_replays; pc_total.halo3 += h->pc.halo3;
   }
   CK(h, cudaGetLastError());
   h->launches = total;
@@ -1366,6 +1378,7 @@ int bsr_plan_counter(const bsr_handle* h, int which) {
     case 2: return h->pc.staged;
     case 3: return h->pc.attn_fused;
     case 4: return h->pc.graph_replays;
+    case 5: return h->pc.halo3;
     default: return 0;
   }
 }

@@ -112,10 +112,11 @@ struct Knobs {
   int host_full_uv = 0;    // BSR_HOST_FULL_UV: the fp32 host path uploads uv / reg in full instead of the rows the model reads
   int no_graph = 0;        // BSR_NO_GRAPH: never replay micro-batches from captured CUDA graphs
   int no_halo = 0;         // BSR_NO_HALO: fused transposed convs fetch every shifted A tile separately (round-1 behaviour)
+  int no_halo3 = 0;        // BSR_NO_HALO3: res conv2 on the generic kernel (nine shifted A tiles) instead of conv3x3_halo.cuh
   int attn_v1 = 0;         // BSR_ATTN_V1=1: round-1 two-pass attention kernel with the fused output conv (A/B measurements)
 };
 // Launch-plan counters of one forward (bsr_plan_counter).
-struct PlanCounters { int resident = 0, pinned = 0, staged = 0, attn_fused = 0, graph_replays = 0; };
+struct PlanCounters { int resident = 0, pinned = 0, staged = 0, attn_fused = 0, graph_replays = 0, halo3 = 0; };
 
 enum OutMode : int {
   OUT_T = 0,     // activation type T, NHWC at out[pix*out_ld + out_coff + c]

@@ -880,6 +880,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tmem_ld16_nowait(ta + 16u, y1v);
           tmem_ld16_nowait(ta + 32u, y2v);
           tmem_ld_wait();
+          if (p.zero_acc) {          // leave the group zeroed for the next tile's all-accumulate program
+            tmem_zero16(ta);
+            tmem_zero16(ta + 16u);
+            tmem_zero16(ta + 32u);
+            tmem_wait_st();
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -1155,6 +1161,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
     const int R = 2, nb = CLR_NB;
     t.kind = TC_CLR; t.cin_pad = 64; t.bn = R * 2 * nb; t.n_tiles = 1; t.b_box_rows = nb; t.b_stage_rows = 0;
     t.b_resident = 1; t.rows_per_tile = R; t.halves = 2; t.tile_w = 128;
+    t.zero_acc = getenv("BSR_NO_ZERO_ACC") ? 0 : 1;          // 4 MMA groups per half tile instead of 5 (see heads)
     const size_t K = 64, rows = 3 * (size_t)nb;
     std::vector<uint16_t> host(rows * K, 0);
     for (int a = 0; a < 3; ++a)
@@ -1168,7 +1175,7 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
       for (int j = 0; j < R + 2; j += rpair ? 2 : 1) {
         TcStep& sp = t.steps[ns++];
         sp.dy = (int8_t)(j - 1); sp.dx = 0; sp.a_x0 = (int16_t)(hh * 128); sp.a_c0 = 0;
-        tc_rows_step(sp, j, R, 3, nb, hh * R, rpair);
+        tc_rows_step(sp, j, R, 3, nb, hh * R, rpair, t.zero_acc != 0);
       }
     t.n_steps = ns;
     (void)bias;

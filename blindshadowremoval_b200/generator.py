@@ -25,7 +25,7 @@ LIB_PATH = os.path.join(_HERE, "libbsr.so")
 # aliases of it ('bf16' is the name round 1 used and north_star's wording), 'fp32check' the CUDA-core check mode.
 PRECISIONS = ("tc16", "fp32check")
 _PRECISION_ALIASES = {"bf16": "tc16", "f16": "tc16", "fp16": "tc16"}
-PLAN_COUNTERS = ("resident", "pinned", "staged", "attn_fused", "graph_replays")
+PLAN_COUNTERS = ("resident", "pinned", "staged", "attn_fused", "graph_replays", "halo3")
 IMG = 256
 FEAT = 32
 

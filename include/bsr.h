@@ -166,7 +166,8 @@ int bsr_check(bsr_handle* h);
 int bsr_launch_count(const bsr_handle* h);          /* kernels launched by the last forward call */
 /* Launch-plan counters of the last forward (tests assert that the benchmarked code paths really ran):
  * which = 0: conv launches with resident weights, 1: with per-CTA pinned weights (qkv), 2: staged TMA-store epilogues,
- * 3: fused attention+w launches, 4: micro-batches replayed from a captured CUDA graph. */
+ * 3: fused attention+w launches, 4: micro-batches replayed from a captured CUDA graph, 5: 3x3 convs run on the halo-tile
+ * kernel (res conv2). */
 int bsr_plan_counter(const bsr_handle* h, int which);
 size_t bsr_workspace_bytes(const bsr_handle* h);
 /* Copy a named intermediate of the LAST micro-batch to host as fp32 (dense NHWC, logical channels).

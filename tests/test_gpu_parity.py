@@ -427,7 +427,7 @@ def test_benchmark_configuration_gsc_256_images_mb128_matches_oracle(G):
     """BASELINE config 4 exactly as bench.py runs it: n = 256, micro_batch = 128, device path and host path.  The second
     micro-batch repeats the first, so (i) both must agree bit for bit, (ii) 16 images sampled from the last micro-batch
     (whose hole mask the handle keeps) are compared with the oracle, (iii) the launch plan must really have used the
-    large-batch code paths (per-CTA pinned qkv weights, resident weights, staged TMA-store epilogues)."""
+    large-batch code paths (per-CTA pinned qkv weights, resident weights, staged TMA-store epilogues, halo-tile conv2)."""
     w, _ = case("gsc", 2, 1)
     base = make_inputs(128, seed=21, with_reg=True)
     d = {k: np.concatenate([v, v]) for k, v in base.items()}
@@ -437,6 +437,7 @@ def test_benchmark_configuration_gsc_256_images_mb128_matches_oracle(G):
     gen.check()
     pc = gen.plan_counters()
     assert pc["pinned"] >= 12 and pc["resident"] >= 12 and pc["staged"] >= 8 and pc["attn_fused"] == 12, pc
+    assert pc["halo3"] == 12, pc                  # every res conv2 ran on the halo-tile kernel (conv3x3_halo.cuh)
     got = dict(zip(("gs", "con_rgb", "mask22", "dif"), (o.cpu().numpy() for o in out)))
     for k, v in got.items():
         assert np.array_equal(v[:128], v[128:]), k                      # micro-batch 0 == micro-batch 1
