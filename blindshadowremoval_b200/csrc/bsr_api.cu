@@ -23,6 +23,7 @@
 #include "conv_direct.cuh"
 #include "conv_tc.cuh"
 #include "conv3x3_halo.cuh"
+#include "convt_halo.cuh"
 #include "glue.cuh"
 #include "postprocess.cuh"
 
@@ -41,6 +42,8 @@ struct Layer {
   TcWeights tc;                        // h16 K-major packing + step program + tensor map (conv_tc.cuh)
   TcWeights tc_phase[4];               // wide transposed convs: one plain gather conv per sub-pixel phase
   bool phases_ready = false;
+  TcWeights tc_halo;                   // the same layers packed for the fused halo kernel (convt_halo.cuh)
+  bool halo_ready = false;
 };
 
 struct DebugBuf { float* dev = nullptr; size_t n = 0; };
@@ -118,6 +121,7 @@ int configure_tc_kernels() {
   if (int r = configure_tc_kernels_conv()) return r;
   if (int r = configure_tc_kernels_attn_fa()) return r;
   if (!configure_conv3x3_halo()) return -9;
+  if (!configure_convt_halo()) return -10;
   return configure_tc_kernels_attn();
 }
 
@@ -250,11 +254,28 @@ int run_conv(bsr_handle* h, cudaStream_t st, ConvCall c, int n) {
     h->pc.halo3++;
     return BSR_OK;
   }
+  if (!h->force_direct && L.tc.ready && !c.in_f32 && !h->kn.no_halo3 && convt_halo_ok(L.tc, c.in_ld, c.in_coff, c.H, c.W, c.e)) {
+    // fused 4-phase transposed conv with streamed weights (up1, up2, clr_up2): one 17x9-pixel halo tile per K block
+    int rc = launch_convt_halo(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, n, c.e, h->num_sms, h->errflag, st,
+                               &h->launches, h->kn);
+    if (rc != 0) return fail(h, BSR_ECUDA, "halo transposed conv %s: launch failed (%d): %s", c.layer, rc, h->tma.last_error.c_str());
+    h->pc.halo3++;
+    return BSR_OK;
+  }
   if (!h->force_direct && L.tc.ready && !c.in_f32 && (!special || c.x.gs_f32 != nullptr)) {
     int rc = launch_conv_tc(h->tma, L.tc, c.in, c.in_ld, c.in_coff, c.H, c.W, c.stride, n, c.e, c.x, -1, h->num_sms,
                             h->errflag, st, &h->launches, h->kn, &h->pc);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core conv %s: launch failed (%d): %s", c.layer, rc,
                              h->tma.last_error.c_str());
+    return BSR_OK;
+  }
+  if (!h->force_direct && L.halo_ready && !c.in_f32 && !h->kn.no_halo3 &&
+      convt_halo_ok(L.tc_halo, c.in_ld, c.in_coff, c.H, c.W, c.e)) {
+    // wide transposed conv (clr_up1): ONE fused launch on halo tiles instead of one gather conv per sub-pixel phase
+    int rc = launch_convt_halo(h->tma, L.tc_halo, c.in, c.in_ld, c.in_coff, c.H, c.W, n, c.e, h->num_sms, h->errflag, st,
+                               &h->launches, h->kn);
+    if (rc != 0) return fail(h, BSR_ECUDA, "halo transposed conv %s: launch failed (%d): %s", c.layer, rc, h->tma.last_error.c_str());
+    h->pc.halo3++;
     return BSR_OK;
   }
   if (!h->force_direct && L.phases_ready && !c.in_f32) {
@@ -1040,6 +1061,7 @@ int bsr_destroy(bsr_handle* h) {
     if (kv.second.b_dev) cudaFree(kv.second.b_dev);
     kv.second.tc.release();
     for (auto& tp : kv.second.tc_phase) tp.release();
+    kv.second.tc_halo.release();
   }
   for (auto& kv : h->dbg) if (kv.second.dev) cudaFree(kv.second.dev);
   for (auto& e : h->ev) cudaEventDestroy(e);
@@ -1098,6 +1120,7 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
     CK(h, cudaMemcpy(L.b_dev, bp.data(), bn * 4, cudaMemcpyHostToDevice));
     for (auto& tp : L.tc_phase) tp.release();
     L.phases_ready = false;
+    L.halo_ready = false;
     if (h->precision == BSR_PRECISION_BF16) {
       std::string why;
       if (!pack_tc_weights(h->tma, L.name, L.kh, L.kw, L.cin, L.cout, L.transposed, L.w_host, L.b_host, &L.tc, &why)) {
@@ -1108,6 +1131,12 @@ int bsr_load_weights(bsr_handle* h, const void* blob, size_t nbytes) {
             ok = pack_tc_weights_phase(h->tma, ph, L.cin, L.cout, L.w_host, &L.tc_phase[ph], &why);
           if (!ok) return fail(h, BSR_ECUDA, "packing %s (per phase) failed: %s", en.name, why.c_str());
           L.phases_ready = true;
+          if (L.kh == 3 && L.kw == 3 && L.cout % 16 == 0 && 4 * L.cout <= 512) {
+            L.tc_halo.release();
+            if (!pack_convt_halo_weights(h->tma, L.cin, L.cout, L.w_host, &L.tc_halo, &why))
+              return fail(h, BSR_ECUDA, "packing %s (fused, halo kernel) failed: %s", en.name, why.c_str());
+            L.halo_ready = true;
+          }
         }
       }
     }

@@ -24,7 +24,7 @@ for key, a in sorted(rows.items(), key=lambda kv: -kv[1]["ms"]):
     src = a["src"]
     lk = alias.get(src, src.replace("res", "r") if src.startswith("res") else src)
     ent = tj["layers"].get(lk) or tj["layers"].get(lk.replace("r0", "r1"))
-    if src == "clr_up1":
+    if src == "clr_up1" and "clr_up1" not in tj["layers"]:      # captures from before the fused halo kernel: 4 phase launches
         b = sum(tj["layers"].get("clr_up1.p%d" % i, {"dram_bytes": 0})["dram_bytes"] for i in range(4))
         ent = {"dram_bytes": b}
     mb = "%.2f" % (ent["dram_bytes"] / tj["images_per_launch"] / 1e6) if ent else "-"
