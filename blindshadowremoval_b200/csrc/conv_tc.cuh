@@ -55,7 +55,7 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 constexpr int CLR_NB = 48;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns
 
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4, TC_PAIRX = 5 };
-enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2 };
+enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2, EPI_PLAIN = 3 };
 
 struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overwrite (first tap), bit 1 = A sub-tile,
                                                          // bit 2 = A view starts one pixel row (128 B) into the tile (halo tiles)
@@ -770,6 +770,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      } else if (EPI == EPI_PLAIN) {
+        // Lean direct-store epilogue for plain convs (selected by launch_conv_tc: no residual, one column group, 16-channel
+        // aligned h16 output).  Its own kernel instantiation, so its registers do not compete with the general paths.
+        const int bw = p.bw, bh = p.bh, out_scale = p.out_scale;
+        const int gyb = (tr / p.tiles_x) * bh * rows_per_tile + r / bw, gx = (tr % p.tiles_x) * bw + r % bw;
+        const int cbase = ntile * bn, total_cols = p.group_cols;
+        ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        if (!ok) break;
+        tc_fence_after();
+        {
+          // plain convs with direct stores (res conv3: two 144-column tiles): this warp's chunks cg, cg + 4, ... (at most four)
+          // come two per TMEM round trip, the accumulators are released before the last stores, the addressing is hoisted -
+          // the general chunk loop below costs ~200 instructions per chunk and made conv3 epilogue-issue bound (ncu: 52 %
+          // issue utilisation with the MMA warp waiting 43 % of the time for TMEM).
+          const int phase = p.group_phase[0];
+          const size_t pix1 = ((size_t)n * OH + gyb * out_scale + (phase >> 1)) * OW + gx * out_scale + (phase & 1);
+          h16* const dst = (h16*)e.out + pix1 * e.out_ld + e.out_coff + cbase + cg * 16;
+          const float* const b0 = bias_s + cbase + cg * 16;
+          const int lim = e.out_c - cbase - 16;          // a chunk is live while its first column is <= lim
+#pragma unroll 1
+          for (int k0 = 0; k0 < 4; k0 += 2) {            // two chunks per TMEM round trip (four would spill)
+            const int c0 = cg * 16 + 64 * k0, c1 = c0 + 64;
+            const bool on0 = c0 < total_cols && c0 <= lim, on1 = c1 < total_cols && c1 <= lim;
+            float v[2][16];
+            if (on0) tmem_ld16_nowait(acc + (uint32_t)c0, v[0]);
+            if (on1) tmem_ld16_nowait(acc + (uint32_t)c1, v[1]);
+            tmem_ld_wait();
+            if (k0 == 2) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (!(k ? on1 : on0)) continue;
+              const float* bk = b0 + 64 * (k0 + k);
+              uint32_t o[8];
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bk + i);
+                float a0 = v[k][i] + b4.x, a1 = v[k][i + 1] + b4.y, a2 = v[k][i + 2] + b4.z, a3 = v[k][i + 3] + b4.w;
+                if (e.act) {
+                  a0 = fmaxf(a0, kLeaky * a0); a1 = fmaxf(a1, kLeaky * a1);
+                  a2 = fmaxf(a2, kLeaky * a2); a3 = fmaxf(a3, kLeaky * a3);
+                }
+                o[i >> 1] = pack_h16x2(a0, a1);
+                o[(i >> 1) + 1] = pack_h16x2(a2, a3);
+              }
+              if (!(p.ablate & 1))
+                st_global_256(dst + 64 * (k0 + k), make_uint4(o[0], o[1], o[2], o[3]), make_uint4(o[4], o[5], o[6], o[7]));
+            }
+          }
+        }
       } else if (EPI == EPI_HEADS) {
         // tile = R image rows of 256 pixels; accumulator group (half, row rr) = 16 columns [kw*2 + o] holding the
         // vertical 7x1 partial sums Y[x][kw][o];  out[x][o] = sum_kw Y[x+kw-3][kw][o] (zero outside the row)
@@ -978,6 +1031,7 @@ inline int configure_tc_kernels_conv() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_HEADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_CLR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -1492,6 +1546,11 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       if ((bufs == 1 || bufs == 2) && (max_smem - fixed_bytes - need) / p.stage_bytes >= 2) { p.st_chunk = 16; p.st_bufs = bufs; staging = need; }
     }
   }
+  // lean direct-store epilogue (its own instantiation) for plain convs the staged epilogue does not take: res conv3
+  if (p.epi_mode == EPI_GENERIC && !p.st_chunk && e.res1 == nullptr && e.res2 == nullptr && e.out_mode == OUT_T &&
+      p.n_groups == 1 && t.rows_per_tile == 1 && !t.zero_acc && p.group_cols <= 256 && p.group_cols != 128 &&
+      e.out_ld % 16 == 0 && e.out_coff % 16 == 0 && e.out_c % 16 == 0 && !getenv("BSR_NO_PLAIN_EPI"))
+    p.epi_mode = EPI_PLAIN;
   p.n_stages = std::min(8, (max_smem - fixed_bytes - staging) / p.stage_bytes);
   if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }
   p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
@@ -1558,6 +1617,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   cudaError_t le;
   if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x, cw, *omap);
   else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x, cw, *omap);
+  else if (p.epi_mode == EPI_PLAIN) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_PLAIN, false>, it->second, t.map, p, e, x, cw, *omap);
   else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x, cw, *omap);
   else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x, cw, *omap);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }
