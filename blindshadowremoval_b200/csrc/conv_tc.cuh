@@ -55,7 +55,7 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 constexpr int CLR_NB = 48;         // clr_conv1 accumulator group: 3 kw x 16 couts = 48 columns
 
 enum TcKind : int { TC_CONV = 0, TC_CONVT_FUSED = 1, TC_ROWPACK = 2, TC_HEADS = 3, TC_CLR = 4, TC_PAIRX = 5 };
-enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2, EPI_PLAIN = 3 };
+enum TcEpi : int { EPI_GENERIC = 0, EPI_HEADS = 1, EPI_CLR = 2, EPI_PLAIN = 3, EPI_QKV = 4 };
 
 struct TcMma { int16_t col, n, brow; int16_t first; };   // first: bit 0 = overwrite (first tap), bit 1 = A sub-tile,
                                                          // bit 2 = A view starts one pixel row (128 B) into the tile (halo tiles)
@@ -770,6 +770,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      } else if (EPI == EPI_QKV) {
+        // q / k / v projection (OUT_QKV, natural V) in two 192-column tiles; its own instantiation like EPI_PLAIN
+        const int bw = p.bw, bh = p.bh;
+        const int gyb = (tr / p.tiles_x) * bh * rows_per_tile + r / bw, gx = (tr % p.tiles_x) * bw + r % bw;
+        const int cbase = ntile * bn;
+        ok = mbar_wait(bar_tfull + 8 * as, aph, p.errflag, 3);
+        if (!ok) break;
+        tc_fence_after();
+        {
+          // q / k / v projection in two 192-column tiles: this warp owns 48 columns = three 16-channel chunks, fetched with
+          // one TMEM round trip.  Lane L stores chunk (j + L) % 3 in store j: theta|phi pixels are 512 bytes and g pixels
+          // 256 bytes apart, so without the rotation all 32 lanes of a store would hit the same 32-byte slice of their lines.
+          const int c0 = cbase + 48 * cg;
+          float v[3][16];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) tmem_ld16_nowait(acc + (uint32_t)(48 * cg + 16 * k), v[k]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+          uint32_t o[3][8];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 16 * k + i);
+              float a0 = v[k][i] + b4.x, a1 = v[k][i + 1] + b4.y, a2 = v[k][i + 2] + b4.z, a3 = v[k][i + 3] + b4.w;
+              if (e.act) {
+                a0 = fmaxf(a0, kLeaky * a0); a1 = fmaxf(a1, kLeaky * a1);
+                a2 = fmaxf(a2, kLeaky * a2); a3 = fmaxf(a3, kLeaky * a3);
+              }
+              o[k][i >> 1] = pack_h16x2(a0, a1);
+              o[k][(i >> 1) + 1] = pack_h16x2(a2, a3);
+            }
+          }
+          const int r3 = lane % 3;
+          const bool z0 = r3 == 0, z1 = r3 == 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t t0 = o[0][i], t1 = o[1][i], t2 = o[2][i];
+            o[0][i] = z0 ? t0 : (z1 ? t1 : t2);
+            o[1][i] = z0 ? t1 : (z1 ? t2 : t0);
+            o[2][i] = z0 ? t2 : (z1 ? t0 : t1);
+          }
+          const size_t pixq = ((size_t)n * OH + gyb) * OW + gx;
+          if (!(p.ablate & 1)) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              int m = j + r3;
+              if (m >= 3) m -= 3;
+              const int c = c0 + 16 * m;
+              h16* const dq = c >= 256 ? (h16*)e.out2 + pixq * 128 + (c - 256) : (h16*)e.out + pixq * 256 + c;
+              st_global_256(dq, make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]), make_uint4(o[j][4], o[j][5], o[j][6], o[j][7]));
+            }
+          }
+        }
       } else if (EPI == EPI_PLAIN) {
         // Lean direct-store epilogue for plain convs (selected by launch_conv_tc: no residual, one column group, 16-channel
         // aligned h16 output).  Its own kernel instantiation, so its registers do not compete with the general paths.
@@ -1032,6 +1088,7 @@ inline int configure_tc_kernels_conv() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_HEADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_CLR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<EPI_QKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -1361,7 +1418,9 @@ inline bool pack_tc_weights(TmaEncoder& tma, const std::string& name, int kh, in
   if (kh * kw * ncb > TC_MAX_STEPS) return false;
   t.kind = TC_CONV;
   const bool pair_k = !getenv("BSR_NO_KPAIR");
-  if (cout == 384) { t.bn = 128; t.n_tiles = 3; }
+  // q | k | v projection: two 192-column tiles (N = 192 MMAs read the A operand twice per pixel tile instead of three times
+  // and amortise the per-MMA cost better than N = 128; measured below); BSR_QKV_128=1 restores three 128-column tiles
+  if (cout == 384) { if (getenv("BSR_QKV_128")) { t.bn = 128; t.n_tiles = 3; } else { t.bn = 192; t.n_tiles = 2; } }
   else if (cout <= 256) { t.bn = (cout + 15) / 16 * 16; t.n_tiles = 1; }
   else { t.n_tiles = (cout + 255) / 256; t.bn = ((cout + t.n_tiles - 1) / t.n_tiles + 15) / 16 * 16; }
   t.b_box_rows = t.bn; t.b_stage_rows = t.bn;
@@ -1551,6 +1610,10 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
       p.n_groups == 1 && t.rows_per_tile == 1 && !t.zero_acc && p.group_cols <= 256 && p.group_cols != 128 &&
       e.out_ld % 16 == 0 && e.out_coff % 16 == 0 && e.out_c % 16 == 0 && !getenv("BSR_NO_PLAIN_EPI"))
     p.epi_mode = EPI_PLAIN;
+  if (p.epi_mode == EPI_GENERIC && e.out_mode == OUT_QKV && e.v_natural && e.res1 == nullptr && e.res2 == nullptr &&
+      p.n_groups == 1 && t.rows_per_tile == 1 && p.group_cols == 192 && e.out_c == t.n_tiles * 192 && p.out_scale == 1) {
+    p.epi_mode = EPI_QKV;
+  }
   p.n_stages = std::min(8, (max_smem - fixed_bytes - staging) / p.stage_bytes);
   if (p.n_stages < 2) { tma.last_error = "stage too large"; return -5; }
   p.acc_stages = 2 * t.bn <= 512 ? 2 : 1;
@@ -1618,6 +1681,7 @@ inline int launch_conv_tc(TmaEncoder& tma, const TcWeights& t, const void* in, i
   if (p.epi_mode == EPI_HEADS) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_HEADS, false>, it->second, t.map, p, e, x, cw, *omap);
   else if (p.epi_mode == EPI_CLR) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_CLR, false>, it->second, t.map, p, e, x, cw, *omap);
   else if (p.epi_mode == EPI_PLAIN) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_PLAIN, false>, it->second, t.map, p, e, x, cw, *omap);
+  else if (p.epi_mode == EPI_QKV) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_QKV, false>, it->second, t.map, p, e, x, cw, *omap);
   else if (e.res1 != nullptr || e.res2 != nullptr) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, true>, it->second, t.map, p, e, x, cw, *omap);
   else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI_GENERIC, false>, it->second, t.map, p, e, x, cw, *omap);
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -6; }

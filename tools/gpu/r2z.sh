@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call Z: lean direct-store epilogue instantiation (res conv3): parity, A/B against the previous build
+# round 2, GPU call Z: qkv in two 192-column tiles: parity, A/B against the previous build
 mkdir -p gpurun_out/r2z; O=gpurun_out/r2z
 timeout 300 python tests/gpu_check.py tc > $O/gpu_check.log 2>&1; grep -E "^(gsc|tsm)|res0|res5|con_rgb|gs  |flips|errflag" $O/gpu_check.log | head -14
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_real_files.py -m gpu -q -x > $O/pytest_parity.log 2>&1; echo "pytest parity rc=$?" > $O/summary.txt
