@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
                                                                      const __grid_constant__ Halo3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = smem_base;                                        // [buffer 2][K block 2] halo tiles
+  // barriers, TMEM slot and bias FIRST (1 KB), the TMA-written tiles behind them
+  const uint32_t bars = smem_base;
+  const uint32_t sA = smem_base + 1024u;                                // [buffer 2][K block 2] halo tiles
   const uint32_t sB = sA + 4u * H3_A_BYTES;                             // weight ring
-  const uint32_t bars = sB + (uint32_t)(H3_B_STAGES * H3_B_BYTES);
   const uint32_t bar_afull = bars, bar_aempty = bars + 16, bar_bfull = bars + 32, bar_bempty = bars + 64;
   const uint32_t bar_tfull = bars + 96, bar_tempty = bars + 112, tmem_slot = bars + 128;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
