@@ -583,11 +583,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 yy = unpack_h16x2(yw[k]), xx = unpack_h16x2(xw[k]);
-              float r0 = __uint_as_float(v[8 * c + 2 * k]) + bb[2 * k] + yy.x + xx.x;
-              float r1 = __uint_as_float(v[8 * c + 2 * k + 1]) + bb[2 * k + 1] + yy.y + xx.y;
-              r0 = fmaxf(r0, kLeaky * r0);
-              r1 = fmaxf(r1, kLeaky * r1);
-              ow[k] = pack_h16x2(r0, r1);
+              // packed fp32 adds / multiply (FADD2, FMUL2): same operations in the same order as the scalar form
+              float r0 = __uint_as_float(v[8 * c + 2 * k]), r1 = __uint_as_float(v[8 * c + 2 * k + 1]), t0, t1;
+              fadd2(r0, r1, bb[2 * k], bb[2 * k + 1]);
+              fadd2(r0, r1, yy.x, yy.y);
+              fadd2(r0, r1, xx.x, xx.y);
+              fmul2_b(t0, t1, r0, r1, kLeaky);
+              ow[k] = pack_h16x2(fmaxf(r0, t0), fmaxf(r1, t1));
             }
             *reinterpret_cast<uint4*>(so + po) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }

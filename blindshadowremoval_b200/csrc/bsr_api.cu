@@ -547,12 +547,14 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     int cx = c_cur;
     int uv_off = tsm ? cx + 1 + 2 * cx : cx + 1;
     int cells = (int)px32;
-    hole_kernel<T><<<(cells + 3) / 4, 128, 0, st>>>(h->DIFGS, (const T*)cur, ld1, (T*)nxt, ld2, cx, h->UVS, uv_off,
-                                                    uv_off + 3, ld2, h->BMASK, h->DIFSMALL, cells);
+    // same channel stride in both halves (GSC): the mask is applied in place and the 257 feature channels are not copied
+    const bool inplace = ld1 == ld2 && !h->kn.no_hole_inplace;
+    hole_kernel<T><<<(cells + 3) / 4, 128, 0, st>>>(h->DIFGS, (const T*)cur, ld1, (T*)(inplace ? cur : nxt), ld2, cx, h->UVS,
+                                                    uv_off, uv_off + 3, ld2, h->BMASK, h->DIFSMALL, cells);
     h->launches++;
+    // otherwise the hole kernel wrote into `nxt` viewed with ld2; from here on (cur, nxt) = (that buffer, the other)
+    if (!inplace) std::swap(cur, nxt);
   }
-  // the hole kernel wrote into `nxt` viewed with ld2; from here on (cur, nxt) = (that buffer, the other)
-  std::swap(cur, nxt);
   if (tsm) {
     if ((rc = run_share<T>(h, st, cur, ld2, c_cur, c_cur + 1, n, frame, share))) return rc;   // model_with_TSM.py:293
   }
@@ -972,6 +974,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->kn.no_halo = env_set("BSR_NO_HALO");
   h->kn.no_halo3 = env_set("BSR_NO_HALO3");
+  h->kn.no_hole_inplace = env_set("BSR_NO_HOLE_INPLACE");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
   h->ld1 = pad16(h->c_first > 257 ? h->c_first : 257);

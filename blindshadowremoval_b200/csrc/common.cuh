@@ -92,6 +92,14 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(aa));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
+// (r0, r1) = (a0, a1) * b
+__device__ __forceinline__ void fmul2_b(float& r0, float& r1, float a0, float a1, float b) {
+  uint64_t d, aa, bb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(aa), "l"(bb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(d));
+}
 __device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float w0, float w1) {
   uint64_t d, aa, ww;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
@@ -112,6 +120,7 @@ struct Knobs {
   int host_full_uv = 0;    // BSR_HOST_FULL_UV: the fp32 host path uploads uv / reg in full instead of the rows the model reads
   int no_graph = 0;        // BSR_NO_GRAPH: never replay micro-batches from captured CUDA graphs
   int no_halo = 0;         // BSR_NO_HALO: fused transposed convs fetch every shifted A tile separately (round-1 behaviour)
+  int no_hole_inplace = 0; // BSR_NO_HOLE_INPLACE: the hole mask copies into the other buffer even when the strides agree
   int no_halo3 = 0;        // BSR_NO_HALO3: res conv2 on the generic kernel (nine shifted A tiles) instead of conv3x3_halo.cuh
   int attn_v1 = 0;         // BSR_ATTN_V1=1: round-1 two-pass attention kernel with the fused output conv (A/B measurements)
 };

@@ -212,8 +212,7 @@ __global__ void compose_kernel(const float* __restrict__ raw, const float* __res
 // x_hole = x*(1-bmask); out = [x_hole (cx ch) | bmask | ... | uv at uv_off]; zero [z0,z1).
 // One warp per 32x32 cell.
 template <typename T>
-__global__ void hole_kernel(const float* __restrict__ difgs, const T* __restrict__ xa, int lda,
-                            T* __restrict__ xb, int ldb, int cx, const float* __restrict__ uvs, int uv_off,
+__global__ void hole_kernel(const float* __restrict__ difgs, const T* xa, int lda, T* xb, int ldb, int cx, const float* __restrict__ uvs, int uv_off,
                             int z0, int z1, float* __restrict__ bmask_out, float* __restrict__ difsmall_out,
                             int n_cells) {
   int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -226,16 +225,28 @@ __global__ void hole_kernel(const float* __restrict__ difgs, const T* __restrict
   const T* src = xa + (size_t)cell * lda;
   T* dst = xb + (size_t)cell * ldb;
   int c_done = 0;
-  if (sizeof(T) == 2 && (lda & 7) == 0 && (ldb & 7) == 0) {
-    // 16-bit storage: 8 channels (16 bytes) per lane and step; keep is 0 or 1, so the product is a select
-    c_done = cx & ~7;
-    for (int c = lane * 8; c < c_done; c += 256) {
-      uint4 v = *reinterpret_cast<const uint4*>(src + c);
-      if (bm != 0.f) v = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(dst + c) = v;
+  if (src == dst) {
+    // in place (both halves of the network use the same channel stride: GSC): a kept cell is already what it has to be,
+    // a masked cell is cleared without being read
+    if (bm != 0.f) {
+      if (sizeof(T) == 2 && (ldb & 7) == 0) {
+        c_done = cx & ~7;
+        for (int c = lane * 8; c < c_done; c += 256) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (int c = c_done + lane; c < cx; c += 32) stf<T>(dst, c, 0.f);
     }
+  } else {
+    if (sizeof(T) == 2 && (lda & 7) == 0 && (ldb & 7) == 0) {
+      // 16-bit storage: 8 channels (16 bytes) per lane and step; keep is 0 or 1, so the product is a select
+      c_done = cx & ~7;
+      for (int c = lane * 8; c < c_done; c += 256) {
+        uint4 v = *reinterpret_cast<const uint4*>(src + c);
+        if (bm != 0.f) v = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst + c) = v;
+      }
+    }
+    for (int c = c_done + lane; c < cx; c += 32) stf<T>(dst, c, ldf<T>(src, c) * keep);
   }
-  for (int c = c_done + lane; c < cx; c += 32) stf<T>(dst, c, ldf<T>(src, c) * keep);
   if (lane == 0) {
     stf<T>(dst, cx, bm);
     bmask_out[cell] = bm;
