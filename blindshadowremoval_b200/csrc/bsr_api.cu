@@ -81,6 +81,8 @@ struct bsr_handle {
   int num_sms = 148;
   float *RAW = nullptr, *DIFGS = nullptr, *UVS = nullptr, *OFF = nullptr, *BMASK = nullptr, *DIFSMALL = nullptr,
         *SH = nullptr;
+  char* TAPS = nullptr;        // bilinear tap records of the ShareLayer, [frames][1024][2] x 16 bytes
+  bool taps_ready = false;     // computed for the offsets currently in OFF
   int* errflag = nullptr;    // device flag set by kernels whose mbarrier wait timed out
   int* errflag_host = nullptr;   // pinned mirror, refreshed by an async copy at the end of every forward
   cudaEvent_t ev_done = nullptr; // recorded at the end of every forward: the next forward (any stream) waits for it
@@ -430,6 +432,24 @@ int run_share(bsr_handle* h, cudaStream_t st, char* x, int ld, int C, int coff, 
   }
   if ((ld & 3) || (coff & 3)) return fail(h, BSR_EINVAL, "share layer needs 4-channel aligned stride / offset (ld %d, coff %d)", ld, coff);
   const int chunks = n / frame, ldsh = (2 * C + 3) / 4 * 4;
+  if (std::is_same<T, h16>::value && ld % 8 == 0 && !h->kn.share_v1) {
+    // 16-bit storage: tap records once per forward, eight lanes per cell, shared features in the alignment of their
+    // destination (see glue.cuh)
+    if (!h->taps_ready) {
+      const int n_rec = n * FEAT * FEAT * 2;
+      share_taps_kernel<<<(n_rec + 255) / 256, 256, 0, st>>>(h->OFF, (TapRec*)h->TAPS, n_rec);
+      h->launches++;
+      h->taps_ready = true;
+    }
+    const int shift = coff & 7, ldsh16 = (shift + 2 * C + 7) / 8 * 8;
+    const int cells1 = chunks * FEAT * FEAT, cells2 = n * FEAT * FEAT;        // eight lanes per cell, 32 cells per block
+    share_reduce_h16_kernel<<<(cells1 + 31) / 32, 256, 0, st>>>((const h16*)x, ld, C, (const TapRec*)h->TAPS, frame, (h16*)h->SH,
+                                                                ldsh16, shift, cells1);
+    share_out_h16_kernel<<<(cells2 + 31) / 32, 256, 0, st>>>((const h16*)h->SH, ldsh16, shift, 2 * C, (const TapRec*)h->TAPS, frame,
+                                                             (h16*)x, ld, coff, cells2);
+    h->launches += 2;
+    return BSR_OK;
+  }
   const int cells1 = chunks * FEAT * FEAT, cells2 = n * FEAT * FEAT;          // one warp per cell, 8 warps per block
   share_reduce_kernel<T><<<(cells1 + 7) / 8, 256, 0, st>>>((const T*)x, ld, C, h->OFF, frame, (T*)h->SH, ldsh, cells1);
   share_out_kernel<T><<<(cells2 + 7) / 8, 256, 0, st>>>((const T*)h->SH, ldsh, 2 * C, h->OFF, frame, (T*)x, ld, coff, cells2);
@@ -487,6 +507,7 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
       else if (h->in_rows) reg_rows_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
       else reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
       h->launches++;
+      h->taps_ready = false;
     }
   }
   int c_cur = h->c_first;
@@ -974,6 +995,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->kn.no_halo = env_set("BSR_NO_HALO");
   h->kn.no_halo3 = env_set("BSR_NO_HALO3");
+  h->kn.share_v1 = env_set("BSR_SHARE_V1");
   h->kn.no_hole_inplace = env_set("BSR_NO_HOLE_INPLACE");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
   h->c_second = variant == BSR_VARIANT_GSC ? 261 : 877;
@@ -996,6 +1018,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
       {(char**)&h->UVS, mb * 1024 * 3 * 4}, {(char**)&h->OFF, mb * 1024 * 4 * 4}, {(char**)&h->BMASK, mb * 1024 * 4},
       {(char**)&h->DIFSMALL, mb * 1024 * 4},
       {(char**)&h->SH, variant == BSR_VARIANT_TSM ? mb * 1024 * 584 * 4 : 256},
+      {&h->TAPS, variant == BSR_VARIANT_TSM ? mb * 1024 * 2 * 16 : 256},
       {(char**)&h->errflag, 16384}};
   // staging of the host / chunk entry points (include/bsr.h: no allocation inside forward_*): host-path chunks are
   // capped at 128 images (the measured optimum is 64-128), chunk entry at one micro-batch
@@ -1300,6 +1323,7 @@ int bsr_share_layer(bsr_handle* h, const float* x, const float* reg, int n, int 
   const int tot4 = n * FEAT * FEAT * 4;
   reg_small_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(reg, h->OFF, n);
   h->launches = 1;
+  h->taps_ready = false;
   int rc;
   if (h->precision == BSR_PRECISION_FP32CHECK) {
     pack_act_kernel<float><<<(unsigned)((npix * C + 255) / 256), 256, 0, st>>>(x, C, (float*)h->XA, ld, npix);

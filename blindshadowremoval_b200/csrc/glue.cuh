@@ -385,6 +385,193 @@ __global__ void share_out_kernel(const T* __restrict__ sh, int ldsh, int C2, con
   }
 }
 
+// ---- 16-bit ShareLayer kernels (the product path).  The warp-per-cell kernels above are bound by instruction issue, not
+// by memory (ncu: 2.6-3.1 IPC, 13 % of DRAM peak): tap arithmetic repeated per vector and frame, scalar fp32 blends, 8-byte
+// accesses.  Here
+//   * the bilinear taps of every (frame, pixel, direction) are computed ONCE per forward into 16-byte records;
+//   * eight lanes share a cell (a warp works on four cells), each lane moves 16-byte vectors of 8 channels;
+//   * the blend runs on packed fp32 FMAs (fma.rn.f32x2; the same operations in the same order as warp_mix);
+//   * the shared features are stored in the alignment of their DESTINATION: row = [shift unused | max: C | mean: C] with
+//     shift = coff % 8, so the un-warp kernel reads and writes aligned 16-byte vectors only and the reduce kernel (which
+//     has 2 x frame fewer vectors to store) takes the odd alignments (C = 291 is odd) on its store side.
+// Needs ld % 8 == 0 and coff % 4 == 0.
+struct __align__(16) TapRec { uint32_t lt_rt, lb_rb; float o0, o1; };     // pixel indices (< 1024) in 16-bit halves
+
+// off[n][pix][4] = (in-warp offset, out-warp offset) -> taps[n][pix][2]
+__global__ void share_taps_kernel(const float* __restrict__ off, TapRec* __restrict__ taps, int n_rec) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rec) return;
+  const int pix = (idx >> 1) & (FEAT * FEAT - 1);
+  const float2 o = *reinterpret_cast<const float2*>(off + (size_t)idx * 2);
+  const WarpTap w = warp_tap(o.x, o.y, pix / FEAT, pix % FEAT);
+  TapRec r;
+  r.lt_rt = (uint32_t)w.lt | ((uint32_t)w.rt << 16);
+  r.lb_rb = (uint32_t)w.lb | ((uint32_t)w.rb << 16);
+  r.o0 = w.o0;
+  r.o1 = w.o1;
+  taps[idx] = r;
+}
+
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t h2_to_f2(uint32_t w) {
+  const float2 f = unpack_h16x2(w);
+  return f2_pack(f.x, f.y);
+}
+// warp_mix on two channels at once: fma(x, -1, y) is the correctly rounded y - x, the other steps are the FMAs the scalar
+// form contracts to
+__device__ __forceinline__ uint64_t warp_mix2(uint32_t lt, uint32_t rt, uint32_t lb, uint32_t rb, uint64_t o0, uint64_t o1,
+                                              uint64_t m1) {
+  const uint64_t a = h2_to_f2(lt), b = h2_to_f2(rt), c = h2_to_f2(lb), d = h2_to_f2(rb);
+  const uint64_t vt = f2_fma(f2_fma(a, m1, b), o0, a);
+  const uint64_t vb = f2_fma(f2_fma(c, m1, d), o0, c);
+  return f2_fma(f2_fma(vt, m1, vb), o1, vt);
+}
+// 8 consecutive 16-bit values (4 words) to a destination of ANY 2-byte alignment; the alignment is the same for every
+// thread of a launch, so the branches do not diverge
+__device__ __forceinline__ void store8_any(h16* dst, const uint32_t* w) {
+  const unsigned a = ((unsigned)(uintptr_t)dst >> 1) & 7u;
+  if (a == 0) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if ((a & 3u) == 0) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+    *reinterpret_cast<uint2*>(dst + 4) = make_uint2(w[2], w[3]);
+  } else if ((a & 1u) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint32_t*>(dst + 2 * k) = w[k];
+  } else {
+    unsigned short* d16 = reinterpret_cast<unsigned short*>(dst);
+    d16[0] = (unsigned short)(w[0] & 0xffffu);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint32_t*>(dst + 1 + 2 * k) = __funnelshift_r(w[k], w[k + 1], 16);
+    d16[7] = (unsigned short)(w[3] >> 16);
+  }
+}
+
+// First half (model_with_TSM.py:204-222): sh[chunk][pix][shift + c] = max_f warp_in(x_f)[c], [shift + C + c] = mean_f.
+__global__ void __launch_bounds__(256) share_reduce_h16_kernel(const h16* __restrict__ x, int ld, int C,
+                                                               const TapRec* __restrict__ taps, int frame,
+                                                               h16* __restrict__ sh, int ldsh, int shift, int n_cells) {
+  const int cell = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+  if (cell >= n_cells) return;
+  const int pix = cell & (FEAT * FEAT - 1), chunk = cell >> 10;
+  const int Cv = (C + 7) >> 3;
+  const uint64_t m1 = f2_pack(-1.f, -1.f);
+  const float fr = (float)frame;
+  h16* drow = sh + (size_t)cell * ldsh + shift;
+  unsigned short* drow16 = reinterpret_cast<unsigned short*>(drow);
+  for (int cv = sub; cv < Cv; cv += 8) {
+    const int c0 = 8 * cv;
+    float mx[8];
+    uint64_t sum[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sum[k] = 0ull;
+    for (int f = 0; f < frame; ++f) {
+      const int n = chunk * frame + f;
+      const uint4 tp = __ldg(reinterpret_cast<const uint4*>(taps + ((size_t)n * (FEAT * FEAT) + pix) * 2));
+      const h16* b = x + (size_t)n * (FEAT * FEAT) * ld + c0;
+      const uint4 lt = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.x & 0xffffu) * ld));
+      const uint4 rt = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.x >> 16) * ld));
+      const uint4 lb = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.y & 0xffffu) * ld));
+      const uint4 rb = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.y >> 16) * ld));
+      const float o0f = __uint_as_float(tp.z), o1f = __uint_as_float(tp.w);
+      const uint64_t o0 = f2_pack(o0f, o0f), o1 = f2_pack(o1f, o1f);
+      const uint32_t a[4] = {lt.x, lt.y, lt.z, lt.w}, bq[4] = {rt.x, rt.y, rt.z, rt.w}, cq[4] = {lb.x, lb.y, lb.z, lb.w},
+                     dq[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t v = warp_mix2(a[k], bq[k], cq[k], dq[k], o0, o1, m1);
+        float v0, v1;
+        f2_unpack(v, v0, v1);
+        mx[2 * k] = fmaxf(mx[2 * k], v0);
+        mx[2 * k + 1] = fmaxf(mx[2 * k + 1], v1);
+        sum[k] = f2_add(sum[k], v);
+      }
+    }
+    uint32_t om[4], oa[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float s0, s1;
+      f2_unpack(sum[k], s0, s1);
+      om[k] = pack_h16x2(mx[2 * k], mx[2 * k + 1]);
+      oa[k] = pack_h16x2(s0 / fr, s1 / fr);
+    }
+    if (c0 + 8 <= C) {
+      store8_any(drow + c0, om);
+      store8_any(drow + C + c0, oa);
+    } else {
+      // last, partial vector: the max half must not run into the mean half that follows it
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (c0 + k < C) {
+          drow16[c0 + k] = (unsigned short)((om[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+          drow16[C + c0 + k] = (unsigned short)((oa[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        }
+      }
+    }
+  }
+}
+
+// Second half (model_with_TSM.py:223-226): x[n][pix][coff + c] = warp_out(sh[chunk])[pix][shift + c], c < C2 = 2C.
+__global__ void __launch_bounds__(256) share_out_h16_kernel(const h16* __restrict__ sh, int ldsh, int shift, int C2,
+                                                            const TapRec* __restrict__ taps, int frame, h16* __restrict__ x,
+                                                            int ld, int coff, int n_cells) {
+  const int cell = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+  if (cell >= n_cells) return;
+  const int n = cell >> 10;
+  const int chunk = n / frame;
+  const uint4 tp = __ldg(reinterpret_cast<const uint4*>(taps + (size_t)cell * 2 + 1));
+  const float o0f = __uint_as_float(tp.z), o1f = __uint_as_float(tp.w);
+  const uint64_t o0 = f2_pack(o0f, o0f), o1 = f2_pack(o1f, o1f), m1 = f2_pack(-1.f, -1.f);
+  const h16* b = sh + (size_t)chunk * (FEAT * FEAT) * ldsh;
+  const h16* p_lt = b + (size_t)(tp.x & 0xffffu) * ldsh;
+  const h16* p_rt = b + (size_t)(tp.x >> 16) * ldsh;
+  const h16* p_lb = b + (size_t)(tp.y & 0xffffu) * ldsh;
+  const h16* p_rb = b + (size_t)(tp.y >> 16) * ldsh;
+  h16* d = x + (size_t)cell * ld + coff - shift;                  // 16-byte aligned: ld % 8 == 0, (coff - shift) % 8 == 0
+  unsigned short* d16 = reinterpret_cast<unsigned short*>(d);
+  const int S = shift + C2, Nv = (S + 7) >> 3;
+  for (int v = sub; v < Nv; v += 8) {
+    const int s0 = 8 * v;
+    const uint4 lt = __ldg(reinterpret_cast<const uint4*>(p_lt + s0));
+    const uint4 rt = __ldg(reinterpret_cast<const uint4*>(p_rt + s0));
+    const uint4 lb = __ldg(reinterpret_cast<const uint4*>(p_lb + s0));
+    const uint4 rb = __ldg(reinterpret_cast<const uint4*>(p_rb + s0));
+    const uint32_t a[4] = {lt.x, lt.y, lt.z, lt.w}, bq[4] = {rt.x, rt.y, rt.z, rt.w}, cq[4] = {lb.x, lb.y, lb.z, lb.w},
+                   dq[4] = {rb.x, rb.y, rb.z, rb.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v0, v1;
+      f2_unpack(warp_mix2(a[k], bq[k], cq[k], dq[k], o0, o1, m1), v0, v1);
+      o[k] = pack_h16x2(v0, v1);
+    }
+    if (s0 >= shift && s0 + 8 <= S) {
+      *reinterpret_cast<uint4*>(d + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (s0 + k >= shift && s0 + k < S) d16[s0 + k] = (unsigned short)((o[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+    }
+  }
+}
+
 // share == False: x_share = concat([x, x])  (model_with_TSM.py:227)
 template <typename T>
 __global__ void share_dup_kernel(T* __restrict__ x, int ld, int C, int coff, long long n_pix) {
