@@ -443,7 +443,7 @@ int run_share(bsr_handle* h, cudaStream_t st, char* x, int ld, int C, int coff, 
     }
     const int shift = coff & 7, ldsh16 = (shift + 2 * C + 7) / 8 * 8;
     const int cells1 = chunks * FEAT * FEAT, cells2 = n * FEAT * FEAT;        // eight lanes per cell, 32 cells per block
-    share_reduce_h16_kernel<<<(cells1 + 31) / 32, 256, 0, st>>>((const h16*)x, ld, C, (const TapRec*)h->TAPS, frame, (h16*)h->SH,
+    share_reduce_h16_kernel<<<(cells1 + 31) / 32, 256, (size_t)32 * ldsh16 * 2, st>>>((const h16*)x, ld, C, (const TapRec*)h->TAPS, frame, (h16*)h->SH,
                                                                 ldsh16, shift, cells1);
     share_out_h16_kernel<<<(cells2 + 31) / 32, 256, 0, st>>>((const h16*)h->SH, ldsh16, shift, 2 * C, (const TapRec*)h->TAPS, frame,
                                                              (h16*)x, ld, coff, cells2);

@@ -463,68 +463,85 @@ __device__ __forceinline__ void store8_any(h16* dst, const uint32_t* w) {
 }
 
 // First half (model_with_TSM.py:204-222): sh[chunk][pix][shift + c] = max_f warp_in(x_f)[c], [shift + C + c] = mean_f.
-__global__ void __launch_bounds__(256) share_reduce_h16_kernel(const h16* __restrict__ x, int ld, int C,
-                                                               const TapRec* __restrict__ taps, int frame,
-                                                               h16* __restrict__ sh, int ldsh, int shift, int n_cells) {
-  const int cell = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
-  if (cell >= n_cells) return;
+// The eight lanes of a cell assemble the row in shared memory (where the odd alignments of the two halves cost nothing)
+// and copy it out with aligned 16-byte stores.  Dynamic shared memory: 32 cells x ldsh x 2 bytes (<= 37 KB).
+__global__ void __launch_bounds__(256, 4) share_reduce_h16_kernel(const h16* __restrict__ x, int ld, int C,
+                                                                  const TapRec* __restrict__ taps, int frame,
+                                                                  h16* __restrict__ sh, int ldsh, int shift, int n_cells) {
+  extern __shared__ uint4 share_rows[];
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int cell = blockIdx.x * 32 + grp;
+  const bool live = cell < n_cells;
   const int pix = cell & (FEAT * FEAT - 1), chunk = cell >> 10;
-  const int Cv = (C + 7) >> 3;
+  const int Cv = (C + 7) >> 3, S = shift + 2 * C;
   const uint64_t m1 = f2_pack(-1.f, -1.f);
-  const float fr = (float)frame;
-  h16* drow = sh + (size_t)cell * ldsh + shift;
-  unsigned short* drow16 = reinterpret_cast<unsigned short*>(drow);
-  for (int cv = sub; cv < Cv; cv += 8) {
-    const int c0 = 8 * cv;
-    float mx[8];
-    uint64_t sum[4];
+  const float fr = (float)frame, inv_fr = 1.f / fr;
+  const bool pow2 = (frame & (frame - 1)) == 0;            // then sum * (1 / frame) IS sum / frame
+  unsigned short* row16 = reinterpret_cast<unsigned short*>(share_rows) + (size_t)grp * ldsh;
+  h16* rowh = reinterpret_cast<h16*>(row16);
+  if (live) {
+    // padding of the row (never read as data): zeros, so that the buffer content is reproducible
+    for (int k = sub; k < shift; k += 8) row16[k] = 0;
+    for (int k = S + sub; k < ldsh; k += 8) row16[k] = 0;
+    for (int cv = sub; cv < Cv; cv += 8) {
+      const int c0 = 8 * cv;
+      float mx[8];
+      uint64_t sum[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
+      for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sum[k] = 0ull;
-    for (int f = 0; f < frame; ++f) {
-      const int n = chunk * frame + f;
-      const uint4 tp = __ldg(reinterpret_cast<const uint4*>(taps + ((size_t)n * (FEAT * FEAT) + pix) * 2));
-      const h16* b = x + (size_t)n * (FEAT * FEAT) * ld + c0;
-      const uint4 lt = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.x & 0xffffu) * ld));
-      const uint4 rt = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.x >> 16) * ld));
-      const uint4 lb = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.y & 0xffffu) * ld));
-      const uint4 rb = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.y >> 16) * ld));
-      const float o0f = __uint_as_float(tp.z), o1f = __uint_as_float(tp.w);
-      const uint64_t o0 = f2_pack(o0f, o0f), o1 = f2_pack(o1f, o1f);
-      const uint32_t a[4] = {lt.x, lt.y, lt.z, lt.w}, bq[4] = {rt.x, rt.y, rt.z, rt.w}, cq[4] = {lb.x, lb.y, lb.z, lb.w},
-                     dq[4] = {rb.x, rb.y, rb.z, rb.w};
+      for (int k = 0; k < 4; ++k) sum[k] = 0ull;
+#pragma unroll 2
+      for (int f = 0; f < frame; ++f) {
+        const int n = chunk * frame + f;
+        const uint4 tp = __ldg(reinterpret_cast<const uint4*>(taps + ((size_t)n * (FEAT * FEAT) + pix) * 2));
+        const h16* b = x + (size_t)n * (FEAT * FEAT) * ld + c0;
+        const uint4 lt = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.x & 0xffffu) * ld));
+        const uint4 rt = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.x >> 16) * ld));
+        const uint4 lb = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.y & 0xffffu) * ld));
+        const uint4 rb = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(tp.y >> 16) * ld));
+        const float o0f = __uint_as_float(tp.z), o1f = __uint_as_float(tp.w);
+        const uint64_t o0 = f2_pack(o0f, o0f), o1 = f2_pack(o1f, o1f);
+        const uint32_t a[4] = {lt.x, lt.y, lt.z, lt.w}, bq[4] = {rt.x, rt.y, rt.z, rt.w}, cq[4] = {lb.x, lb.y, lb.z, lb.w},
+                       dq[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t v = warp_mix2(a[k], bq[k], cq[k], dq[k], o0, o1, m1);
+          float v0, v1;
+          f2_unpack(v, v0, v1);
+          mx[2 * k] = fmaxf(mx[2 * k], v0);
+          mx[2 * k + 1] = fmaxf(mx[2 * k + 1], v1);
+          sum[k] = f2_add(sum[k], v);
+        }
+      }
+      uint32_t om[4], oa[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint64_t v = warp_mix2(a[k], bq[k], cq[k], dq[k], o0, o1, m1);
-        float v0, v1;
-        f2_unpack(v, v0, v1);
-        mx[2 * k] = fmaxf(mx[2 * k], v0);
-        mx[2 * k + 1] = fmaxf(mx[2 * k + 1], v1);
-        sum[k] = f2_add(sum[k], v);
+        float s0, s1;
+        f2_unpack(sum[k], s0, s1);
+        om[k] = pack_h16x2(mx[2 * k], mx[2 * k + 1]);
+        oa[k] = pow2 ? pack_h16x2(s0 * inv_fr, s1 * inv_fr) : pack_h16x2(s0 / fr, s1 / fr);
       }
-    }
-    uint32_t om[4], oa[4];
+      if (c0 + 8 <= C) {
+        store8_any(rowh + shift + c0, om);
+        store8_any(rowh + shift + C + c0, oa);
+      } else {
+        // last, partial vector: the max half must not run into the mean half that follows it
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float s0, s1;
-      f2_unpack(sum[k], s0, s1);
-      om[k] = pack_h16x2(mx[2 * k], mx[2 * k + 1]);
-      oa[k] = pack_h16x2(s0 / fr, s1 / fr);
-    }
-    if (c0 + 8 <= C) {
-      store8_any(drow + c0, om);
-      store8_any(drow + C + c0, oa);
-    } else {
-      // last, partial vector: the max half must not run into the mean half that follows it
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (c0 + k < C) {
-          drow16[c0 + k] = (unsigned short)((om[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-          drow16[C + c0 + k] = (unsigned short)((oa[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        for (int k = 0; k < 8; ++k) {
+          if (c0 + k < C) {
+            row16[shift + c0 + k] = (unsigned short)((om[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            row16[shift + C + c0 + k] = (unsigned short)((oa[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+          }
         }
       }
     }
+  }
+  __syncwarp();
+  if (live) {
+    const uint4* src = reinterpret_cast<const uint4*>(row16);
+    uint4* dst = reinterpret_cast<uint4*>(sh + (size_t)cell * ldsh);
+    for (int v = sub; v < (ldsh >> 3); v += 8) dst[v] = src[v];
   }
 }
 
