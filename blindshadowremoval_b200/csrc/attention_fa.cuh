@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap tmY,
                                                                      const __grid_constant__ CUtensorMap tmX,
                                                                      const EpiParams e, const h16* __restrict__ w_rows,
-                                                                     const int n_items, int* errflag) {
+                                                                     const int n_items, int* errflag,
+                                                                     long long* timers) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sR = sQ + 2 * FA_TILE, sO = sR + 4 * FA_TILE, bars = sO + 2 * FA_OSTAGE;
@@ -397,11 +398,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
     uint8_t* stage = smem_al + (sO + x * FA_OSTAGE - base);
     const uint32_t stage_u32 = sO + x * FA_OSTAGE;
     uint32_t w = 0;
+    // role timers (-DBSR_ROLE_TIMERS, tools/role_timers.py): thread 0 of CTA 0 = row 0 of tile A
+    const bool tm = timers != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_total = 0, t_swait = 0, t_main = 0, t_o2s = 0, t_d2w = 0, t_tail = 0, t_resw = 0, t_bar = 0, t_items = 0;
+    const long long t_begin = BSR_CLK();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
       const int n = item / FA_PAIRS, q0 = (item % FA_PAIRS) * 2 * FA_BQ + x * FA_BQ;
       float m_ref = 0.f, l = 0.f;
+      const long long t_item = BSR_CLK();
       for (int j = 0; j < FA_NK; ++j) {
+        const long long t_s0 = BSR_CLK();
         fa_wait(b_sfull + 8 * x, (8u * w + (uint32_t)j) & 1u, ctx, 60 + x);
+        t_swait += BSR_CLK() - t_s0;
         tc_fence_after();
         uint32_t v[64];
         // ---- sweep 1: row maximum of this key tile
@@ -471,6 +479,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
       }
       fa_wait(b_ofull + 8 * x, w & 1u, ctx, 62 + x);
       tc_fence_after();
+      const long long t_m1 = BSR_CLK();
+      t_main += t_m1 - t_item;
+      ++t_items;
       const float inv = 1.f / l;
       const int pix0 = n * FA_S + q0;
       if (!FUSE) {
@@ -550,8 +561,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(b_a2full + 8 * x);
+        const long long t_a2 = BSR_CLK();
+        t_o2s += t_a2 - t_m1;
         fa_wait(b_d2full + 8 * x, w & 1u, ctx, 64 + x);
         tc_fence_after();
+        const long long t_d2 = BSR_CLK();
+        t_d2w += t_d2 - t_a2;
         // ---- block tail: 8 batches of 32 channels; residuals from the ring stage of K7 (tile A) / V7 (tile B)
         const uint32_t rs_slot = (RING * w + 14u + (uint32_t)x) & 3u;
         const uint32_t sw = ((uint32_t)row >> 1) & 3u, rowo = (uint32_t)row * 64u;
@@ -561,7 +576,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
           const uint32_t u = 4u * w + (uint32_t)(b >> 1);
           uint32_t v[32];
           tmem_ld32_nowait(tS + 32u * b, v);
+          const long long t_r0 = BSR_CLK();
           fa_wait(b_resfull + 8 * sidx, u & 1u, ctx, 66 + x);
+          t_resw += BSR_CLK() - t_r0;
           tmem_wait_ld();
           if (b == 3 || b == 7) {                          // D2 columns 0-127 / all 256 are in registers
             tc_fence_before();
@@ -598,13 +615,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
           if (lane == 0) mbar_arrive(b_resempty + 8 * sidx);
           // the store issued one batch ago has finished reading the OTHER staging half before anyone passes the barrier
           // and overwrites it in the next batch
+          const long long t_b0 = BSR_CLK();
           if (wg_leader) bulk_wait_read0();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+          t_bar += BSR_CLK() - t_b0;
           if (wg_leader) {
             tma_store_2d(&tmO, stage_u32 + (uint32_t)(b & 1) * 8192u, 32 * b, pix0);
             bulk_commit();
           }
         }
+        t_tail += BSR_CLK() - t_d2;
         // ---- channels 256..271: the 257th channel (CUDA-core dot product) and the 15 padding channels
         {
           float t[16];
@@ -633,6 +653,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attention_fa_kernel(const __gri
       }
     }
     if (wg_leader) bulk_wait0();
+    if (tm) {
+      t_total = BSR_CLK() - t_begin;
+      timers[0] = t_total; timers[1] = t_main; timers[2] = t_swait; timers[3] = t_o2s; timers[4] = t_d2w; timers[5] = t_tail;
+      timers[6] = t_resw; timers[7] = t_bar; timers[8] = t_items; timers[9] = -1;      // [9] = -1 marks an attention record
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -650,7 +675,8 @@ struct FaTailMaps { CUtensorMap w, y, x, out; };
 // With `w_packed` / `e` (FUSE): out = LeakyReLU(x_in + y + W_w . O + b) is written instead of O (see the kernel comment);
 // w_packed = the [288 rows][128] K-major 16-bit matrix of the output conv, e = bias / res1 = y / res2 = x_in / out.
 inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h16* o, int n, int num_sms, int* errflag,
-                               cudaStream_t st, const Knobs& kn, const h16* w_packed = nullptr, const EpiParams* e = nullptr) {
+                               cudaStream_t st, const Knobs& kn, const h16* w_packed = nullptr, const EpiParams* e = nullptr,
+                               int launch_idx = 0) {
   static thread_local std::map<std::tuple<const void*, const void*, const void*, int>, FaMaps> cache;
   auto key = std::make_tuple((const void*)qk, (const void*)vt, (const void*)o, n);
   auto it = cache.find(key);
@@ -683,6 +709,7 @@ inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h1
   EpiParams ep;
   memset(&ep, 0, sizeof ep);
   cudaError_t le;
+  long long* timers = (kn.ablate & 8) ? reinterpret_cast<long long*>(errflag) + 16 + 16 * (launch_idx & 63) : nullptr;
   if (w_packed && e) {
     // tail maps: W_w rows 0..255 as [64 K x 256 rows] boxes; y / x_in / out as [pixels x channels], 32-channel boxes, 64B swizzle
     static thread_local std::map<std::tuple<const void*, const void*, const void*, const void*, int, int>, FaTailMaps> tcache;
@@ -706,10 +733,10 @@ inline int launch_attention_fa(TmaEncoder& tma, const h16* qk, const h16* vt, h1
     }
     ep = *e;
     le = cudaLaunchKernelEx(&cfg, attention_fa_kernel<true>, it->second.qk, it->second.vt, tt->second.out, tt->second.w,
-                            tt->second.y, tt->second.x, ep, w_packed, n_items, errflag);
+                            tt->second.y, tt->second.x, ep, w_packed, n_items, errflag, timers);
   } else {
     le = cudaLaunchKernelEx(&cfg, attention_fa_kernel<false>, it->second.qk, it->second.vt, it->second.o, it->second.qk,
-                            it->second.qk, it->second.qk, ep, (const h16*)nullptr, n_items, errflag);
+                            it->second.qk, it->second.qk, ep, (const h16*)nullptr, n_items, errflag, timers);
   }
   if (le != cudaSuccess) { tma.last_error = cudaGetErrorString(le); return -3; }
   return 0;

@@ -326,7 +326,7 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
     EpiParams e2;
     if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
     int rc = launch_attention_fa(h->tma, (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, n, h->num_sms, h->errflag, st, h->kn,
-                                 wl ? (const h16*)wl->tc.dev : nullptr, wl ? &e2 : nullptr);
+                                 wl ? (const h16*)wl->tc.dev : nullptr, wl ? &e2 : nullptr, h->launches);
     if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
     h->launches++;
     h->pc.attn_fused += wl != nullptr;

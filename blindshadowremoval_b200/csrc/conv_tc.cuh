@@ -37,11 +37,6 @@
 
 // Role timers (tools/role_timers.py) are compiled in only with -DBSR_ROLE_TIMERS: the clock reads sit on the
 // single-thread producer / MMA critical paths.
-#ifdef BSR_ROLE_TIMERS
-#define BSR_CLK() clock64()
-#else
-#define BSR_CLK() 0ll
-#endif
 
 namespace bsr {
 

@@ -10,6 +10,13 @@
 
 #include "common.cuh"
 
+// cycle counter of the role timers: compiled in only with -DBSR_ROLE_TIMERS (make timers)
+#ifdef BSR_ROLE_TIMERS
+#define BSR_CLK() clock64()
+#else
+#define BSR_CLK() 0ll
+#endif
+
 namespace bsr {
 
 #ifdef BSR_ACT_BF16
