@@ -782,10 +782,13 @@ int forward_host(bsr_handle* h, const float* img, const float* uv, const float* 
   DeviceScope dev_scope(h->device);
   if (!dev_scope.ok) return fail(h, BSR_ECUDA, "cudaSetDevice(%d) failed", h->device);
   // transfer/compute chunk of the pipelined host path: smaller than the device micro-batch so that PCIe copies and
-  // kernels of neighbouring chunks overlap well (measured optimum ~64 images; BSR_HOST_CHUNK overrides)
-  // measured: fp32 I/O, 256 images/call: 64 -> 17.2k img/s, 128 -> 13.8k; 1024 images/call: 64 -> 18.7k, 128 -> 19.4k;
-  // compact I/O (transfers 5x smaller, head/tail cheap): 256/call: 64 -> 17.9k, 128 -> 18.6k; 1024/call: 128 -> 19.9k
-  int host_chunk = (compact || n >= 512) ? 128 : 64;
+  // kernels of neighbouring chunks overlap (BSR_HOST_CHUNK overrides).
+  // chunk = a multiple of num_sms / 4 images (37 on a B200): attention has 4 work items and res conv2 4 regions per image, the
+  // 1x1 convs 8 tiles, so such chunks fill every round of their persistent grids exactly.  Measured on one B200, 256 images
+  // per call (images/s, fp32 | compact I/O): 37 -> 24.8 k | 24.9 k, 64 -> 25.1 k | 26.7 k, 74 -> 26.4 k | 28.0 k,
+  // 111 -> 21.9 k | 29.2 k, 128 -> 20.2 k | 27.5 k (fp32 transfers are 5x larger: long first / last copies cost more)
+  const int q = h->num_sms >= 8 ? h->num_sms / 4 : 32;
+  int host_chunk = (compact || n >= 512) ? 3 * q : 2 * q;
   if (h->kn.host_chunk > 0) host_chunk = h->kn.host_chunk;
   if (host_chunk > h->host_step_cap) host_chunk = h->host_step_cap;
   int step = h->mb < host_chunk ? h->mb : host_chunk;
