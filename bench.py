@@ -455,6 +455,7 @@ def main():
                     acc.setdefault(name, []).append(ms)
         work = layer_work(args.variant)
         rows = []
+        net_target_s = 0.0      # sum over the layers of max(FLOPs / tensor peak, bytes / HBM peak), per image
         # res blocks: the profiler names attention/res_tail/share generically -> aggregate by name
         for name, v in acc.items():
             per_call = sum(v) / len(v)
@@ -465,6 +466,7 @@ def main():
                 fa, ba = work["res1.attention"]
                 fw, bw = work["res1.w"]
                 fl, by = fa + fw, ba + bw - 2 * 1024 * 128 * 2
+            net_target_s += calls * max(fl / (peaks["bf16_tflops_sustained"] * 1e12), by / (peaks["hbm_gbs"] * 1e9))
             t_s = per_call * 1e-3
             tf = fl * mb / t_s / 1e12 if t_s > 0 else 0.0
             gb = by * mb / t_s / 1e9 if t_s > 0 else 0.0
@@ -498,6 +500,9 @@ def main():
                 "algorithmic_bytes_per_image": unit_work[1], "algorithmic_flops_per_image": unit_work[0],
                 "ms_per_launch": top["ms_per_launch"],
                 "network": {"ms_per_forward_profiled": round(total_ms, 4),
+                            # whole network against the sum of its per-layer rooflines, on the timed steps
+                            "roofline_target_us_per_image": round(net_target_s * 1e6, 3),
+                            "frac": round(net_target_s * B / (ms_step / 1e3), 4),
                             "tflops_effective": round(GSC_GFLOP_PER_IMAGE * 1e9 * B * world / (ms_step / 1e3) / 1e12, 1)
                             if args.variant == "gsc" else None}}
         table = rows
