@@ -18,7 +18,6 @@
 #include "../../include/bsr.h"
 #include "attention_simple.cuh"
 #include "attention_fa.cuh"
-#include "attention_tc.cuh"
 #include "common.cuh"
 #include "conv_direct.cuh"
 #include "conv_tc.cuh"
@@ -124,7 +123,7 @@ int configure_tc_kernels() {
   if (int r = configure_tc_kernels_attn_fa()) return r;
   if (!configure_conv3x3_halo()) return -9;
   if (!configure_convt_halo()) return -10;
-  return configure_tc_kernels_attn();
+  return 0;
 }
 
 int fail(bsr_handle* h, int code, const char* fmt, ...) {
@@ -143,7 +142,6 @@ int fail(bsr_handle* h, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(h, BSR_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-inline int pad8(int c) { return (c + 7) / 8 * 8; }
 inline int pad16(int c) { return (c + 15) / 16 * 16; }
 constexpr int kLdY = 272;      // 257 res-block channels padded to a multiple of 16: every epilogue chunk is a full vector chunk
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -320,7 +318,7 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
     h->launches++;
     return BSR_OK;
   }
-  if (!h->force_direct && !h->kn.attn_v1) {
+  if (!h->force_direct) {
     // single-pass kernel (attention_fa.cuh): O = softmax(QK^T) V, or with `wl` the whole rest of the block:
     // out = LeakyReLU(x_in + y + W_w . O + b)
     EpiParams e2;
@@ -332,16 +330,7 @@ int run_attention(bsr_handle* h, cudaStream_t st, int n, const Layer* wl = nullp
     h->pc.attn_fused += wl != nullptr;
     return BSR_OK;
   }
-  if (!h->force_direct) {
-    EpiParams e2;
-    if (wl) { e2 = *ew; e2.bias = wl->b_dev; e2.cout = wl->cout; }
-    int rc = launch_attention_tc(h->tma, (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, n, h->errflag, st, h->kn,
-                                 wl ? &wl->tc.map : nullptr, wl ? &e2 : nullptr, h->launches);
-    if (rc != 0) return fail(h, BSR_ECUDA, "tensor-core attention launch failed (%d): %s", rc, h->tma.last_error.c_str());
-    h->launches++;
-    h->pc.attn_fused += wl != nullptr;
-    return BSR_OK;
-  }
+  // BSR_FORCE_DIRECT=1 (bring-up): CUDA-core attention on V^T
   attention_simple_kernel<h16><<<dim3(AS_S / AS_Q, n), 256, kAttnSimpleSmem, st>>>(
       (const h16*)h->QK, (const h16*)h->VT, (h16*)h->O, 128);
   h->launches++;
@@ -369,8 +358,8 @@ int run_res_block(bsr_handle* h, cudaStream_t st, int idx, char* cur, char* nxt,
   eq.out2 = h->VT;
   eq.spatial = FEAT * FEAT;
   // g leaves the projection conv untransposed ([pix][128]) for the single-pass attention kernel (MN-major B operand of
-  // its P V MMA); the round-1 kernel and the fp32 check kernels read V^T
-  const bool v_natural = h->precision != BSR_PRECISION_FP32CHECK && !h->force_direct && !h->kn.attn_v1;
+  // its P V MMA); the fp32 check kernels read V^T
+  const bool v_natural = h->precision != BSR_PRECISION_FP32CHECK && !h->force_direct;
   eq.v_natural = v_natural ? 1 : 0;
   ConvCall c4{nm[3], h->Y, ldy, 0, false, FEAT, FEAT, 1, eq, no_extra()};
   if ((rc = run_conv(h, st, c4, n))) return rc;
@@ -995,7 +984,6 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.host_chunk = env_int("BSR_HOST_CHUNK");
   h->kn.no_graph = env_set("BSR_NO_GRAPH");
   h->kn.host_full_uv = env_set("BSR_HOST_FULL_UV");
-  h->kn.attn_v1 = env_int("BSR_ATTN_V1");
   h->kn.no_halo = env_set("BSR_NO_HALO");
   h->kn.no_halo3 = env_set("BSR_NO_HALO3");
   h->kn.share_v1 = env_set("BSR_SHARE_V1");

@@ -123,7 +123,6 @@ struct Knobs {
   int no_hole_inplace = 0; // BSR_NO_HOLE_INPLACE: the hole mask copies into the other buffer even when the strides agree
   int share_v1 = 0;        // BSR_SHARE_V1: warp-per-cell ShareLayer kernels on the 16-bit path too (A/B measurements)
   int no_halo3 = 0;        // BSR_NO_HALO3: res conv2 on the generic kernel (nine shifted A tiles) instead of conv3x3_halo.cuh
-  int attn_v1 = 0;         // BSR_ATTN_V1=1: round-1 two-pass attention kernel with the fused output conv (A/B measurements)
 };
 // Launch-plan counters of one forward (bsr_plan_counter).
 struct PlanCounters { int resident = 0, pinned = 0, staged = 0, attn_fused = 0, graph_replays = 0, halo3 = 0; };

@@ -24,7 +24,6 @@ torch.cuda.synchronize()
 lt = gen.layer_times()
 t = gen.debug_read("timers").reshape(64, 16)
 names = dict(enumerate(LAUNCHES))           # launch index inside one forward (h->launches at launch time)
-ATT = {i for i, nm in names.items() if nm.endswith("attn+w")}
 print("launch  name       | producer: total wait_empty dep_wait steps | mma: total wait_full wait_tempty wait_res tiles | epi: total wait_tfull tiles")
 for i in range(64):
     if t[i, 0] == 0 and t[i, 4] == 0:
@@ -33,10 +32,6 @@ for i in range(64):
         it = max(t[i, 8], 1)
         print("%3d attn+w (fa) | softmax warp: total %d = %d items; per item: main loop %d (waiting for S %d) | O->smem %d | wait D2 %d | tail %d (waiting for residuals %d, staging barrier %d)" % (
             i, t[i, 0], t[i, 8], t[i, 1] / it, t[i, 2] / it, t[i, 3] / it, t[i, 4] / it, t[i, 5] / it, t[i, 6] / it, t[i, 7] / it))
-        continue
-    if i in ATT:
-        print("%3d attn+w | mma: total %d (main %d) wait k %d s_empty %d p_full %d v_full %d w+a2 %d | softmax: passes %d wait s(p1) %d s(p2) %d p_empty %d o_full %d | O->smem %d d2 wait %d epilogue2 %d" % (
-            i, t[i, 0], t[i, 6], t[i, 1], t[i, 2], t[i, 3], t[i, 4], t[i, 5], t[i, 8], t[i, 9], t[i, 10], t[i, 11], t[i, 12], t[i, 13], t[i, 14], t[i, 15]))
         continue
     print("%3d %-10s | %9d %9d %8d %5d | %9d %9d %9d %8d %4d | %9d %9d %4d" % (
         i, names.get(i, ""), t[i, 0], t[i, 1], t[i, 2], t[i, 3], t[i, 4], t[i, 5], t[i, 6], t[i, 7], t[i, 8], t[i, 9],
