@@ -559,8 +559,12 @@ int forward_mb(bsr_handle* h, cudaStream_t st, const float* img, const float* uv
     int cells = (int)px32;
     // same channel stride in both halves (GSC): the mask is applied in place and the 257 feature channels are not copied
     const bool inplace = ld1 == ld2 && !h->kn.no_hole_inplace;
-    hole_kernel<T><<<(cells + 3) / 4, 128, 0, st>>>(h->DIFGS, (const T*)cur, ld1, (T*)(inplace ? cur : nxt), ld2, cx, h->UVS,
-                                                    uv_off, uv_off + 3, ld2, h->BMASK, h->DIFSMALL, cells);
+    if (inplace && std::is_same<T, h16>::value && ld2 % 8 == 0)
+      hole_inplace_h16_kernel<<<(cells + 255) / 256, 256, 0, st>>>(h->DIFGS, (h16*)cur, ld2, cx, h->UVS, uv_off, uv_off + 3, ld2,
+                                                                   h->BMASK, h->DIFSMALL, cells);
+    else
+      hole_kernel<T><<<(cells + 3) / 4, 128, 0, st>>>(h->DIFGS, (const T*)cur, ld1, (T*)(inplace ? cur : nxt), ld2, cx, h->UVS,
+                                                      uv_off, uv_off + 3, ld2, h->BMASK, h->DIFSMALL, cells);
     h->launches++;
     // otherwise the hole kernel wrote into `nxt` viewed with ld2; from here on (cur, nxt) = (that buffer, the other)
     if (!inplace) std::swap(cur, nxt);

@@ -256,6 +256,39 @@ __global__ void hole_kernel(const float* __restrict__ difgs, const T* xa, int ld
   for (int c = z0 + lane; c < z1; c += 32) stf<T>(dst, c, 0.f);
 }
 
+// In-place form of hole_kernel for 16-bit storage (GSC: both halves of the network share the channel stride): one THREAD
+// per cell takes the four resize taps and writes the cell's few side values; the warp then clears the cx feature channels
+// of its masked cells together (16 bytes per lane), kept cells are not touched.  Needs ld % 8 == 0.
+__global__ void __launch_bounds__(256) hole_inplace_h16_kernel(const float* __restrict__ difgs, h16* __restrict__ xb, int ld, int cx,
+                                                               const float* __restrict__ uvs, int uv_off, int z0, int z1,
+                                                               float* __restrict__ bmask_out, float* __restrict__ difsmall_out,
+                                                               int n_cells) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const bool live = cell < n_cells;
+  bool masked = false;
+  if (live) {
+    const int j = cell % FEAT, i = (cell / FEAT) % FEAT, n = cell / (FEAT * FEAT);
+    const float d = resize8(difgs, n, i, j, 1, 0);
+    masked = d > kHoleThr;
+    h16* dst = xb + (size_t)cell * ld;
+    dst[cx] = f32_to_h16(masked ? 1.f : 0.f);
+    bmask_out[cell] = masked ? 1.f : 0.f;
+    difsmall_out[cell] = d;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst[uv_off + k] = f32_to_h16(uvs[(size_t)cell * 3 + k]);
+    for (int c = z0; c < z1; ++c) dst[c] = f32_to_h16(0.f);
+  }
+  unsigned m = __ballot_sync(0xffffffffu, masked);
+  const int cell0 = cell - lane, c_vec = cx & ~7;
+  while (m) {
+    const int src_lane = __ffs(m) - 1;
+    m &= m - 1;
+    h16* dst = xb + (size_t)(cell0 + src_lane) * ld;
+    for (int c = lane * 8; c < c_vec; c += 256) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < cx - c_vec) dst[c_vec + lane] = f32_to_h16(0.f);
+  }
+}
+
 // ---- ShareLayer (model_with_TSM.py:204-229) ---------------------------------------------------
 // tf_batch_map_coordinates (warp.py:71-115): clip coords to [0, s-1], corners floor/ceil,
 // v_t = lt + (rt-lt)*o0 ; v_b = lb + (rb-lb)*o0 ; out = v_t + (v_b-v_t)*o1, with coordinate 0 = row.
