@@ -453,6 +453,30 @@ def test_benchmark_configuration_gsc_256_images_mb128_matches_oracle(G):
     gen.close()
 
 
+def test_benchmark_configuration_gsc_256_images_mb256_matches_oracle(G):
+    """BASELINE config 4 as bench.py's default runs it since the attention kernel became persistent over 1024 work items:
+    n = 256 in ONE micro-batch of 256.  16 sampled images against the oracle, the large-batch launch plan, and the host path
+    (chunks of 74 = 2 x num_sms / 4 images: 74 + 74 + 74 + 34, or the ramped form) bit for bit equal to the device path."""
+    w, _ = case("gsc", 2, 1)
+    d = make_inputs(256, seed=22, with_reg=True)
+    gen = G.Generator("gsc", "tc16", device=0, micro_batch=256, weights=w)
+    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    out = gen(t["img"], t["uv"], None)
+    gen.check()
+    pc = gen.plan_counters()
+    assert pc["pinned"] >= 6 and pc["resident"] >= 6 and pc["staged"] >= 2 and pc["attn_fused"] == 6 and pc["halo3"] == 10, pc
+    assert gen.launch_count() == 46
+    got = dict(zip(("gs", "con_rgb", "mask22", "dif"), (o.cpu().numpy() for o in out)))
+    bm = gen.debug_read("bmask").reshape(256, 32, 32, 1)
+    idx = np.arange(5, 256, 16)                                          # 16 images
+    worst, flips = _check_against_oracle("gsc", w, d, 1, got, bm, idx)
+    print("gsc n=256 mb=256: worst", worst, "flip rate", flips)
+    hg, hrgb, hm, hdif = gen(d["img"], d["uv"], None)
+    assert np.array_equal(hrgb, got["con_rgb"]) and np.array_equal(hdif, got["dif"]) and np.array_equal(hg, got["gs"])
+    assert np.array_equal(hm, got["mask22"])
+    gen.close()
+
+
 @pytest.mark.parametrize("frame,n", [(2, 256), (10, 240)])
 def test_benchmark_configuration_tsm_mb128_matches_oracle(G, frame, n):
     """The TSM variant at micro-batch 128 (frame 2: 64 chunks per micro-batch; frame 10: 12 chunks = 120 images per
