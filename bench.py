@@ -190,7 +190,7 @@ def workload_config(args):
                         "random-init weights seed 1234" % (args.variant.upper(), args.batch, args.micro_batch),
             "variant": args.variant, "images_per_gpu_per_step": args.batch, "micro_batch": args.micro_batch,
             "frame": args.frame if args.variant == "tsm" else None,
-            "host_path_chunk": 64,
+            "host_path_chunk": os.environ.get("BSR_HOST_CHUNK") or "2 x (num_sms / 4) images for fp32 I/O, 3 x for compact I/O (74 / 111 on a B200)",
             "cache": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" %
                      (args.batch * 256 * 256 * 6 * 4 / 1e6)}
 
