@@ -990,6 +990,7 @@ int bsr_create(int variant, int precision, int device, int micro_batch, bsr_hand
   h->kn.host_full_uv = env_set("BSR_HOST_FULL_UV");
   h->kn.no_halo = env_set("BSR_NO_HALO");
   h->kn.no_halo3 = env_set("BSR_NO_HALO3");
+  h->kn.unpack_v1 = env_set("BSR_UNPACK_V1");
   h->kn.share_v1 = env_set("BSR_SHARE_V1");
   h->kn.no_hole_inplace = env_set("BSR_NO_HOLE_INPLACE");
   h->c_first = variant == BSR_VARIANT_GSC ? 99 : 291;
@@ -1283,8 +1284,12 @@ int bsr_forward_chunk(bsr_handle* h, const float* chunk, int n, int layout, int 
   for (int i0 = 0; i0 < n; i0 += step) {
     const int m = n - i0 < step ? n - i0 : step;
     const long long mpx = (long long)m * px;
-    unpack_chunk_kernel<<<(unsigned)((mpx * 13 + 255) / 256), 256, 0, st>>>(chunk + (size_t)i0 * px * C, C, o_uv, o_reg, o_face,
-                                                                        d_img, d_uv, tsm ? d_reg : nullptr, d_face, mpx);
+    if (h->kn.unpack_v1)
+      unpack_chunk_kernel<<<(unsigned)((mpx * 13 + 255) / 256), 256, 0, st>>>(chunk + (size_t)i0 * px * C, C, o_uv, o_reg, o_face,
+                                                                          d_img, d_uv, tsm ? d_reg : nullptr, d_face, mpx);
+    else
+      unpack_chunk_tile_kernel<<<(unsigned)((mpx + 255) / 256), 256, (size_t)256 * (C | 1) * sizeof(float), st>>>(
+          chunk + (size_t)i0 * px * C, C, o_uv, o_reg, o_face, d_img, d_uv, tsm ? d_reg : nullptr, d_face, mpx);
     float* rgb_o = rgb_clipped + (size_t)i0 * px * 3;
     float* mp_o = mask_pred + (size_t)i0 * px;
     int rc = forward_common(h, d_img, d_uv, tsm ? d_reg : nullptr, m, frame, share, gs ? gs + (size_t)i0 * px : nullptr, rgb_o,

@@ -122,6 +122,7 @@ struct Knobs {
   int no_halo = 0;         // BSR_NO_HALO: fused transposed convs fetch every shifted A tile separately (round-1 behaviour)
   int no_hole_inplace = 0; // BSR_NO_HOLE_INPLACE: the hole mask copies into the other buffer even when the strides agree
   int share_v1 = 0;        // BSR_SHARE_V1: warp-per-cell ShareLayer kernels on the 16-bit path too (A/B measurements)
+  int unpack_v1 = 0;       // BSR_UNPACK_V1: per-thread chunk split instead of the shared-memory tile form (A/B measurements)
   int no_halo3 = 0;        // BSR_NO_HALO3: res conv2 on the generic kernel (nine shifted A tiles) instead of conv3x3_halo.cuh
 };
 // Launch-plan counters of one forward (bsr_plan_counter).
