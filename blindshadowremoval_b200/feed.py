@@ -97,6 +97,25 @@ def _pool_centres(v64: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(top * h + bot * h)
 
 
+_LOCATED: Dict[tuple, "TriInterpolator"] = {}
+
+
+def _located(points: np.ndarray, grid: str) -> "TriInterpolator":
+    """Triangulation of `points` with every pixel of the 256 x 256 grid ('full') or of the cell-centre grid ('centres')
+    already located.  The un-warp field of every frame interpolates over the SAME point set - the template landmarks plus
+    the 16 border anchors (dataset.py:635) - so its Delaunay triangulation, point location and barycentric weights are
+    computed once per process instead of once per frame; other point sets (the frame's own landmarks) are not cached."""
+    key = (grid, points.shape, points.dtype.str, points.tobytes())
+    it = _LOCATED.get(key)
+    if it is None:
+        it = TriInterpolator(points)
+        it.locate(*(_grid(IMG) if grid == "full" else _cell_centre_grid()))
+        if len(_LOCATED) >= 8:
+            _LOCATED.clear()
+        _LOCATED[key] = it
+    return it
+
+
 def _uv_values(uv: np.ndarray) -> np.ndarray:
     return np.stack([uv[:, 1], uv[:, 0], uv[:, 2]], axis=1)       # stack([_offsetmapy, _offsetmapx, _offsetmapz]), warp.py:230
 
@@ -114,10 +133,20 @@ def generate_offset_map(source: np.ndarray, target: np.ndarray, img_size: int = 
     src = np.concatenate([np.asarray(source, np.float64), _ANCHORS], axis=0).astype(np.float32)
     tgt = np.concatenate([np.asarray(target, np.float64), _ANCHORS], axis=0).astype(np.float32)
     off = (src - tgt).astype(np.float64)
-    it = TriInterpolator(tgt)
-    it.locate(*_grid(img_size))
+    if img_size == IMG and _is_template(target):
+        it = _located(tgt, "full")
+    else:
+        it = TriInterpolator(tgt)
+        it.locate(*_grid(img_size))
     m = it(np.stack([off[:, 1], off[:, 0]], axis=1))
     return np.concatenate([m, m[..., 1:2] * 0], axis=2)
+
+
+def _is_template(points: np.ndarray) -> bool:
+    """True for the (constant) template landmarks: only those are worth caching."""
+    ref = face_template()[1]
+    p = np.asarray(points)
+    return p.shape == ref.shape and np.array_equal(p.astype(np.float32), ref)
 
 
 def _hull_points(source: np.ndarray) -> np.ndarray:
@@ -171,8 +200,11 @@ def frame_maps_compact(lm: np.ndarray, uv: Optional[np.ndarray] = None, lm_ref: 
         src = np.concatenate([np.asarray(source, np.float64), _ANCHORS], axis=0).astype(np.float32)
         tgt = np.concatenate([np.asarray(target, np.float64), _ANCHORS], axis=0).astype(np.float32)
         off = (src - tgt).astype(np.float64)
-        io = TriInterpolator(tgt)
-        io.locate(xq, yq)
+        if _is_template(target):
+            io = _located(tgt, "centres")
+        else:
+            io = TriInterpolator(tgt)
+            io.locate(xq, yq)
         m = io(np.stack([off[:, 1], off[:, 0]], axis=1))
         regs.append(np.concatenate([m, m[..., 1:2] * 0], axis=2))
     out = {"uv32": _pool_centres(uv64), "reg32": _pool_centres(np.concatenate(regs, axis=2))}
